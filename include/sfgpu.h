@@ -1,0 +1,193 @@
+/*
+ * sfgpu.h -- C ABI of libstarfish_gpu.so: the B200 (sm_100a) replacement for the kinetic
+ * particle hot path of particleincell/Starfish.
+ *
+ * The reference has no native boundary: the path lives behind the Java plugin API
+ * (MaterialsModule.registerMaterialType, MaterialsModule.java:91-95; a KineticMaterial subclass
+ * overriding updateFields(), KineticMaterial.java:117 -- the GrainMaterial precedent,
+ * plugins/surface_processing/GrainMaterial.java:14-24).  Each entry point below names the Java
+ * member(s) it replaces ("KM" = src/starfish/core/materials/KineticMaterial.java,
+ * "F2D" = core/domain/Field2D.java, "MESH" = core/domain/Mesh.java, "UM" = UniformMesh.java).
+ * INTEGRATION.md shows the JNI / FFM binding a Starfish maintainer adds on the Java side.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative SFGPU_E* code otherwise; the message is
+ *    available from sfgpu_last_error(); nothing throws across the ABI;
+ *  - all pointers are caller-owned HOST memory valid for the duration of the call, the library
+ *    owns all device memory; "nullable" arguments may be NULL;
+ *  - fields are Java double[ni][nj] flattened row by row: index i*nj + j;
+ *  - one caller thread per context (Starfish's main loop is single threaded, Starfish.java:77-121);
+ *  - there is no CPU fallback: without a CUDA device sfgpu_create fails.
+ */
+#ifndef SFGPU_H
+#define SFGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFGPU_ABI_VERSION 1
+
+/* error codes */
+#define SFGPU_OK 0
+#define SFGPU_EINVAL (-1)   /* bad argument                               */
+#define SFGPU_ECUDA (-2)    /* CUDA runtime / launch failure               */
+#define SFGPU_ENOMEM (-3)   /* device or host allocation failed            */
+#define SFGPU_ENCCL (-4)    /* NCCL missing or failed                      */
+#define SFGPU_EOVERFLOW (-5)/* an internal list overflowed (hand-off/slow) */
+#define SFGPU_ESTATE (-6)   /* call not valid in the current state         */
+
+/* DomainModule.DomainType, DomainModule.java:28 */
+#define SFGPU_XY 0
+#define SFGPU_RZ 1
+#define SFGPU_ZR 2
+
+/* Mesh.Face.val(), MESH:107-118: order of every [4] face array below */
+#define SFGPU_FACE_RIGHT 0
+#define SFGPU_FACE_TOP 1
+#define SFGPU_FACE_LEFT 2
+#define SFGPU_FACE_BOTTOM 3
+
+/* Mesh.DomainBoundaryType.value(), MESH:140-155 */
+#define SFGPU_BC_OPEN (-1)
+#define SFGPU_BC_DIRICHLET 0
+#define SFGPU_BC_NEUMANN 1
+#define SFGPU_BC_PERIODIC 2
+#define SFGPU_BC_SYMMETRY 3
+#define SFGPU_BC_MESH 4
+#define SFGPU_BC_SINK 5
+#define SFGPU_BC_CIRCUIT 6
+
+/* sfgpu_inject flags */
+#define SFGPU_INJECT_REWIND 1u      /* apply the -0.5*dt velocity rewind of addParticle, KM:776-794 */
+#define SFGPU_INJECT_DEPOSIT_NOW 2u /* particle was already moved this step (slow-path survivor):
+                                       add it to this step's deposit, move it from the next step on */
+#define SFGPU_INJECT_TRANSFER 4u    /* particle enters a mesh's transfer list (KM:1377-1380): it is
+                                       moved by the transfer sweeps of the next sfgpu_step          */
+
+/* sfgpu_step flags */
+#define SFGPU_STEP_GENERIC 1u  /* force the generic (untiled, global-atomic) kernels            */
+#define SFGPU_STEP_DEFER_FINISH 2u /* do not close the step: the host still has slow-path survivors to
+                                      re-inject (SFGPU_INJECT_DEPOSIT_NOW); it calls sfgpu_finish_step */
+
+/* index of each raw per-step deposit field inside the packed device buffer / sfgpu_get_deposit */
+#define SFGPU_F_DEN 0 /* += mpw            KM:184, KM:1590 */
+#define SFGPU_F_U 1   /* += mpw*vel[0]     KM:185, KM:1584 */
+#define SFGPU_F_V 2   /* += mpw*vel[1]     KM:186, KM:1585 */
+#define SFGPU_F_W 3   /* += mpw*vel[2]     KM:187, KM:1586 */
+#define SFGPU_F_UU 4  /* += mpw*vel[0]^2   KM:1587         */
+#define SFGPU_F_VV 5  /* += mpw*vel[1]^2   KM:1588         */
+#define SFGPU_F_WW 6  /* += mpw*vel[2]^2   KM:1589         */
+#define SFGPU_F_MPC 7 /* += 1 per particle in cell ((int)lc0,(int)lc1), KM:1593 */
+#define SFGPU_NFIELDS 8
+
+typedef struct sfgpu_ctx sfgpu_ctx;
+
+/* SoA view of particles on the host, used by inject / download / take_slowpath.
+ * Mirrors KineticMaterial.Particle, KM:1207-1217.  All arrays have n entries. */
+typedef struct sfgpu_particles {
+    int64_t n;
+    double *x, *y, *z;     /* pos[0..2]                                   */
+    double *u, *v, *w;     /* vel[0..2]                                   */
+    double *mpw;           /* macroparticle weight                        */
+    double *li, *lj;       /* lc[0..1]; nullable on inject => XtoL(pos) with the plus-edge clamp KM:762-773 */
+    double *dt;            /* remaining dt; nullable on inject => 0       */
+    int32_t *id;           /* nullable on inject => part_id_counter++ (KM:797) */
+    int32_t *born_it;      /* nullable on inject => 0                     */
+} sfgpu_particles;
+
+/* pre-substep state handed back with slow-path particles: the arguments of
+ * ProcessBoundary(part, mesh, old, lc_old), KM:471 */
+typedef struct sfgpu_slow_extra {
+    double *old_x, *old_y;   /* old[0..1]              */
+    double *old_li, *old_lj; /* lc_old[0..1]           */
+    int32_t *bounces;        /* substeps already taken */
+    int32_t *mesh;           /* mesh the particle is in */
+} sfgpu_slow_extra;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int sfgpu_abi_version(void);
+/* device: CUDA ordinal; domain_type: SFGPU_XY/RZ/ZR (Starfish.getDomainType()) */
+int sfgpu_create(int device, int domain_type, sfgpu_ctx **out);
+void sfgpu_destroy(sfgpu_ctx *ctx);
+/* ctx may be NULL: returns the last error of the calling thread's most recent failing call */
+const char *sfgpu_last_error(sfgpu_ctx *ctx);
+
+/* ---- mesh and fields (replaces the reads of UniformMesh / Mesh state on the path) ------- */
+/* UM:33-43 geometry; bc[f]: DomainBoundaryType per node of face f (MESH:215), nj entries for
+ * RIGHT/LEFT, ni for TOP/BOTTOM; nbr[f] (nullable): 2 neighbour mesh ids per node or -1
+ * (MeshBoundaryData.neighbor, MESH:160-165); has_seg (nullable): 1 where node[i][j].segments holds
+ * a DIRICHLET or SINK segment (KM:508-518); node_vol (nullable): mesh.node_vol.data (F2D:418-431). */
+int sfgpu_mesh_add(sfgpu_ctx *ctx, int32_t ni, int32_t nj, const double x0[2], const double dh[2],
+                   const int8_t *const bc[4], const int32_t *const nbr[4], const uint8_t *has_seg,
+                   const double *node_vol, int32_t *mesh_id);
+/* efi/efj/bfi/bfj of MeshData, KM:1319-1322; bfi/bfj nullable => zero field */
+int sfgpu_set_fields(sfgpu_ctx *ctx, int32_t mesh_id, const double *efi, const double *efj,
+                     const double *bfi, const double *bfj);
+
+/* ---- species (one KineticMaterial) ------------------------------------------------------ */
+/* q_over_m = charge/mass as Material.java:711 */
+int sfgpu_species_add(sfgpu_ctx *ctx, double charge, double mass, int64_t capacity_hint, int32_t *sp);
+
+/* KineticMaterial.addParticle(MeshData, Particle), KM:759-802 (+ MeshData.addParticle finite-velocity
+ * filter KM:1356-1361).  dt_step is Starfish.getDt() for the rewind.  n_added (nullable) returns how
+ * many were accepted. */
+int sfgpu_inject(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const sfgpu_particles *p, double dt_step,
+                 uint32_t flags, int64_t *n_added);
+
+/* KineticMaterial.updateFields(), KM:117-163: moveParticles(false) + transfer sweeps (KM:126-142),
+ * fused with the deposit of updateFields(MeshData) KM:168-188 and updateSamples KM:1570-1595, then the
+ * cross-GPU sum of the deposit when a communicator is attached. */
+int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags);
+/* closes a step opened with SFGPU_STEP_DEFER_FINISH: cross-GPU sum of the deposit and of the mover sums */
+int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp);
+
+/* raw per-step sums, each ni*nj, any pointer nullable: order SFGPU_F_* */
+int sfgpu_get_deposit(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, double *const out[SFGPU_NFIELDS]);
+/* nd,u,v,w after KM:190-196 (U,V,W /= Den; Den /= node_vol); needs node_vol; any nullable */
+int sfgpu_get_moments(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, double *nd, double *u, double *v,
+                      double *w);
+/* sums5 = {N, Px, Py, Pz, E} of KM:406-413 (not yet multiplied by mass, KM:252-258), summed over ranks
+ * when a communicator is attached; counts are local to this context */
+int sfgpu_get_sums(sfgpu_ctx *ctx, int32_t sp, double sums5[5], int64_t *np_alive, int64_t *n_exited,
+                   int64_t *n_slow);
+/* MeshData.getNp(), KM:1385-1390 (mesh_id <0: KineticMaterial.getNp(), KM:1297) */
+int sfgpu_np(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t *np);
+
+/* particles that need the unchanged Java ProcessBoundary (KM:471-750): a DIRICHLET/SINK segment lies in
+ * the node bounding box of their substep, or a CIRCUIT face was hit by an electron.  They are handed over
+ * in their pre-ProcessBoundary state and removed from the device store; survivors come back through
+ * sfgpu_inject(.., SFGPU_INJECT_DEPOSIT_NOW).  *n returns the number copied (<= max). */
+int sfgpu_take_slowpath(sfgpu_ctx *ctx, int32_t sp, int64_t max, sfgpu_particles *out, sfgpu_slow_extra *extra,
+                        int64_t *n);
+
+/* iterators / output / restart / collisions (KM:271, :1187, :904-1000): copy particles [first, first+n)
+ * of a mesh's store to the host, or overwrite them after a host-side mutation */
+int sfgpu_download(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t first, sfgpu_particles *out);
+int sfgpu_upload(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t first, const sfgpu_particles *in);
+
+/* explicit cell sort + compaction (sortParticlesToCells, KM:1150-1179: order only, no result change) */
+int sfgpu_sort(sfgpu_ctx *ctx, int32_t sp);
+
+/* ---- multi GPU: particles are partitioned over contexts, meshes replicated ------------- */
+/* 128-byte NCCL unique id, created on one rank and distributed by the host */
+int sfgpu_comm_unique_id(void *id128);
+int sfgpu_comm_init(sfgpu_ctx *ctx, int32_t nranks, int32_t rank, const void *id128);
+/* device pointer + element count of the packed [SFGPU_NFIELDS][ni][nj] deposit buffer, for hosts that
+ * run their own collective */
+int sfgpu_deposit_device_ptr(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, void **ptr, int64_t *count);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* device milliseconds of the last step, from CUDA events on the context's own stream: ms_total spans the
+ * whole step (memsets, kernels, collective), ms_kernel only the fused move+deposit kernel(s) of the main
+ * pass; launches = kernels launched by the step.  Any pointer nullable. */
+int sfgpu_last_step_timing(sfgpu_ctx *ctx, float *ms_total, float *ms_kernel, int32_t *launches);
+/* cudaStreamSynchronize on the context's stream */
+int sfgpu_sync(sfgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFGPU_H */

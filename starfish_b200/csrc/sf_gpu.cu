@@ -1,0 +1,991 @@
+// sf_gpu.cu -- libstarfish_gpu.so: context management and the C ABI of include/sfgpu.h.
+// Build: see starfish_b200/csrc/Makefile (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo).
+// There is no CPU fallback anywhere in this file: without a CUDA device sfgpu_create() fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sfgpu.h"
+#include "sf_generic.cuh"
+#include "sf_store.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+struct sfgpu_ctx;
+static int fail(sfgpu_ctx *ctx, int code, const char *fmt, ...);
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? SFGPU_ENOMEM : SFGPU_ECUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen: no link-time dependency, and a host process that already carries an NCCL
+// (torch's bundled one) shares it instead of loading a second copy.
+// ---------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } sf_ncclUniqueId;
+typedef void *sf_ncclComm_t;
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(sf_ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(sf_ncclComm_t *, int, sf_ncclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, sf_ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(sf_ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static NcclApi g_nccl;
+static const int SF_NCCL_FLOAT64 = 8, SF_NCCL_SUM = 0; // nccl.h: ncclFloat64 = 8, ncclSum = 0
+
+static bool nccl_load(std::string &why)
+{
+    if (g_nccl.ok) return true;
+    const char *names[] = {getenv("SFGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) {
+        why = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?");
+        return false;
+    }
+    g_nccl.GetUniqueId = (int (*)(sf_ncclUniqueId *))dlsym(g_nccl.handle, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(sf_ncclComm_t *, int, sf_ncclUniqueId, int))dlsym(g_nccl.handle, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, sf_ncclComm_t, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(sf_ncclComm_t))dlsym(g_nccl.handle, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        why = "libnccl lacks a required symbol";
+        return false;
+    }
+    g_nccl.ok = true;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side containers
+// ---------------------------------------------------------------------------------------------
+struct Records { // growable SoA slab of full particle records on the device
+    RecPtrs p{};
+    char *slab = nullptr;
+    int64_t cap = 0, n = 0;
+};
+
+static void rec_bind(Records &r, char *slab, int64_t cap)
+{
+    double **arr[SF_REC_NDOUBLES] = {&r.p.x, &r.p.y, &r.p.z, &r.p.u, &r.p.v, &r.p.w, &r.p.mpw, &r.p.li, &r.p.lj, &r.p.dt};
+    for (int k = 0; k < SF_REC_NDOUBLES; k++) *arr[k] = (double *)(slab + (size_t)k * cap * sizeof(double));
+    r.p.tag = (int2 *)(slab + (size_t)SF_REC_NDOUBLES * cap * sizeof(double));
+    r.slab = slab;
+    r.cap = cap;
+}
+
+struct MeshHost {
+    MeshDev dev{}; // device pointers inside
+    int8_t *bc[4] = {nullptr, nullptr, nullptr, nullptr};
+    int *nbr[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *has_seg = nullptr;
+    double *fields = nullptr; // efi, efj, bfi, bfj packed
+    double *node_vol = nullptr;
+    bool needs_slow = false; // segments or a CIRCUIT face present
+};
+
+struct Pop { // one species on one mesh: MeshData, KM:1314-1427
+    Records cur, nxt;  // particle_block lists (this step / next step)
+    Records xin, xout; // transfer_particles (being moved / being filled)
+    double *dep = nullptr; // packed [SFGPU_NFIELDS][ni][nj] raw per-step deposit
+};
+
+struct Species {
+    double charge = 0, mass = 0, qm = 0;
+    int32_t id_counter = 0; // part_id_counter, KM:80
+    std::vector<Pop> pops;  // per mesh
+    Records slow;
+    double *slow_extra_d = nullptr; // old_x, old_y, old_li, old_lj
+    int *slow_extra_i = nullptr;    // bounces, mesh
+    int64_t slow_cap = 0, slow_n = 0;
+    double sums[5] = {0, 0, 0, 0, 0};
+    int64_t n_exited = 0, n_removed = 0;
+    int64_t capacity_hint = 0;
+    bool step_open = false; // sfgpu_step ran, sfgpu_finish_step pending
+};
+
+struct sfgpu_ctx {
+    int device = 0, domain = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    std::vector<MeshHost> meshes;
+    MeshDev *d_meshes = nullptr;
+    bool meshes_dirty = true;
+    std::vector<Species> species;
+    StepCounters *d_cnt = nullptr, *h_cnt = nullptr; // device / pinned host
+    XferDev *d_xfer = nullptr;
+    char *stage = nullptr; // pinned staging
+    size_t stage_bytes = 0;
+    double *d_tmp = nullptr; // moments scratch
+    size_t tmp_bytes = 0;
+    sf_ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    int last_launches = 0;
+    bool timing_valid = false;
+    std::string err;
+};
+
+static int fail(sfgpu_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+static int rec_reserve(sfgpu_ctx *ctx, Records &r, int64_t need, bool keep)
+{
+    if (need <= r.cap) return 0;
+    int64_t cap = r.cap + r.cap / 2;
+    if (cap < need) cap = need;
+    if (cap < 1024) cap = 1024;
+    cap = (cap + 255) & ~int64_t(255); // keeps every array 2 KiB aligned for 128-bit access
+    char *slab = nullptr;
+    const size_t bytes = (size_t)cap * (SF_REC_NDOUBLES * sizeof(double) + sizeof(int2));
+    CU(cudaMalloc(&slab, bytes));
+    Records old = r;
+    rec_bind(r, slab, cap);
+    if (keep && old.n > 0) {
+        const double *src[SF_REC_NDOUBLES] = {old.p.x, old.p.y, old.p.z, old.p.u, old.p.v, old.p.w, old.p.mpw, old.p.li, old.p.lj, old.p.dt};
+        double *dst[SF_REC_NDOUBLES] = {r.p.x, r.p.y, r.p.z, r.p.u, r.p.v, r.p.w, r.p.mpw, r.p.li, r.p.lj, r.p.dt};
+        for (int k = 0; k < SF_REC_NDOUBLES; k++)
+            CU(cudaMemcpyAsync(dst[k], src[k], (size_t)old.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(r.p.tag, old.p.tag, (size_t)old.n * sizeof(int2), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (old.slab) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(old.slab));
+    }
+    return 0;
+}
+
+static void rec_free(Records &r)
+{
+    if (r.slab) cudaFree(r.slab);
+    r = Records();
+}
+
+static int stage_reserve(sfgpu_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->stage_bytes) return 0;
+    if (ctx->stage) CU(cudaFreeHost(ctx->stage));
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+    size_t want = bytes + bytes / 4;
+    CU(cudaMallocHost(&ctx->stage, want));
+    ctx->stage_bytes = want;
+    return 0;
+}
+
+static int sync_meshes(sfgpu_ctx *ctx)
+{
+    if (!ctx->meshes_dirty) return 0;
+    std::vector<MeshDev> h(ctx->meshes.size());
+    for (size_t k = 0; k < h.size(); k++) h[k] = ctx->meshes[k].dev;
+    if (!ctx->d_meshes) CU(cudaMalloc(&ctx->d_meshes, sizeof(MeshDev) * SF_MAX_MESHES));
+    CU(cudaMemcpyAsync(ctx->d_meshes, h.data(), sizeof(MeshDev) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // h goes out of scope
+    ctx->meshes_dirty = false;
+    return 0;
+}
+
+#define CHECK_CTX()                                                        \
+    do {                                                                   \
+        if (!ctx) return fail(nullptr, SFGPU_EINVAL, "null context");      \
+        cudaError_t e0_ = cudaSetDevice(ctx->device);                      \
+        if (e0_ != cudaSuccess) return fail(ctx, SFGPU_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e0_)); \
+    } while (0)
+#define CHECK_SP()                                                                                         \
+    do {                                                                                                   \
+        if (sp < 0 || sp >= (int)ctx->species.size()) return fail(ctx, SFGPU_EINVAL, "bad species id %d", sp); \
+    } while (0)
+#define CHECK_MESH()                                                                                       \
+    do {                                                                                                   \
+        if (mesh_id < 0 || mesh_id >= (int)ctx->meshes.size()) return fail(ctx, SFGPU_EINVAL, "bad mesh id %d", mesh_id); \
+    } while (0)
+
+static inline unsigned grid_for(int64_t n, int block, int max_blocks)
+{
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (unsigned)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfgpu_abi_version(void) { return SFGPU_ABI_VERSION; }
+
+extern "C" const char *sfgpu_last_error(sfgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
+{
+    if (!out) return fail(nullptr, SFGPU_EINVAL, "out is null");
+    *out = nullptr;
+    if (domain_type < SFGPU_XY || domain_type > SFGPU_ZR) return fail(nullptr, SFGPU_EINVAL, "bad domain type %d", domain_type);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SFGPU_ECUDA, "no CUDA device (%s): libstarfish_gpu has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, SFGPU_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    sfgpu_ctx *ctx = new (std::nothrow) sfgpu_ctx();
+    if (!ctx) return fail(nullptr, SFGPU_ENOMEM, "host allocation failed");
+    ctx->device = device;
+    ctx->domain = domain_type;
+    int rc = [&]() -> int {
+        CU(cudaSetDevice(device));
+        CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&ctx->ev0));
+        CU(cudaEventCreate(&ctx->ev1));
+        CU(cudaEventCreate(&ctx->evk0));
+        CU(cudaEventCreate(&ctx->evk1));
+        CU(cudaMalloc(&ctx->d_cnt, sizeof(StepCounters)));
+        CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
+        CU(cudaMallocHost(&ctx->h_cnt, sizeof(StepCounters)));
+        CU(cudaMalloc(&ctx->d_xfer, sizeof(XferDev) * SF_MAX_MESHES));
+        // bit-parity self test: a*b+c must round twice
+        double *d = nullptr, h = 0;
+        CU(cudaMalloc(&d, sizeof(double)));
+        const double a = 1.0 + ldexp(1.0, -30), b = 1.0 - ldexp(1.0, -30), c = -1.0;
+        k_selftest_fmad<<<1, 1, 0, ctx->stream>>>(a, b, c, d);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&h, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(d));
+        if (h != 0.0) // fused: -2^-60; unfused: a*b rounds to 1.0 -> 0
+            return fail(ctx, SFGPU_ESTATE, "library was built with FMA contraction enabled (self test gave %g); rebuild with -fmad=false", h);
+        return 0;
+    }();
+    if (rc) {
+        g_last_error = ctx->err;
+        sfgpu_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    for (auto &s : ctx->species) {
+        for (auto &p : s.pops) {
+            rec_free(p.cur); rec_free(p.nxt); rec_free(p.xin); rec_free(p.xout);
+            if (p.dep) cudaFree(p.dep);
+        }
+        rec_free(s.slow);
+        if (s.slow_extra_d) cudaFree(s.slow_extra_d);
+        if (s.slow_extra_i) cudaFree(s.slow_extra_i);
+    }
+    for (auto &m : ctx->meshes) {
+        for (int f = 0; f < 4; f++) {
+            if (m.bc[f]) cudaFree(m.bc[f]);
+            if (m.nbr[f]) cudaFree(m.nbr[f]);
+        }
+        if (m.has_seg) cudaFree(m.has_seg);
+        if (m.fields) cudaFree(m.fields);
+        if (m.node_vol) cudaFree(m.node_vol);
+    }
+    if (ctx->d_meshes) cudaFree(ctx->d_meshes);
+    if (ctx->d_cnt) cudaFree(ctx->d_cnt);
+    if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
+    if (ctx->d_xfer) cudaFree(ctx->d_xfer);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evk0) cudaEventDestroy(ctx->evk0);
+    if (ctx->evk1) cudaEventDestroy(ctx->evk1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mesh + fields
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfgpu_mesh_add(sfgpu_ctx *ctx, int32_t ni, int32_t nj, const double x0[2], const double dh[2],
+                              const int8_t *const bc[4], const int32_t *const nbr[4], const uint8_t *has_seg,
+                              const double *node_vol, int32_t *mesh_id)
+{
+    CHECK_CTX();
+    if (ni < 2 || nj < 2 || !x0 || !dh || !bc || !mesh_id) return fail(ctx, SFGPU_EINVAL, "sfgpu_mesh_add: bad arguments");
+    if (!(dh[0] > 0) || !(dh[1] > 0)) return fail(ctx, SFGPU_EINVAL, "sfgpu_mesh_add: spacing must be positive");
+    if ((int)ctx->meshes.size() >= SF_MAX_MESHES) return fail(ctx, SFGPU_EINVAL, "at most %d meshes", SF_MAX_MESHES);
+    if (!ctx->species.empty()) return fail(ctx, SFGPU_ESTATE, "add all meshes before the first species");
+    MeshHost m;
+    MeshDev &d = m.dev;
+    d.ni = ni; d.nj = nj; d.domain = ctx->domain;
+    d.x0 = x0[0]; d.y0 = x0[1]; d.dhx = dh[0]; d.dhy = dh[1];
+    // UM:131-135 xd = x0 + (n-1)*dh, KM:700-706 shift by (xd - x0): same two roundings as Java
+    const double xd0 = x0[0] + (ni - 1) * dh[0], xd1 = x0[1] + (nj - 1) * dh[1];
+    d.lenx = xd0 - x0[0];
+    d.leny = xd1 - x0[1];
+    const size_t plane = (size_t)ni * nj;
+    for (int f = 0; f < 4; f++) {
+        const int len = (f == SFGPU_FACE_RIGHT || f == SFGPU_FACE_LEFT) ? nj : ni;
+        if (!bc[f]) return fail(ctx, SFGPU_EINVAL, "sfgpu_mesh_add: bc[%d] is null", f);
+        CU(cudaMalloc(&m.bc[f], len));
+        CU(cudaMemcpy(m.bc[f], bc[f], len, cudaMemcpyHostToDevice));
+        d.bc[f] = m.bc[f];
+        for (int k = 0; k < len; k++)
+            if (bc[f][k] == SFGPU_BC_CIRCUIT) m.needs_slow = true;
+        d.nbr[f] = nullptr;
+        if (nbr && nbr[f]) {
+            CU(cudaMalloc(&m.nbr[f], sizeof(int) * 2 * len));
+            CU(cudaMemcpy(m.nbr[f], nbr[f], sizeof(int) * 2 * len, cudaMemcpyHostToDevice));
+            d.nbr[f] = m.nbr[f];
+        }
+    }
+    d.any_seg = 0;
+    d.has_seg = nullptr;
+    if (has_seg) {
+        for (size_t k = 0; k < plane; k++)
+            if (has_seg[k]) { d.any_seg = 1; break; }
+        if (d.any_seg) {
+            CU(cudaMalloc(&m.has_seg, plane));
+            CU(cudaMemcpy(m.has_seg, has_seg, plane, cudaMemcpyHostToDevice));
+            d.has_seg = m.has_seg;
+            m.needs_slow = true;
+        }
+    }
+    CU(cudaMalloc(&m.fields, 4 * plane * sizeof(double)));
+    CU(cudaMemset(m.fields, 0, 4 * plane * sizeof(double)));
+    d.efi = m.fields; d.efj = m.fields + plane; d.bfi = m.fields + 2 * plane; d.bfj = m.fields + 3 * plane;
+    d.has_b = 0;
+    d.node_vol = nullptr;
+    if (node_vol) {
+        CU(cudaMalloc(&m.node_vol, plane * sizeof(double)));
+        CU(cudaMemcpy(m.node_vol, node_vol, plane * sizeof(double), cudaMemcpyHostToDevice));
+        d.node_vol = m.node_vol;
+    }
+    ctx->meshes.push_back(m);
+    ctx->meshes_dirty = true;
+    *mesh_id = (int)ctx->meshes.size() - 1;
+    return 0;
+}
+
+extern "C" int sfgpu_set_fields(sfgpu_ctx *ctx, int32_t mesh_id, const double *efi, const double *efj,
+                                const double *bfi, const double *bfj)
+{
+    CHECK_CTX();
+    CHECK_MESH();
+    MeshHost &m = ctx->meshes[mesh_id];
+    const size_t plane = (size_t)m.dev.ni * m.dev.nj, bytes = plane * sizeof(double);
+    if (!efi || !efj) return fail(ctx, SFGPU_EINVAL, "sfgpu_set_fields: efi/efj are required");
+    if ((bfi == nullptr) != (bfj == nullptr)) return fail(ctx, SFGPU_EINVAL, "sfgpu_set_fields: give both bfi and bfj or neither");
+    const int nf = bfi ? 4 : 2;
+    int rc = stage_reserve(ctx, nf * bytes);
+    if (rc) return rc;
+    // the stage may still feed an earlier async copy
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->stage, efi, bytes);
+    memcpy(ctx->stage + bytes, efj, bytes);
+    if (bfi) {
+        memcpy(ctx->stage + 2 * bytes, bfi, bytes);
+        memcpy(ctx->stage + 3 * bytes, bfj, bytes);
+    }
+    CU(cudaMemcpyAsync(m.fields, ctx->stage, nf * bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int has_b = bfi ? 1 : 0;
+    if (!bfi && m.dev.has_b) CU(cudaMemsetAsync(m.fields + 2 * plane, 0, 2 * bytes, ctx->stream));
+    if (has_b != m.dev.has_b) {
+        m.dev.has_b = has_b;
+        ctx->meshes_dirty = true;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// species
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfgpu_species_add(sfgpu_ctx *ctx, double charge, double mass, int64_t capacity_hint, int32_t *sp)
+{
+    CHECK_CTX();
+    if (!sp) return fail(ctx, SFGPU_EINVAL, "sp is null");
+    if (ctx->meshes.empty()) return fail(ctx, SFGPU_ESTATE, "add a mesh before the first species");
+    if (!(mass > 0)) return fail(ctx, SFGPU_EINVAL, "mass must be positive");
+    Species s;
+    s.charge = charge;
+    s.mass = mass;
+    s.qm = charge / mass; // Material.java:711
+    s.capacity_hint = capacity_hint;
+    s.pops.resize(ctx->meshes.size());
+    for (size_t k = 0; k < ctx->meshes.size(); k++) {
+        const size_t plane = (size_t)ctx->meshes[k].dev.ni * ctx->meshes[k].dev.nj;
+        CU(cudaMalloc(&s.pops[k].dep, SFGPU_NFIELDS * plane * sizeof(double)));
+        CU(cudaMemset(s.pops[k].dep, 0, SFGPU_NFIELDS * plane * sizeof(double)));
+    }
+    ctx->species.push_back(s);
+    *sp = (int)ctx->species.size() - 1;
+    return 0;
+}
+
+static int slow_reserve(sfgpu_ctx *ctx, Species &s, int64_t need)
+{
+    if (need <= s.slow_cap) return 0;
+    if (s.slow_n) return fail(ctx, SFGPU_ESTATE, "slow-path list must be taken before it can grow");
+    rec_free(s.slow);
+    if (s.slow_extra_d) CU(cudaFree(s.slow_extra_d));
+    if (s.slow_extra_i) CU(cudaFree(s.slow_extra_i));
+    s.slow_extra_d = nullptr; s.slow_extra_i = nullptr; s.slow_cap = 0;
+    int rc = rec_reserve(ctx, s.slow, need, false);
+    if (rc) return rc;
+    CU(cudaMalloc(&s.slow_extra_d, (size_t)s.slow.cap * 4 * sizeof(double)));
+    CU(cudaMalloc(&s.slow_extra_i, (size_t)s.slow.cap * 2 * sizeof(int)));
+    s.slow_cap = s.slow.cap;
+    return 0;
+}
+
+static SlowPtrs slow_ptrs(const Species &s)
+{
+    SlowPtrs sp{};
+    sp.rec = s.slow.p;
+    sp.cap = (unsigned long long)s.slow_cap;
+    if (s.slow_cap) {
+        sp.old_x = s.slow_extra_d; sp.old_y = s.slow_extra_d + s.slow_cap;
+        sp.old_li = s.slow_extra_d + 2 * s.slow_cap; sp.old_lj = s.slow_extra_d + 3 * s.slow_cap;
+        sp.bounces = s.slow_extra_i; sp.mesh = s.slow_extra_i + s.slow_cap;
+    }
+    return sp;
+}
+
+// copy host SoA -> device records [first, first+n) through the pinned stage, chunked
+static int upload_records(sfgpu_ctx *ctx, Records &r, int64_t first, const sfgpu_particles *p, int32_t id_base, bool assign_ids)
+{
+    const int64_t n = p->n;
+    const int64_t chunk = 1 << 20;
+    int rc = stage_reserve(ctx, (size_t)chunk * (SF_REC_NDOUBLES * sizeof(double) + sizeof(int2)));
+    if (rc) return rc;
+    const double *src[SF_REC_NDOUBLES] = {p->x, p->y, p->z, p->u, p->v, p->w, p->mpw, p->li, p->lj, p->dt};
+    double *dst[SF_REC_NDOUBLES] = {r.p.x, r.p.y, r.p.z, r.p.u, r.p.v, r.p.w, r.p.mpw, r.p.li, r.p.lj, r.p.dt};
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t c = (n - off < chunk) ? n - off : chunk;
+        CU(cudaStreamSynchronize(ctx->stream)); // stage reuse
+        for (int k = 0; k < SF_REC_NDOUBLES; k++) {
+            double *st = (double *)ctx->stage + (size_t)k * chunk;
+            if (src[k]) memcpy(st, src[k] + off, (size_t)c * sizeof(double));
+            else memset(st, 0, (size_t)c * sizeof(double));
+            CU(cudaMemcpyAsync(dst[k] + first + off, st, (size_t)c * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        int2 *tg = (int2 *)((double *)ctx->stage + (size_t)SF_REC_NDOUBLES * chunk);
+        for (int64_t q = 0; q < c; q++) {
+            tg[q].x = assign_ids ? (int32_t)(id_base + off + q) : (p->id ? p->id[off + q] : -1);
+            tg[q].y = p->born_it ? p->born_it[off + q] : 0;
+        }
+        CU(cudaMemcpyAsync(r.p.tag + first + off, tg, (size_t)c * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int download_records(sfgpu_ctx *ctx, const RecPtrs &r, int64_t first, const sfgpu_particles *p)
+{
+    const int64_t n = p->n;
+    const int64_t chunk = 1 << 20;
+    int rc = stage_reserve(ctx, (size_t)chunk * (SF_REC_NDOUBLES * sizeof(double) + sizeof(int2)));
+    if (rc) return rc;
+    double *dst[SF_REC_NDOUBLES] = {p->x, p->y, p->z, p->u, p->v, p->w, p->mpw, p->li, p->lj, p->dt};
+    const double *src[SF_REC_NDOUBLES] = {r.x, r.y, r.z, r.u, r.v, r.w, r.mpw, r.li, r.lj, r.dt};
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t c = (n - off < chunk) ? n - off : chunk;
+        for (int k = 0; k < SF_REC_NDOUBLES; k++)
+            if (dst[k])
+                CU(cudaMemcpyAsync((double *)ctx->stage + (size_t)k * chunk, src[k] + first + off, (size_t)c * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        int2 *tg = (int2 *)((double *)ctx->stage + (size_t)SF_REC_NDOUBLES * chunk);
+        if (p->id || p->born_it)
+            CU(cudaMemcpyAsync(tg, r.tag + first + off, (size_t)c * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < SF_REC_NDOUBLES; k++)
+            if (dst[k]) memcpy(dst[k] + off, (double *)ctx->stage + (size_t)k * chunk, (size_t)c * sizeof(double));
+        for (int64_t q = 0; q < c; q++) {
+            if (p->id) p->id[off + q] = tg[q].x;
+            if (p->born_it) p->born_it[off + q] = tg[q].y;
+        }
+    }
+    return 0;
+}
+
+extern "C" int sfgpu_inject(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const sfgpu_particles *p, double dt_step,
+                            uint32_t flags, int64_t *n_added)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    if (n_added) *n_added = 0;
+    if (!p || p->n < 0) return fail(ctx, SFGPU_EINVAL, "sfgpu_inject: bad particle view");
+    if (p->n == 0) return 0;
+    if (!p->x || !p->y || !p->z || !p->u || !p->v || !p->w || !p->mpw) return fail(ctx, SFGPU_EINVAL, "sfgpu_inject: pos/vel/mpw arrays are required");
+    if ((p->li == nullptr) != (p->lj == nullptr)) return fail(ctx, SFGPU_EINVAL, "sfgpu_inject: give both li and lj or neither");
+    if ((flags & SFGPU_INJECT_TRANSFER) && (flags & (SFGPU_INJECT_REWIND | SFGPU_INJECT_DEPOSIT_NOW)))
+        return fail(ctx, SFGPU_EINVAL, "sfgpu_inject: TRANSFER excludes REWIND and DEPOSIT_NOW");
+    int rc = sync_meshes(ctx);
+    if (rc) return rc;
+    Species &s = ctx->species[sp];
+    Pop &pop = s.pops[mesh_id];
+    Records &r = (flags & SFGPU_INJECT_TRANSFER) ? pop.xout : pop.cur;
+    const int64_t first = r.n;
+    int64_t want = first + p->n;
+    if (first == 0 && s.capacity_hint > want) want = s.capacity_hint;
+    rc = rec_reserve(ctx, r, want, true);
+    if (rc) return rc;
+    const bool assign_ids = p->id == nullptr;
+    rc = upload_records(ctx, r, first, p, s.id_counter, assign_ids);
+    if (rc) return rc;
+    if (assign_ids) s.id_counter += (int32_t)p->n; // KM:797
+    CU(cudaMemsetAsync(&ctx->d_cnt->n_bad, 0, sizeof(unsigned long long), ctx->stream));
+    const int compute_lc = p->li == nullptr;
+    const int rewind = (flags & SFGPU_INJECT_REWIND) ? 1 : 0;
+    k_inject<<<(unsigned)((p->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, s.qm, dt_step, compute_lc, rewind, r.p, (unsigned long long)first, (unsigned long long)p->n, ctx->d_cnt);
+    CU(cudaGetLastError());
+    if (flags & SFGPU_INJECT_DEPOSIT_NOW) {
+        k_deposit_records<<<(unsigned)((p->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, r.p, (unsigned long long)first, (unsigned long long)p->n, pop.dep, ctx->d_cnt);
+        CU(cudaGetLastError());
+    }
+    unsigned long long n_bad = 0;
+    CU(cudaMemcpyAsync(&n_bad, &ctx->d_cnt->n_bad, sizeof n_bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int64_t added = p->n;
+    if (n_bad) {
+        // MeshData.addParticle drops non-finite velocities (KM:1357-1361): rare, compact on the host
+        std::vector<double> buf((size_t)p->n * SF_REC_NDOUBLES);
+        std::vector<int32_t> ids(p->n), born(p->n);
+        sfgpu_particles v{};
+        v.n = p->n;
+        double **arr[SF_REC_NDOUBLES] = {&v.x, &v.y, &v.z, &v.u, &v.v, &v.w, &v.mpw, &v.li, &v.lj, &v.dt};
+        for (int k = 0; k < SF_REC_NDOUBLES; k++) *arr[k] = buf.data() + (size_t)k * p->n;
+        v.id = ids.data();
+        v.born_it = born.data();
+        rc = download_records(ctx, r.p, first, &v);
+        if (rc) return rc;
+        int64_t w = 0;
+        for (int64_t q = 0; q < p->n; q++) {
+            if (!(std::isfinite(v.u[q]) && std::isfinite(v.v[q]) && std::isfinite(v.w[q]))) continue;
+            for (int k = 0; k < SF_REC_NDOUBLES; k++) (*arr[k])[w] = (*arr[k])[q];
+            ids[w] = ids[q];
+            born[w] = born[q];
+            w++;
+        }
+        v.n = w;
+        added = w;
+        if (w) {
+            rc = upload_records(ctx, r, first, &v, 0, false);
+            if (rc) return rc;
+        }
+    }
+    r.n = first + added;
+    if (n_added) *n_added = added;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------------------------
+static int read_counters(sfgpu_ctx *ctx)
+{
+    CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(StepCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int push_xfer_table(sfgpu_ctx *ctx, Species &s)
+{
+    XferDev h[SF_MAX_MESHES];
+    memset(h, 0, sizeof h);
+    for (size_t k = 0; k < s.pops.size(); k++) {
+        h[k].rec = s.pops[k].xout.p;
+        h[k].cap = (unsigned long long)s.pops[k].xout.cap;
+    }
+    CU(cudaMemcpyAsync(ctx->d_xfer, h, sizeof(XferDev) * s.pops.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // h is on the stack
+    return 0;
+}
+
+extern "C" int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp);
+
+extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    int rc = sync_meshes(ctx);
+    if (rc) return rc;
+    Species &s = ctx->species[sp];
+    const int nmesh = (int)ctx->meshes.size();
+    if (s.slow_n) return fail(ctx, SFGPU_ESTATE, "take the slow-path particles of the previous step first");
+    if (s.step_open) return fail(ctx, SFGPU_ESTATE, "previous step was deferred: call sfgpu_finish_step first");
+    int64_t n_total = 0;
+    bool needs_slow = false;
+    for (int m = 0; m < nmesh; m++) {
+        n_total += s.pops[m].cur.n;
+        needs_slow = needs_slow || ctx->meshes[m].needs_slow;
+    }
+    if (needs_slow) {
+        rc = slow_reserve(ctx, s, n_total > 4096 ? n_total : 4096);
+        if (rc) return rc;
+    }
+    bool multi = nmesh > 1;
+    for (int m = 0; m < nmesh; m++) multi = multi || s.pops[m].xout.n > 0;
+    if (multi) {
+        int64_t xcap = n_total > 65536 ? n_total : 65536;
+        for (int m = 0; m < nmesh; m++) {
+            rc = rec_reserve(ctx, s.pops[m].xout, s.pops[m].xout.n + xcap, true);
+            if (rc) return rc;
+        }
+        rc = push_xfer_table(ctx, s);
+        if (rc) return rc;
+    }
+    ctx->last_launches = 0;
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
+    // pre-seed the transfer cursors with particles the host put on the transfer lists
+    if (multi) {
+        unsigned long long pre[SF_MAX_MESHES] = {0};
+        bool any = false;
+        for (int m = 0; m < nmesh; m++) {
+            pre[m] = (unsigned long long)s.pops[m].xout.n;
+            any = any || pre[m];
+        }
+        if (any) {
+            CU(cudaMemcpyAsync(ctx->d_cnt->xfer_n, pre, sizeof(unsigned long long) * nmesh, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    const SlowPtrs slow = slow_ptrs(s);
+    // moveParticles(false), KM:126
+    for (int m = 0; m < nmesh; m++) {
+        const size_t plane = (size_t)ctx->meshes[m].dev.ni * ctx->meshes[m].dev.nj;
+        CU(cudaMemsetAsync(s.pops[m].dep, 0, SFGPU_NFIELDS * plane * sizeof(double), ctx->stream));
+        rc = rec_reserve(ctx, s.pops[m].nxt, s.pops[m].cur.n, false);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->evk0, ctx->stream));
+    for (int m = 0; m < nmesh; m++) {
+        Pop &pop = s.pops[m];
+        if (pop.cur.n == 0) continue;
+        k_generic_step<<<grid_for(pop.cur.n, 256, 148 * 32), 256, 0, ctx->stream>>>(
+            ctx->d_meshes, m, s.qm, s.charge, dt, 0, pop.cur.p, (unsigned long long)pop.cur.n, pop.nxt.p,
+            &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt);
+        CU(cudaGetLastError());
+        ctx->last_launches++;
+    }
+    CU(cudaEventRecord(ctx->evk1, ctx->stream));
+    rc = read_counters(ctx);
+    if (rc) return rc;
+    // transfer sweeps, KM:131-142
+    if (multi) {
+        for (int loop = 0; loop < 10; loop++) {
+            unsigned long long pending = 0;
+            for (int m = 0; m < nmesh; m++) pending += ctx->h_cnt->xfer_n[m];
+            if (!pending) break;
+            if (ctx->h_cnt->overflow) break;
+            // what was filled becomes the input of this sweep; fresh lists collect new hand-offs
+            for (int m = 0; m < nmesh; m++) {
+                Pop &pop = s.pops[m];
+                std::swap(pop.xin, pop.xout);
+                pop.xin.n = (int64_t)ctx->h_cnt->xfer_n[m];
+                pop.xout.n = 0;
+                rc = rec_reserve(ctx, pop.xout, pop.xin.cap, false);
+                if (rc) return rc;
+                const int64_t have = (int64_t)ctx->h_cnt->n_out[m];
+                pop.nxt.n = have;
+                rc = rec_reserve(ctx, pop.nxt, have + pop.xin.n, true);
+                if (rc) return rc;
+            }
+            rc = push_xfer_table(ctx, s);
+            if (rc) return rc;
+            CU(cudaMemsetAsync(ctx->d_cnt->xfer_n, 0, sizeof(unsigned long long) * SF_MAX_MESHES, ctx->stream));
+            for (int m = 0; m < nmesh; m++) {
+                Pop &pop = s.pops[m];
+                if (pop.xin.n == 0) continue;
+                k_generic_step<<<grid_for(pop.xin.n, 256, 148 * 32), 256, 0, ctx->stream>>>(
+                    ctx->d_meshes, m, s.qm, s.charge, dt, 1, pop.xin.p, (unsigned long long)pop.xin.n, pop.nxt.p,
+                    &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt);
+                CU(cudaGetLastError());
+                ctx->last_launches++;
+                pop.xin.n = 0;
+            }
+            rc = read_counters(ctx);
+            if (rc) return rc;
+        }
+        // anything still pending stays on the lists for the next step ("Failed to transfer all particles", KM:141)
+        for (int m = 0; m < nmesh; m++) s.pops[m].xout.n = (int64_t)ctx->h_cnt->xfer_n[m];
+    }
+    if (ctx->h_cnt->overflow)
+        return fail(ctx, SFGPU_EOVERFLOW, "%llu particles did not fit an internal list (slow path / mesh hand-off)", ctx->h_cnt->overflow);
+    for (int m = 0; m < nmesh; m++) {
+        Pop &pop = s.pops[m];
+        pop.nxt.n = (int64_t)ctx->h_cnt->n_out[m];
+        std::swap(pop.cur, pop.nxt);
+        pop.nxt.n = 0;
+    }
+    s.n_exited = (int64_t)ctx->h_cnt->n_exited;
+    s.n_removed = (int64_t)ctx->h_cnt->n_removed;
+    s.slow_n = (int64_t)ctx->h_cnt->n_slow;
+    s.step_open = true;
+    if (flags & SFGPU_STEP_DEFER_FINISH) return 0;
+    return sfgpu_finish_step(ctx, sp);
+}
+
+// cross-GPU sum of the deposit (particles are partitioned, the mesh is replicated) and of the
+// mover sums; closes the step opened by sfgpu_step
+extern "C" int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    Species &s = ctx->species[sp];
+    if (!s.step_open) return fail(ctx, SFGPU_ESTATE, "sfgpu_finish_step without an open step");
+    const int nmesh = (int)ctx->meshes.size();
+    if (ctx->comm) {
+        for (int m = 0; m < nmesh; m++) {
+            const size_t plane = (size_t)ctx->meshes[m].dev.ni * ctx->meshes[m].dev.nj;
+            int r = g_nccl.AllReduce(s.pops[m].dep, s.pops[m].dep, SFGPU_NFIELDS * plane, SF_NCCL_FLOAT64, SF_NCCL_SUM, ctx->comm, ctx->stream);
+            if (r) return fail(ctx, SFGPU_ENCCL, "ncclAllReduce(deposit): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        }
+        int r = g_nccl.AllReduce(ctx->d_cnt->sums, ctx->d_cnt->sums, 5, SF_NCCL_FLOAT64, SF_NCCL_SUM, ctx->comm, ctx->stream);
+        if (r) return fail(ctx, SFGPU_ENCCL, "ncclAllReduce(sums): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    CU(cudaMemcpyAsync(ctx->h_cnt->sums, ctx->d_cnt->sums, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->timing_valid = true;
+    for (int k = 0; k < 5; k++) s.sums[k] = ctx->h_cnt->sums[k];
+    s.step_open = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfgpu_get_deposit(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, double *const out[SFGPU_NFIELDS])
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    if (!out) return fail(ctx, SFGPU_EINVAL, "out is null");
+    const size_t plane = (size_t)ctx->meshes[mesh_id].dev.ni * ctx->meshes[mesh_id].dev.nj, bytes = plane * sizeof(double);
+    int rc = stage_reserve(ctx, SFGPU_NFIELDS * bytes);
+    if (rc) return rc;
+    Pop &pop = ctx->species[sp].pops[mesh_id];
+    // contiguous run of requested fields -> one copy
+    int lo = -1, hi = -1;
+    for (int f = 0; f < SFGPU_NFIELDS; f++)
+        if (out[f]) { if (lo < 0) lo = f; hi = f; }
+    if (lo < 0) return 0;
+    CU(cudaMemcpyAsync(ctx->stage + lo * bytes, pop.dep + lo * plane, (hi - lo + 1) * bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int f = lo; f <= hi; f++)
+        if (out[f]) memcpy(out[f], ctx->stage + f * bytes, bytes);
+    return 0;
+}
+
+extern "C" int sfgpu_get_moments(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, double *nd, double *u, double *v, double *w)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    MeshHost &m = ctx->meshes[mesh_id];
+    if (!m.node_vol) return fail(ctx, SFGPU_ESTATE, "mesh %d was added without node_vol", mesh_id);
+    const size_t plane = (size_t)m.dev.ni * m.dev.nj, bytes = plane * sizeof(double);
+    if (ctx->tmp_bytes < 4 * bytes) {
+        if (ctx->d_tmp) CU(cudaFree(ctx->d_tmp));
+        ctx->d_tmp = nullptr;
+        ctx->tmp_bytes = 0;
+        CU(cudaMalloc(&ctx->d_tmp, 4 * bytes));
+        ctx->tmp_bytes = 4 * bytes;
+    }
+    int rc = stage_reserve(ctx, 4 * bytes);
+    if (rc) return rc;
+    k_moments<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(ctx->species[sp].pops[mesh_id].dep, m.node_vol, plane, ctx->d_tmp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->stage, ctx->d_tmp, 4 * bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    double *dst[4] = {nd, u, v, w};
+    for (int k = 0; k < 4; k++)
+        if (dst[k]) memcpy(dst[k], ctx->stage + k * bytes, bytes);
+    return 0;
+}
+
+extern "C" int sfgpu_get_sums(sfgpu_ctx *ctx, int32_t sp, double sums5[5], int64_t *np_alive, int64_t *n_exited, int64_t *n_slow)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    Species &s = ctx->species[sp];
+    if (sums5) for (int k = 0; k < 5; k++) sums5[k] = s.sums[k];
+    if (np_alive) {
+        int64_t n = 0;
+        for (auto &p : s.pops) n += p.cur.n;
+        *np_alive = n;
+    }
+    if (n_exited) *n_exited = s.n_exited;
+    if (n_slow) *n_slow = s.slow_n;
+    return 0;
+}
+
+extern "C" int sfgpu_np(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t *np)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    if (!np) return fail(ctx, SFGPU_EINVAL, "np is null");
+    Species &s = ctx->species[sp];
+    if (mesh_id < 0) {
+        int64_t n = 0;
+        for (auto &p : s.pops) n += p.cur.n;
+        *np = n;
+        return 0;
+    }
+    CHECK_MESH();
+    *np = s.pops[mesh_id].cur.n;
+    return 0;
+}
+
+extern "C" int sfgpu_take_slowpath(sfgpu_ctx *ctx, int32_t sp, int64_t max, sfgpu_particles *out, sfgpu_slow_extra *extra, int64_t *n)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    if (!out || !n) return fail(ctx, SFGPU_EINVAL, "sfgpu_take_slowpath: out/n are required");
+    Species &s = ctx->species[sp];
+    if (max < s.slow_n) return fail(ctx, SFGPU_EINVAL, "sfgpu_take_slowpath: room for %lld, list holds %lld", (long long)max, (long long)s.slow_n);
+    *n = s.slow_n;
+    if (s.slow_n == 0) return 0;
+    sfgpu_particles v = *out;
+    v.n = s.slow_n;
+    int rc = download_records(ctx, s.slow.p, 0, &v);
+    if (rc) return rc;
+    if (extra) {
+        const SlowPtrs spt = slow_ptrs(s);
+        const size_t nb = (size_t)s.slow_n;
+        if (extra->old_x) CU(cudaMemcpy(extra->old_x, spt.old_x, nb * sizeof(double), cudaMemcpyDeviceToHost));
+        if (extra->old_y) CU(cudaMemcpy(extra->old_y, spt.old_y, nb * sizeof(double), cudaMemcpyDeviceToHost));
+        if (extra->old_li) CU(cudaMemcpy(extra->old_li, spt.old_li, nb * sizeof(double), cudaMemcpyDeviceToHost));
+        if (extra->old_lj) CU(cudaMemcpy(extra->old_lj, spt.old_lj, nb * sizeof(double), cudaMemcpyDeviceToHost));
+        if (extra->bounces) CU(cudaMemcpy(extra->bounces, spt.bounces, nb * sizeof(int), cudaMemcpyDeviceToHost));
+        if (extra->mesh) CU(cudaMemcpy(extra->mesh, spt.mesh, nb * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    s.slow_n = 0;
+    return 0;
+}
+
+extern "C" int sfgpu_download(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t first, sfgpu_particles *out)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    if (!out) return fail(ctx, SFGPU_EINVAL, "out is null");
+    Pop &pop = ctx->species[sp].pops[mesh_id];
+    if (first < 0 || out->n < 0 || first + out->n > pop.cur.n)
+        return fail(ctx, SFGPU_EINVAL, "sfgpu_download: range [%lld,%lld) outside [0,%lld)", (long long)first, (long long)(first + out->n), (long long)pop.cur.n);
+    if (out->n == 0) return 0;
+    return download_records(ctx, pop.cur.p, first, out);
+}
+
+extern "C" int sfgpu_upload(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t first, const sfgpu_particles *in)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    if (!in) return fail(ctx, SFGPU_EINVAL, "in is null");
+    Pop &pop = ctx->species[sp].pops[mesh_id];
+    if (first < 0 || in->n < 0 || first + in->n > pop.cur.n)
+        return fail(ctx, SFGPU_EINVAL, "sfgpu_upload: range outside the store");
+    if (!in->x || !in->y || !in->z || !in->u || !in->v || !in->w || !in->mpw || !in->li || !in->lj || !in->dt || !in->id || !in->born_it)
+        return fail(ctx, SFGPU_EINVAL, "sfgpu_upload: every array is required");
+    if (in->n == 0) return 0;
+    return upload_records(ctx, pop.cur, first, in, 0, false);
+}
+
+extern "C" int sfgpu_sort(sfgpu_ctx *ctx, int32_t sp)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    return 0; // order is not observable in the generic store; the tiled store sorts as part of every step
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi GPU
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfgpu_comm_unique_id(void *id128)
+{
+    if (!id128) return fail(nullptr, SFGPU_EINVAL, "id128 is null");
+    std::string why;
+    if (!nccl_load(why)) return fail(nullptr, SFGPU_ENCCL, "%s", why.c_str());
+    sf_ncclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r) return fail(nullptr, SFGPU_ENCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    memcpy(id128, &id, sizeof id);
+    return 0;
+}
+
+extern "C" int sfgpu_comm_init(sfgpu_ctx *ctx, int32_t nranks, int32_t rank, const void *id128)
+{
+    CHECK_CTX();
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(ctx, SFGPU_EINVAL, "sfgpu_comm_init: bad arguments");
+    std::string why;
+    if (!nccl_load(why)) return fail(ctx, SFGPU_ENCCL, "%s", why.c_str());
+    if (ctx->comm) return fail(ctx, SFGPU_ESTATE, "communicator already attached");
+    sf_ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    int r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r) {
+        ctx->comm = nullptr;
+        return fail(ctx, SFGPU_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return 0;
+}
+
+extern "C" int sfgpu_deposit_device_ptr(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, void **ptr, int64_t *count)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    if (!ptr || !count) return fail(ctx, SFGPU_EINVAL, "ptr/count are required");
+    *ptr = ctx->species[sp].pops[mesh_id].dep;
+    *count = (int64_t)SFGPU_NFIELDS * ctx->meshes[mesh_id].dev.ni * ctx->meshes[mesh_id].dev.nj;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfgpu_last_step_timing(sfgpu_ctx *ctx, float *ms_total, float *ms_kernel, int32_t *launches)
+{
+    CHECK_CTX();
+    if (!ctx->timing_valid) return fail(ctx, SFGPU_ESTATE, "no step has run yet");
+    if (ms_total) CU(cudaEventElapsedTime(ms_total, ctx->ev0, ctx->ev1));
+    if (ms_kernel) CU(cudaEventElapsedTime(ms_kernel, ctx->evk0, ctx->evk1));
+    if (launches) *launches = ctx->last_launches;
+    return 0;
+}
+
+extern "C" int sfgpu_sync(sfgpu_ctx *ctx)
+{
+    CHECK_CTX();
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

@@ -1,0 +1,112 @@
+"""Host-side mirror of the mesh state the hot path reads.
+
+Mirrors ``starfish.core.domain.UniformMesh`` (UniformMesh.java:33-43, :139-161) and the parts of
+``Mesh`` the particle path touches: face boundary types (Mesh.java:107-118, :140-155, :215),
+mesh neighbours (Mesh.java:160-165), node volumes (Mesh.java:998-1020) and ``containsPos``
+(Mesh.java:1476-1483).  Pure data + numpy: no particle arithmetic happens here.
+"""
+from __future__ import annotations
+
+import enum
+
+import numpy as np
+
+FLT_EPS = 1e-7  # Constants.java:26
+
+
+class DomainType(enum.IntEnum):  # DomainModule.java:28
+    XY = 0
+    RZ = 1
+    ZR = 2
+
+
+class Face(enum.IntEnum):  # Mesh.java:107-118
+    RIGHT = 0
+    TOP = 1
+    LEFT = 2
+    BOTTOM = 3
+
+
+class DomainBoundaryType(enum.IntEnum):  # Mesh.java:140-155
+    OPEN = -1
+    DIRICHLET = 0
+    NEUMANN = 1
+    PERIODIC = 2
+    SYMMETRY = 3
+    MESH = 4
+    SINK = 5
+    CIRCUIT = 6
+
+
+class UniformMesh:
+    """Rectilinear mesh with uniform spacing: ``pos(i,j) = x0 + (i,j)*dh`` (UniformMesh.java:139-145)."""
+
+    def __init__(self, ni, nj, x0, dh, domain_type=DomainType.XY, name="mesh"):
+        self.ni, self.nj = int(ni), int(nj)
+        self.x0 = np.array(x0, dtype=np.float64)
+        self.dh = np.array(dh, dtype=np.float64)
+        self.domain_type = DomainType(domain_type)
+        self.name = name
+        # xd = x0 + (n-1)*dh, UniformMesh.java:131-135
+        self.xd = np.array([self.x0[0] + (self.ni - 1) * self.dh[0], self.x0[1] + (self.nj - 1) * self.dh[1]])
+        # per-face per-node boundary type, default OPEN (Mesh.java:162)
+        self.bc = [np.full(self._face_len(f), int(DomainBoundaryType.OPEN), dtype=np.int8) for f in range(4)]
+        # per-face per-node two neighbour mesh ids, -1 = none (Mesh.java:160-165)
+        self.nbr = [np.full((self._face_len(f), 2), -1, dtype=np.int32) for f in range(4)]
+        self.has_seg = np.zeros((self.ni, self.nj), dtype=np.uint8)
+        self.efi = np.zeros((self.ni, self.nj))
+        self.efj = np.zeros((self.ni, self.nj))
+        self.bfi = None
+        self.bfj = None
+        self.node_vol = self._node_volumes()
+        self.index = -1  # set when attached to a material
+
+    def _face_len(self, f):
+        return self.nj if f in (Face.RIGHT, Face.LEFT) else self.ni
+
+    # Mesh.setMeshBCType, Mesh.java:191-207
+    def setMeshBCType(self, face, bc_type):
+        self.bc[int(face)][:] = int(bc_type)
+
+    def boundaryType(self, face, index):  # Mesh.java:215-217
+        return DomainBoundaryType(int(self.bc[int(face)][index]))
+
+    def setNeighbor(self, face, index, slot, mesh_index):
+        self.nbr[int(face)][index, slot] = mesh_index
+        self.bc[int(face)][index] = int(DomainBoundaryType.MESH)
+
+    def XtoL(self, x):  # UniformMesh.java:154-161
+        x = np.asarray(x, dtype=np.float64)
+        return np.stack([(x[..., 0] - self.x0[0]) / self.dh[0], (x[..., 1] - self.x0[1]) / self.dh[1]], axis=-1)
+
+    def pos(self, lc):  # UniformMesh.java:139-145
+        lc = np.asarray(lc, dtype=np.float64)
+        return np.stack([self.x0[0] + lc[..., 0] * self.dh[0], self.x0[1] + lc[..., 1] * self.dh[1]], axis=-1)
+
+    def containsPos(self, x):  # Mesh.java:1476-1483
+        lc = self.XtoL(x)
+        return ~((lc[..., 0] < -FLT_EPS) | (lc[..., 1] < -FLT_EPS) | (lc[..., 0] > self.ni - 1 + FLT_EPS)
+                 | (lc[..., 1] > self.nj - 1 + FLT_EPS))
+
+    def _node_volumes(self):
+        """Node control volumes in the spirit of Mesh.nodeVol (Mesh.java:998-1020): half cells on mesh
+        edges, XY depth 1, axisymmetric volumes 2*pi*r*area with the r +- 0.25*dr shift on the edge
+        rows.  Mesh setup stays in Java; this array is an INPUT of the path (Field2D.scaleByVol)."""
+        wi = np.ones(self.ni)
+        wi[0] = wi[-1] = 0.5
+        wj = np.ones(self.nj)
+        wj[0] = wj[-1] = 0.5
+        area = np.outer(wi * self.dh[0], wj * self.dh[1])
+        if self.domain_type == DomainType.XY:
+            return area
+        if self.domain_type == DomainType.RZ:
+            ii = np.arange(self.ni, dtype=np.float64)
+            ii[0] += 0.25
+            ii[-1] -= 0.25
+            r = (self.x0[0] + ii * self.dh[0])[:, None]
+        else:
+            jj = np.arange(self.nj, dtype=np.float64)
+            jj[0] += 0.25
+            jj[-1] -= 0.25
+            r = (self.x0[1] + jj * self.dh[1])[None, :]
+        return 2 * np.pi * area * r
