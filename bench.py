@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- particle pushes/s (fused move+deposit) of the Starfish kinetic hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|b|b_beam|c|e]
+
+One "step" = one KineticMaterial.updateFields() pass (move + deposit + moment sums) over the whole resident
+particle population; one "push" = one particle advanced one step including its deposit contribution.
+
+Workloads (BASELINE.json configs):
+  b  (default at N=1)  XY 512x512 nodes, 16,777,216 uniformly loaded particles, all faces periodic
+  N>1 default           the same shard on every rank (weak scaling: N x 16M particles on the replicated mesh,
+                        per-step NCCL allreduce of the deposit)
+  e                     XY 2048x2048 nodes, 2^30 particles partitioned by index over the ranks
+  c                     RZ 1024x1024, beam over r < 0.25 Rmax, LEFT symmetry, other faces open
+Particle arrays (1 GiB at 16M) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
+
+JSON keys: see the task contract; `value` is device-resident throughput (CUDA events on the library's stream,
+max over ranks), `e2e` is the same metric through the plugin API with host buffers for the fields (E upload,
+deposit/moment download every step), `roofline` is the fused step kernel against the measured HBM copy peak,
+`cpu_baseline` the oracle restatement of the Java algorithm timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_BYTES_PER_PUSH = 104  # read pos[3],vel[3],mpw + write pos[3],vel[3], FP64
+
+
+def workload(name, world):
+    from starfish_b200 import synthetic as S
+    if name == "b":
+        return S.config_b(), 1 << 24
+    if name == "b_beam":
+        return S.config_b(beam=True), 1 << 24
+    if name == "c":
+        return S.config_c(), 1 << 27
+    if name == "e":
+        return S.config_e(), (1 << 30) // world
+    raise ValueError(name)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(wl, n_sample, steps, warmup, threads):
+    """The reference's CPU algorithm (oracle port: T mover threads, serial deposit + sampling like KM:180/:1580)."""
+    from oracle import oracle as O
+    ok = O.OracleKM(wl.charge, wl.mass, [wl.mesh], threads=threads)
+    ok.addParticles(0, wl.particles(0, n_sample), wl.dt)
+    for _ in range(warmup):
+        ok.updateFields(wl.dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ok.updateFields(wl.dt)
+    t = time.perf_counter() - t0
+    return n_sample * steps / t, t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    wl, _n = workload("b" if args.workload == "auto" else args.workload, world)
+    threads = os.cpu_count() or 1
+    n_sample = args.ref_particles
+    value, t = cpu_reference_run(wl, n_sample, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "particle pushes/sec (move+deposit)", "value": value, "unit": "pushes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.name, "mesh_nodes": [wl.mesh.ni, wl.mesh.nj], "particles": n_sample,
+                   "note": "bounded sample of the workload on the host cores; JVM unavailable, C restatement of the Java algorithm"},
+        "cpu_baseline": {"value": value, "unit": "pushes/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_sample} particles x {args.steps} steps, {threads} mover threads + serial deposit (as KineticMaterial.java:180,:1580)"},
+        "e2e": {"value": value, "unit": "pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "b", "b_beam", "c", "e"])
+    ap.add_argument("--particles", type=int, default=0, help="particles per rank (default: the config's)")
+    ap.add_argument("--ref-particles", type=int, default=1 << 21)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--step-flags", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from starfish_b200 import KineticMaterial, Particles
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: starfish_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wname = args.workload if args.workload != "auto" else "b"
+    wl, n_rank = workload(wname, world)
+    if args.particles:
+        n_rank = args.particles
+    m = wl.mesh
+    km = KineticMaterial("O+", wl.charge, wl.mass, [m], m.domain_type, device=local_rank, capacity_hint=n_rank, step_flags=args.step_flags)
+    km.dt = wl.dt
+    if world > 1:
+        ids = [KineticMaterial.commUniqueId() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        km.commInit(world, rank, ids[0])
+    # this rank's shard: particle indices [rank*n_rank, (rank+1)*n_rank) of the global population
+    chunk = 1 << 22
+    for first in range(0, n_rank, chunk):
+        c = min(chunk, n_rank - first)
+        arr = wl.particles(rank * n_rank + first, c)
+        km.addParticles(m, Particles(c, **arr), wl.dt)
+    n_local = km.getNp()
+
+    def barrier():
+        km.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident throughput ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        km.step_raw(wl.dt)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = km.launchCount()
+    ker_ms, pushes = 0.0, 0
+    t0 = time.perf_counter()
+    km.timerStart()
+    for _ in range(args.steps):
+        pushes += km.getNp()
+        km.step_raw(wl.dt)
+        _tot, ker, _n = km.lastStepTiming()
+        ker_ms += ker
+    dev_ms = km.timerStop()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    launches = km.launchCount() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = allmax(dev_ms)
+    wall_ms = allmax(wall_ms)
+    total_pushes = allsum(float(pushes))
+    value = total_pushes / (dev_ms * 1e-3)
+
+    # ---- end to end through the plugin API: E upload + step + deposit/moment download, host buffers ------
+    for _ in range(2):
+        km.setFields(m)
+        km.updateFields()
+    barrier()
+    e_pushes = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e_pushes += km.getNp()
+        km.setFields(m)       # host -> device: efi, efj of this step (the Java solver's output)
+        km.updateFields()     # step + device -> host: 8 raw deposit fields, nd/u/v/w, mover sums
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_value = allsum(float(e_pushes)) / e2e_s
+    plane = m.ni * m.nj * 8
+    h2d, d2h = 2 * plane, 12 * plane + 5 * 8
+
+    if rank == 0:
+        peaks, peak_src = None, "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak = float(peaks["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            peak = 6650.0
+        achieved = ALGO_BYTES_PER_PUSH * float(pushes) / (ker_ms * 1e-3) / 1e9 if ker_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wname)
+        except Exception:
+            pass
+        line = {
+            "metric": "particle pushes/sec (move+deposit)", "value": value, "unit": "pushes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.name, "mesh_nodes": [m.ni, m.nj], "particles_per_gpu": n_local, "particles_total": int(allsum(float(n_local))) if world == 1 else int(n_local * world),
+                       "l2": "particle arrays (64 B x N per GPU) exceed the 126 MB L2; no flush needed",
+                       "parallelism": "particles partitioned by index, mesh replicated, NCCL allreduce of the deposit" if world > 1 else "single GPU"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": "pushes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel": "fused move+deposit step kernel(s)",
+                         "algorithmic_bytes_per_push": ALGO_BYTES_PER_PUSH, "kernel_ms_per_step": ker_ms / args.steps,
+                         "pushes_per_s_at_peak": peak * 1e9 / ALGO_BYTES_PER_PUSH},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_sample = args.ref_particles
+            v, t = cpu_reference_run(wl, n_sample, 3, 1, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "pushes/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n_sample} particles x 3 steps of the same workload, {threads} mover threads + serial deposit"}
+        print(json.dumps(line), flush=True)
+    km.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

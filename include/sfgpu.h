@@ -186,6 +186,12 @@ int sfgpu_deposit_device_ptr(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, void *
 int sfgpu_last_step_timing(sfgpu_ctx *ctx, float *ms_total, float *ms_kernel, int32_t *launches);
 /* cudaStreamSynchronize on the context's stream */
 int sfgpu_sync(sfgpu_ctx *ctx);
+/* bracket any sequence of calls with CUDA events on the context's stream (the stream every kernel of the
+ * library is launched on): stop synchronises and returns the device milliseconds since start */
+int sfgpu_timer_start(sfgpu_ctx *ctx);
+int sfgpu_timer_stop(sfgpu_ctx *ctx, float *ms);
+/* kernels launched by this context since sfgpu_create (cumulative) */
+int sfgpu_launch_count(sfgpu_ctx *ctx, int64_t *n);
 
 #ifdef __cplusplus
 }

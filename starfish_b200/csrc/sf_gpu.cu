@@ -126,7 +126,8 @@ struct Species {
 struct sfgpu_ctx {
     int device = 0, domain = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    int64_t launch_total = 0;
     std::vector<MeshHost> meshes;
     MeshDev *d_meshes = nullptr;
     bool meshes_dirty = true;
@@ -263,6 +264,8 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaEventCreate(&ctx->ev1));
         CU(cudaEventCreate(&ctx->evk0));
         CU(cudaEventCreate(&ctx->evk1));
+        CU(cudaEventCreate(&ctx->evt0));
+        CU(cudaEventCreate(&ctx->evt1));
         CU(cudaMalloc(&ctx->d_cnt, sizeof(StepCounters)));
         CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
         CU(cudaMallocHost(&ctx->h_cnt, sizeof(StepCounters)));
@@ -323,6 +326,8 @@ extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evk0) cudaEventDestroy(ctx->evk0);
     if (ctx->evk1) cudaEventDestroy(ctx->evk1);
+    if (ctx->evt0) cudaEventDestroy(ctx->evt0);
+    if (ctx->evt1) cudaEventDestroy(ctx->evt1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -562,10 +567,12 @@ extern "C" int sfgpu_inject(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const s
     const int compute_lc = p->li == nullptr;
     const int rewind = (flags & SFGPU_INJECT_REWIND) ? 1 : 0;
     k_inject<<<(unsigned)((p->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, s.qm, dt_step, compute_lc, rewind, r.p, (unsigned long long)first, (unsigned long long)p->n, ctx->d_cnt);
+    ctx->launch_total++;
     CU(cudaGetLastError());
     if (flags & SFGPU_INJECT_DEPOSIT_NOW) {
         k_deposit_records<<<(unsigned)((p->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, r.p, (unsigned long long)first, (unsigned long long)p->n, pop.dep, ctx->d_cnt);
-        CU(cudaGetLastError());
+        ctx->launch_total++;
+    CU(cudaGetLastError());
     }
     unsigned long long n_bad = 0;
     CU(cudaMemcpyAsync(&n_bad, &ctx->d_cnt->n_bad, sizeof n_bad, cudaMemcpyDeviceToHost, ctx->stream));
@@ -691,7 +698,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             ctx->d_meshes, m, s.qm, s.charge, dt, 0, pop.cur.p, (unsigned long long)pop.cur.n, pop.nxt.p,
             &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt);
         CU(cudaGetLastError());
-        ctx->last_launches++;
+        { ctx->last_launches++; ctx->launch_total++; }
     }
     CU(cudaEventRecord(ctx->evk1, ctx->stream));
     rc = read_counters(ctx);
@@ -726,7 +733,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                     ctx->d_meshes, m, s.qm, s.charge, dt, 1, pop.xin.p, (unsigned long long)pop.xin.n, pop.nxt.p,
                     &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt);
                 CU(cudaGetLastError());
-                ctx->last_launches++;
+                { ctx->last_launches++; ctx->launch_total++; }
                 pop.xin.n = 0;
             }
             rc = read_counters(ctx);
@@ -821,6 +828,7 @@ extern "C" int sfgpu_get_moments(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, do
     int rc = stage_reserve(ctx, 4 * bytes);
     if (rc) return rc;
     k_moments<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(ctx->species[sp].pops[mesh_id].dep, m.node_vol, plane, ctx->d_tmp);
+    ctx->launch_total++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(ctx->stage, ctx->d_tmp, 4 * bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -987,5 +995,30 @@ extern "C" int sfgpu_sync(sfgpu_ctx *ctx)
 {
     CHECK_CTX();
     CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int sfgpu_timer_start(sfgpu_ctx *ctx)
+{
+    CHECK_CTX();
+    CU(cudaEventRecord(ctx->evt0, ctx->stream));
+    return 0;
+}
+
+extern "C" int sfgpu_timer_stop(sfgpu_ctx *ctx, float *ms)
+{
+    CHECK_CTX();
+    if (!ms) return fail(ctx, SFGPU_EINVAL, "ms is null");
+    CU(cudaEventRecord(ctx->evt1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->evt1));
+    CU(cudaEventElapsedTime(ms, ctx->evt0, ctx->evt1));
+    return 0;
+}
+
+extern "C" int sfgpu_launch_count(sfgpu_ctx *ctx, int64_t *n)
+{
+    CHECK_CTX();
+    if (!n) return fail(ctx, SFGPU_EINVAL, "n is null");
+    *n = ctx->launch_total;
     return 0;
 }

@@ -309,3 +309,17 @@ class KineticMaterial:
 
     def sync(self):
         self._check(self.lib.sfgpu_sync(self._ctx))
+
+    def timerStart(self):
+        self._check(self.lib.sfgpu_timer_start(self._ctx))
+
+    def timerStop(self):
+        """Device milliseconds since timerStart(), CUDA events on the stream the kernels run on."""
+        ms = C.c_float()
+        self._check(self.lib.sfgpu_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def launchCount(self):
+        n = C.c_int64()
+        self._check(self.lib.sfgpu_launch_count(self._ctx, C.byref(n)))
+        return n.value

@@ -1,0 +1,235 @@
+"""Parity of the CUDA path (through the C ABI of libstarfish_gpu.so) against the CPU oracle.
+
+Bars (BASELINE.json north_star): particle positions/velocities bit exact in XY (the theta coordinate pos[2]
+of axisymmetric runs goes through asin/acos: 1e-12 relative), cell indices and particle counts bit exact,
+deposited fields within 1e-10 relative (atomic summation order differs).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from starfish_b200 import KineticMaterial, Particles, synthetic as S
+from starfish_b200 import _lib
+from starfish_b200.domain import DomainBoundaryType as BC, DomainType, Face, UniformMesh
+
+pytestmark = pytest.mark.gpu
+
+PATHS = [pytest.param(_lib.STEP_GENERIC, id="generic"), pytest.param(0, id="tiled")]
+
+
+def to_particles(arr):
+    return Particles(len(arr["x"]), **arr)
+
+
+def field_close(got, want, rtol=1e-10):
+    scale = np.abs(want).max()
+    return np.allclose(got, want, rtol=rtol, atol=rtol * scale)
+
+
+def compare_state(km, ok, theta_tol=1e-12):
+    """Particles by id, per mesh."""
+    for k, m in enumerate(km.meshes):
+        g = km.getParticles(m).sorted_by_id()
+        o = ok.sorted_parts(k)
+        assert g.n == len(o["x"]), f"mesh {k}: np {g.n} vs oracle {len(o['x'])}"
+        assert np.array_equal(g.id, o["id"])
+        for key in ("x", "y", "u", "v", "w", "mpw", "li", "lj", "dt"):
+            a, b = getattr(g, key), o[key]
+            assert np.array_equal(a, b, equal_nan=True), f"mesh {k} field {key}: {np.sum(a != b)} of {g.n} differ"
+        if m.domain_type == DomainType.XY:
+            assert np.array_equal(g.z, o["z"])
+        else:
+            assert np.allclose(g.z, o["z"], rtol=theta_tol, atol=1e-300)
+        assert np.array_equal(g.li.astype(np.int64), o["li"].astype(np.int64))
+        assert np.array_equal(g.lj.astype(np.int64), o["lj"].astype(np.int64))
+
+
+def compare_fields(km, ok):
+    for k in range(len(km.meshes)):
+        dep, raw = km.last_deposit[k], ok.raw[k]
+        for f in range(7):
+            assert field_close(dep[f], raw[f]), f"mesh {k} raw field {_lib.FIELD_NAMES[f]}"
+        assert np.array_equal(dep[7], raw[7]), "mpc (cell counts) must be exact"
+        for name in ("nd", "u", "v", "w", "count-sum", "u-sum", "uu-sum", "ww-sum", "mpc-sum"):
+            assert field_close(km.fields[k][name], ok.fields[k][name]), name
+    assert np.allclose([km.mass_sum, *km.momentum_sum, km.energy_sum], [ok.mass_sum, *ok.momentum_sum, ok.energy_sum], rtol=1e-10,
+                       atol=1e-10 * abs(ok.energy_sum))
+    assert km.n_exited == ok.n_exited
+    assert km.getNp() == ok.getNp()
+
+
+def make_pair(meshes, wl, arrays, flags, dom=None):
+    dom = meshes[0].domain_type if dom is None else dom
+    km = KineticMaterial("ion", wl.charge, wl.mass, meshes, dom, step_flags=flags)
+    ok = O.OracleKM(wl.charge, wl.mass, meshes)
+    km.dt = wl.dt
+    for k, arr in enumerate(arrays):
+        if arr is None:
+            continue
+        assert km.addParticles(meshes[k], to_particles(arr), wl.dt) == ok.addParticles(k, arr, wl.dt)
+    return km, ok
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("dom,bc", [(DomainType.XY, "periodic"), (DomainType.XY, "open"), (DomainType.XY, "symmetry"),
+                                    (DomainType.RZ, "beam"), (DomainType.RZ, "symmetry"), (DomainType.ZR, "open")])
+def test_move_and_deposit_match_oracle(dom, bc, flags):
+    m = S.make_mesh(67, 45, dom, 1e-3, bc)
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 42, vth_cells=0.7, kick_frac=0.1)
+    arr = wl.particles(0, 20000)
+    km, ok = make_pair([m], wl, [arr], flags)
+    with km:
+        compare_state(km, ok)  # injection: XtoL + -0.5dt rewind
+        for _ in range(5):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            compare_state(km, ok)
+            compare_fields(km, ok)
+        assert km.num_samples == ok.num_samples == 5
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_fast_particles_many_bounces_and_residual_dt(flags):
+    """CFL >> 1 on a tiny symmetric box: >10 bounces leaves dt > 0 that is added to the next step (KM:333, :360)."""
+    m = S.make_mesh(5, 4, DomainType.XY, 1e-3, "symmetry")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 9, vth_cells=25.0, kick_frac=0.05)
+    arr = wl.particles(0, 3000)
+    km, ok = make_pair([m], wl, [arr], flags)
+    with km:
+        for _ in range(4):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            compare_state(km, ok)
+            compare_fields(km, ok)
+        assert (ok.parts[0]["dt"] > 0).any(), "case must exercise the residual dt"
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_boris_rotation(flags):
+    m = S.make_mesh(33, 33, DomainType.XY, 1e-3, "periodic")
+    wl = S.Workload("t", m, 1e-9, -S.QE, 9.109e-31, 5, vth_cells=0.4, kick_frac=0.05)
+    m.bfi = np.full((33, 33), 0.02)
+    m.bfj = np.linspace(-0.01, 0.03, 33 * 33).reshape(33, 33)
+    arr = wl.particles(0, 5000)
+    km, ok = make_pair([m], wl, [arr], flags)
+    with km:
+        for _ in range(3):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            compare_state(km, ok)
+            compare_fields(km, ok)
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_mesh_handoff(flags):
+    """Two RZ meshes joined by MESH faces, different spacings: transfer sweeps (KM:131-142, :708-722)."""
+    a = UniformMesh(33, 33, (0.0, 0.0), (1e-3, 1e-3), DomainType.RZ)
+    b = UniformMesh(17, 41, (0.0, 32e-3), (2e-3, 0.5e-3), DomainType.RZ)
+    for mm in (a, b):
+        mm.setMeshBCType(Face.LEFT, BC.SYMMETRY)
+    for i in range(a.ni):
+        a.setNeighbor(Face.TOP, i, 0, 1)
+    for i in range(b.ni):
+        b.setNeighbor(Face.BOTTOM, i, 0, 0)
+    wl = S.Workload("t", a, 1e-7, S.QE, 16 * S.AMU, 11, vth_cells=0.3, drift_cells=(0.0, 0.9), kick_frac=0.0)
+    arr = wl.particles(0, 8000)
+    km, ok = make_pair([a, b], wl, [arr, None], flags)
+    with km:
+        for _ in range(30):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+        compare_state(km, ok)
+        compare_fields(km, ok)
+        assert km.getNp(b) == ok.getNp(1) > 0
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_slow_path_classification(flags):
+    """Particles whose substep bounding box touches a segment node are handed to the host untouched (KM:504-518)."""
+    m = S.make_mesh(40, 40, DomainType.XY, 1e-3, "open")
+    m.has_seg[18:22, 18:22] = 1
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 21, vth_cells=0.5, kick_frac=0.05)
+    arr = wl.particles(0, 10000)
+    km, ok = make_pair([m], wl, [arr], flags)
+    taken = {}
+    km.slow_path_handler = lambda k_, slow, extra: (taken.update(slow=slow, extra=extra), [])[1]
+    with km:
+        km.updateFields()
+        ok.updateFields(wl.dt)
+        compare_state(km, ok)
+        compare_fields(km, ok)
+        assert ok.slow and taken["slow"].n == sum(len(s[1]["x"]) for s in ok.slow)
+        g = taken["slow"]
+        order = np.argsort(g.id)
+        _mid, op, oaux = ok.slow[0]
+        oo = np.argsort(op["id"])
+        for key in ("x", "y", "z", "u", "v", "w", "li", "lj", "dt"):
+            assert np.array_equal(getattr(g, key)[order], op[key][oo]), key
+        for key in ("old_x", "old_y", "old_li", "old_lj", "bounces"):
+            assert np.array_equal(taken["extra"][key][order], oaux[key][oo]), key
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_injection_every_step_zero_weight_and_edges(flags):
+    m = S.make_mesh(30, 20, DomainType.XY, 1e-3, "open")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 33, vth_cells=0.8, kick_frac=0.1)
+    km, ok = make_pair([m], wl, [None], flags)
+    with km:
+        km.updateFields()  # empty store
+        ok.updateFields(wl.dt)
+        assert km.getNp() == 0
+        first = 0
+        for step in range(6):
+            arr = wl.particles(first, 1500)
+            first += 1500
+            if step == 2:
+                arr["mpw"][::7] = 0.0  # removed at the next move (KM:322)
+                arr["x"][:5] = m.x0[0] + (m.ni - 1) * m.dh[0]  # exactly on the plus edge: gather_safe, no deposit
+                arr["x"][5:8] = m.x0[0] + (m.ni + 2.5) * m.dh[0]  # beyond: lc clamp of KM:770-773
+            assert km.addParticles(m, to_particles(arr), wl.dt) == ok.addParticles(0, arr, wl.dt)
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            compare_state(km, ok)
+            compare_fields(km, ok)
+
+
+def test_download_upload_round_trip():
+    m = S.make_mesh(16, 16, DomainType.XY, 1e-3, "periodic")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 1)
+    arr = wl.particles(0, 1000)
+    km, ok = make_pair([m], wl, [arr], 0)
+    with km:
+        p = km.getParticles(m)
+        p.u[:] *= 2.0
+        km.setParticles(m, p)
+        q = km.getParticles(m)
+        assert np.array_equal(p.u, q.u) and np.array_equal(p.id, q.id)
+
+
+@pytest.mark.parametrize("n", [1 << 24])
+def test_full_size_properties_config_b(n):
+    """BASELINE config B at full size (512x512, 16M): size-independent properties instead of the oracle."""
+    wl = S.config_b()
+    m = wl.mesh
+    km = KineticMaterial("O+", wl.charge, wl.mass, [m], DomainType.XY, capacity_hint=n)
+    km.dt = wl.dt
+    with km:
+        chunk = 1 << 22
+        for first in range(0, n, chunk):
+            km.addParticles(m, to_particles(wl.particles(first, chunk)), wl.dt)
+        assert km.getNp() == n
+        for _ in range(3):
+            km.updateFields()
+        dep = km.last_deposit[0]
+        assert km.getNp() == n and km.n_exited == 0  # periodic box: nothing leaves
+        assert dep[7].sum() == n  # every particle counted once in mpc
+        w_total = n * wl.mpw
+        assert abs(dep[0].sum() - w_total) <= 1e-10 * w_total  # bilinear weights sum to 1
+        assert abs(km.mass_sum / wl.mass - w_total) <= 1e-10 * w_total
+        for f, s in ((1, km.momentum_sum[0]), (2, km.momentum_sum[1]), (3, km.momentum_sum[2])):
+            scale = wl.mpw * n * wl.vth
+            assert abs(dep[f].sum() - s / wl.mass) <= 1e-9 * scale  # checksum of checksums: sum_nodes U = sum_p mpw*u
+        p = km.getParticles(m)
+        lx = (m.ni - 1) * m.dh[0]
+        assert p.x.min() >= 0 and p.x.max() <= lx and p.y.min() >= 0 and p.y.max() <= lx
+        assert np.array_equal(np.sort(p.id), np.arange(n, dtype=np.int32))  # a permutation: nobody lost or duplicated

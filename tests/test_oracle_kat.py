@@ -1,0 +1,334 @@
+"""Pins the CPU oracle (oracle/sf_oracle.c).
+
+The reference ships no tests or golden vectors and no JVM exists in the image, so the
+oracle is "parity unpinned" against Java outputs.  It is pinned here by
+ (1) analytic known-answer tests derived from the Java source (SURVEY.md 8c list), and
+ (2) bit-for-bit agreement with an independent pure-Python restatement (tests/pyref.py) on randomized
+     cases covering XY / RZ / ZR, OPEN / SYMMETRY / PERIODIC / MESH faces, Boris, injection and the
+     segment slow-path classification.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import pyref
+from oracle import oracle as O
+from starfish_b200.domain import DomainBoundaryType as BC, DomainType, Face, UniformMesh
+from starfish_b200 import synthetic as S
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def mesh_xy(ni=9, nj=7, dh=(0.5, 0.25), x0=(1.0, -2.0), dom=DomainType.XY):
+    return UniformMesh(ni, nj, x0, dh, dom)
+
+
+def parts_from(d, n):
+    p = O.empty_parts(n)
+    for k, v in d.items():
+        p[k][:] = v
+    return p
+
+
+# ---------------------------------------------------------------- (1) analytic known answers
+def test_kat_free_flight_is_repeated_add():
+    """Zero field, XY: pos_n = pos_0 + n*(v*dt) accumulated by repeated addition, bit exact (KM:369-380)."""
+    m = mesh_xy(65, 65, (1e-3, 1e-3), (0, 0))
+    km = O.OracleKM(1.6e-19, 2.6e-26, [m])
+    x0, y0, u, v, w, dt = 0.0123, 0.0311, 812.5, -433.25, 91.0, 1e-7
+    km.addParticles(0, dict(x=[x0], y=[y0], z=[0.0], u=[u], v=[v], w=[w], mpw=[5.0]), dt)
+    ex, ey, ez = x0, y0, 0.0
+    for _ in range(25):
+        km.updateFields(dt)
+        ex += u * dt
+        ey += v * dt
+        ez += w * dt
+    p = km.parts[0]
+    assert p["x"][0] == ex and p["y"][0] == ey and p["z"][0] == ez
+    assert p["li"][0] == (ex - 0.0) / 1e-3 and p["lj"][0] == (ey - 0.0) / 1e-3
+    assert p["u"][0] == u and p["dt"][0] == 0.0
+
+
+def test_kat_uniform_field_leapfrog():
+    """Uniform E: injection rewinds by -0.5dt (KM:776-794), every step adds (q/m*E)*dt (KM:345-346)."""
+    m = mesh_xy(33, 33, (1e-3, 1e-3), (0, 0))
+    m.efi[:] = 250.0
+    m.efj[:] = -125.0
+    q, mass, dt = 1.602e-19, 2.6e-26, 1e-8
+    km = O.OracleKM(q, mass, [m])
+    km.addParticles(0, dict(x=[0.016], y=[0.016], z=[0.0], u=[10.0], v=[20.0], w=[30.0], mpw=[1.0]), dt)
+    qm = q / mass
+    # gather of a constant field returns the constant up to the rounding of the 4 weighted terms: use the oracle gather
+    ex = O.load().sfo_gather(m.efi.ctypes.data, 33, 33, 16.0, 16.0)
+    assert ex == 250.0  # weights (1,0,0,0)
+    u = 10.0 + qm * 250.0 * (-0.5 * dt)
+    v = 20.0 + qm * -125.0 * (-0.5 * dt)
+    assert km.parts[0]["u"][0] == u and km.parts[0]["v"][0] == v
+    x = 0.016
+    for _ in range(3):
+        km.updateFields(dt)
+        li, lj = km.parts[0]["li"][0], km.parts[0]["lj"][0]
+    # closed form within rounding: v_n = v_0 + (n - 1/2) a dt
+    assert math.isclose(km.parts[0]["u"][0], 10.0 + qm * 250.0 * 2.5 * dt, rel_tol=1e-14)
+    assert km.parts[0]["w"][0] == 30.0
+
+
+def test_kat_scatter_weights_node_and_centre():
+    m = mesh_xy()
+    ms = O.MeshSet([m])
+    lib = O.load()
+    d = np.zeros((m.ni, m.nj))
+    lib.sfo_scatter(d.ctypes.data, ms.arr[0], 3.0, 2.0, 7.0)  # on a node: weight 1 (F2D:290)
+    assert d[3, 2] == 7.0 and d.sum() == 7.0
+    d[:] = 0
+    lib.sfo_scatter(d.ctypes.data, ms.arr[0], 3.5, 2.5, 8.0)  # cell centre: 1/4 each
+    assert d[3, 2] == d[4, 2] == d[4, 3] == d[3, 3] == 2.0
+    d[:] = 0
+    for fi, fj in ((-1.5, 1.0), (1.0, -1.2), (m.ni - 1.0, 1.0), (1.0, m.nj - 1.0), (m.ni + 3.0, 1.0)):
+        lib.sfo_scatter(d.ctypes.data, ms.arr[0], fi, fj, 1.0)  # F2D:252 early return
+    assert d.sum() == 0.0
+    # (int) truncates toward zero: fi in (-1,0) is cell 0 with a negative weight, not an early return
+    lib.sfo_scatter(d.ctypes.data, ms.arr[0], -0.5, 1.0, 1.0)
+    assert d[0, 1] == 1.5 and d[1, 1] == -0.5
+
+
+def test_kat_scatter_rz_ruyten_hand_evaluated():
+    """F2D:269-276 for one particle, hand evaluated with Python floats in the Java evaluation order."""
+    m = mesh_xy(6, 5, (0.2, 0.1), (0.4, 0.0), DomainType.RZ)
+    ms = O.MeshSet([m])
+    fi, fj, val = 2.3, 1.6, 3.0
+    i, j = 2, 1
+    rp = 0.4 + (i + 1) * 0.2
+    rm = 0.4 + i * 0.2
+    r = 0.4 + fi * 0.2
+    di = 1 - (0.5 * (rp - r) * (2 * rp + 3 * rm - r) / (rp * rp - rm * rm))
+    dj = fj - j
+    d = np.zeros((m.ni, m.nj))
+    O.load().sfo_scatter(d.ctypes.data, ms.arr[0], fi, fj, val)
+    assert d[2, 1] == (1 - di) * (1 - dj) * val
+    assert d[3, 1] == di * (1 - dj) * val
+    assert d[3, 2] == di * dj * val
+    assert d[2, 2] == (1 - di) * dj * val
+    assert abs(d.sum() - val) < 1e-15 * 8
+    # ZR mirrors it on j
+    mz = mesh_xy(5, 6, (0.1, 0.2), (0.0, 0.4), DomainType.ZR)
+    msz = O.MeshSet([mz])
+    dz = np.zeros((mz.ni, mz.nj))
+    O.load().sfo_scatter(dz.ctypes.data, msz.arr[0], fj, fi, val)
+    assert np.array_equal(dz, d.T)
+
+
+def test_kat_gather_bilinear_and_safe_edge():
+    m = mesh_xy(5, 4)
+    lib = O.load()
+    d = np.arange(20, dtype=np.float64).reshape(5, 4) ** 2
+    fi, fj = 1.25, 2.5
+    di, dj = 0.25, 0.5
+    v = (1 - di) * (1 - dj) * d[1, 2]
+    v += di * (1 - dj) * d[2, 2]
+    v += di * dj * d[2, 3]
+    v += (1 - di) * dj * d[1, 3]
+    assert lib.sfo_gather(d.ctypes.data, 5, 4, fi, fj) == v
+    # plus edge: i == ni-1 -> IndexOutOfBounds in Java -> gather_safe (F2D:371-390) = edge node value
+    assert lib.sfo_gather(d.ctypes.data, 5, 4, 4.0, 1.0) == d[4, 1]
+    assert lib.sfo_gather(d.ctypes.data, 5, 4, 4.0, 1.5) == (1 - 0.5) * d[4, 1] + 0.5 * d[4, 2]
+    assert lib.sfo_gather(d.ctypes.data, 5, 4, 9.0, 7.0) == d[4, 3]
+    # (int) truncation toward zero: fi in (-1,0) has i = 0 and a negative weight, no exception
+    vv = (1 + 0.5) * 1.0 * d[0, 1]
+    vv += -0.5 * 1.0 * d[1, 1]
+    vv += -0.5 * 0.0 * d[1, 2]
+    vv += (1 + 0.5) * 0.0 * d[0, 2]
+    assert lib.sfo_gather(d.ctypes.data, 5, 4, -0.5, 1.0) == vv
+    assert lib.sfo_gather(d.ctypes.data, 5, 4, -1.5, 1.0) == d[0, 1]
+
+
+def test_kat_deposit_conserves_weight():
+    """Sum over nodes of the raw density equals the weight of the particles with 0 <= lc < n-1 (XY, RZ, ZR)."""
+    for dom in (DomainType.XY, DomainType.RZ, DomainType.ZR):
+        m = UniformMesh(17, 13, (0.05, 0.07), (1e-3, 2e-3), dom)
+        km = O.OracleKM(1.0, 1.0, [m])
+        n = 500
+        rng = np.random.default_rng(5)
+        li, lj = rng.uniform(0, 16, n), rng.uniform(0, 12, n)
+        arr = dict(x=m.x0[0] + li * m.dh[0], y=m.x0[1] + lj * m.dh[1], z=np.zeros(n), u=rng.normal(size=n), v=rng.normal(size=n),
+                   w=rng.normal(size=n), mpw=rng.uniform(1, 2, n))
+        km.addParticles(0, arr, 0.0)
+        km.deposit()
+        assert math.isclose(km.raw[0][0].sum(), arr["mpw"].sum(), rel_tol=1e-13)
+        assert km.raw[0][7].sum() == n
+        # increments of the sample pass equal the deposit pass (multiplication commutes)
+        assert np.array_equal(km.sample_pass[0], km.raw[0][0])
+        for f in (1, 2, 3):
+            assert np.array_equal(km.sample_pass[f], km.raw[0][f])
+
+
+def test_kat_rz_rotation_invariants():
+    """rotateToRZ: R^2 = A^2+B^2 and vel[r]^2+vel[2]^2 is preserved (KM:424-442)."""
+    m = UniformMesh(40, 40, (0, 0), (1e-3, 1e-3), DomainType.RZ)
+    km = O.OracleKM(1.0, 1.0, [m])
+    dt = 1e-7
+    km.addParticles(0, dict(x=[0.011], y=[0.02], z=[0.0], u=[300.0], v=[-100.0], w=[2500.0], mpw=[1.0]), dt)
+    A, B = 2500.0 * dt, 0.011 + 300.0 * dt
+    km.updateFields(dt)
+    p = km.parts[0]
+    assert p["x"][0] == math.sqrt(A * A + B * B)
+    assert math.isclose(p["u"][0] ** 2 + p["w"][0] ** 2, 300.0 ** 2 + 2500.0 ** 2, rel_tol=1e-14)
+    assert math.isclose(p["z"][0], -math.asin(A / math.sqrt(A * A + B * B)), rel_tol=1e-14)
+    assert p["v"][0] == -100.0
+
+
+def test_kat_symmetry_bounce_mirrors_trajectory():
+    """A particle reflected by a SYMMETRY face at LEFT ends where the unmirrored one would, mirrored (KM:692-696)."""
+    m = UniformMesh(11, 11, (0, 0), (1.0, 1.0))
+    m.setMeshBCType(Face.LEFT, BC.SYMMETRY)
+    km = O.OracleKM(1.0, 1.0, [m])
+    km.addParticles(0, dict(x=[0.25], y=[5.0], z=[0.0], u=[-1.0], v=[0.5], w=[0.25], mpw=[1.0]), 1.0)
+    km.updateFields(1.0)
+    p = km.parts[0]
+    assert km.getNp() == 1
+    assert p["u"][0] == 1.0 and p["v"][0] == 0.5 and p["w"][0] == 0.25
+    assert math.isclose(p["x"][0], 0.75, rel_tol=1e-15) and math.isclose(p["y"][0], 5.5, rel_tol=1e-15)
+
+
+def test_kat_open_exit_count_of_a_beam():
+    """Cold beam toward an OPEN face: particle k leaves at the step its position passes n-1 (KM:606, :690)."""
+    m = UniformMesh(11, 5, (0, 0), (1.0, 1.0))
+    km = O.OracleKM(1.0, 1.0, [m])
+    n = 10
+    xs = np.arange(n) + 0.5  # 0.5 .. 9.5, right boundary at 10
+    km.addParticles(0, dict(x=xs, y=np.full(n, 2.0), z=np.zeros(n), u=np.full(n, 1.0), v=np.zeros(n), w=np.zeros(n), mpw=np.ones(n)), 1.0)
+    for step in range(1, 12):
+        km.updateFields(1.0)
+        assert km.getNp() == max(0, n - step)
+        assert km.n_exited == (1 if step <= n else 0)
+
+
+def test_kat_periodic_wrap_keeps_stale_lc():
+    """PERIODIC shifts pos by the domain length and leaves lc on the exit edge until the next substep (KM:697-707)."""
+    m = UniformMesh(11, 11, (0, 0), (1.0, 1.0))
+    for f in Face:
+        m.setMeshBCType(f, BC.PERIODIC)
+    km = O.OracleKM(1.0, 1.0, [m])
+    km.addParticles(0, dict(x=[9.5], y=[5.0], z=[0.0], u=[1.0], v=[0.0], w=[0.0], mpw=[1.0]), 1.0)
+    km.updateFields(1.0)
+    p = km.parts[0]
+    assert km.getNp() == 1 and p["x"][0] == 0.5 and p["li"][0] == 0.5 and p["dt"][0] == 0.0
+
+
+def test_kat_mirror_and_boris():
+    lib = O.load()
+    v = np.array([3.0, -2.0, 0.5])
+    n = np.array([0.0, -1.0, 0.0])
+    lib.sfo_mirror(_dp(v), _dp(n))
+    assert list(v) == [3.0, 2.0, 0.5]
+    # Boris with E = 0 preserves |v|
+    vel = np.array([1.0e3, -2.0e3, 5.0e2])
+    E = np.zeros(3)
+    B = np.array([0.01, -0.02, 0.0])
+    s0 = float(np.sqrt((vel ** 2).sum()))
+    lib.sfo_boris(9.58e7, 1e-9, _dp(E), _dp(B), _dp(vel))
+    assert math.isclose(float(np.sqrt((vel ** 2).sum())), s0, rel_tol=1e-13)
+    # against the pure-Python statement of KM:847-893
+    km = pyref.KM(9.58e7, 1.0, [])
+    part = pyref.Particle([0, 0, 0], [1.0e3, -2.0e3, 5.0e2], 1.0)
+    part.dt = 1e-9
+    km.boris(part, [12.0, -7.0, 0.0], list(B))
+    vel = np.array([1.0e3, -2.0e3, 5.0e2])
+    lib.sfo_boris(9.58e7, 1e-9, _dp(np.array([12.0, -7.0, 0.0])), _dp(B), _dp(vel))
+    assert list(vel) == part.vel
+
+
+# ---------------------------------------------------------------- (2) oracle == independent Python restatement
+def _py_mesh(m):
+    pm = pyref.Mesh(m.ni, m.nj, m.x0, m.dh, int(m.domain_type))
+    for f in range(4):
+        pm.bc[f] = [int(v) for v in m.bc[f]]
+        pm.nbr[f] = [[None if v < 0 else int(v) for v in row] for row in m.nbr[f]]
+    pm.has_seg = m.has_seg.tolist()
+    pm.Efi = pyref.Field(pm, m.efi)
+    pm.Efj = pyref.Field(pm, m.efj)
+    if m.bfi is not None:
+        pm.Bfi = pyref.Field(pm, m.bfi)
+        pm.Bfj = pyref.Field(pm, m.bfj)
+    return pm
+
+
+def _compare(km, pk, nmesh):
+    for k in range(nmesh):
+        po = km.sorted_parts(k)
+        pp = sorted(pk.particles[k], key=lambda q: q.id)
+        assert len(pp) == len(po["x"])
+        for a, q in enumerate(pp):
+            got = (po["x"][a], po["y"][a], po["z"][a], po["u"][a], po["v"][a], po["w"][a], po["li"][a], po["lj"][a], po["dt"][a])
+            want = (q.pos[0], q.pos[1], q.pos[2], q.vel[0], q.vel[1], q.vel[2], q.lc[0], q.lc[1], q.dt)
+            for g, w_ in zip(got, want):
+                assert g == w_ or (g != g and w_ != w_), (k, a, got, want)
+        raw = np.array(pk.raw[k])
+        # same arithmetic, but the oracle walks particles in store order and the Python lists in theirs
+        assert np.allclose(km.raw[k], raw, rtol=1e-12, atol=0)
+        assert np.array_equal(km.raw[k][7], raw[7])
+
+
+def _run_pair(meshes, charge, mass, dt, arrays_per_mesh, steps, check_sums=True):
+    km = O.OracleKM(charge, mass, meshes)
+    pk = pyref.KM(charge, mass, [_py_mesh(m) for m in meshes])
+    for k, arr in enumerate(arrays_per_mesh):
+        if arr is None:
+            continue
+        km.addParticles(k, arr, dt)
+        for q in range(len(arr["x"])):
+            pk.addParticle(k, pyref.Particle([arr["x"][q], arr["y"][q], arr["z"][q]], [arr["u"][q], arr["v"][q], arr["w"][q]],
+                                             arr["mpw"][q]), dt)
+    for _ in range(steps):
+        km.updateFields(dt)
+        pk.updateFields(dt)
+        _compare(km, pk, len(meshes))
+        assert km.n_exited == pk.n_exited
+        if check_sums and len(meshes) == 1:
+            assert list(km.sums5) == pk.sums
+        assert sum(len(s[1]["x"]) for s in km.slow) == len(pk.slow)
+    return km, pk
+
+
+@pytest.mark.parametrize("dom", [DomainType.XY, DomainType.RZ, DomainType.ZR])
+@pytest.mark.parametrize("bc", ["periodic", "open", "symmetry"])
+def test_oracle_matches_python_restatement(dom, bc):
+    if bc == "periodic" and dom != DomainType.XY:
+        pytest.skip("periodic axis is not meaningful in axisymmetric runs")
+    m = S.make_mesh(12, 10, dom, 1e-3, bc)
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 77, vth_cells=0.9, kick_frac=0.2)
+    arr = wl.particles(0, 300)
+    _run_pair([m], wl.charge, wl.mass, wl.dt, [arr], 6)
+
+
+def test_oracle_matches_python_restatement_boris_and_segments():
+    m = S.make_mesh(10, 10, DomainType.XY, 1e-3, "symmetry")
+    wl = S.Workload("t", m, 1e-7, -S.QE, 9.109e-31 * 2000, 3, vth_cells=0.5, kick_frac=0.1)
+    m.bfi = np.full((10, 10), 0.02)
+    m.bfj = np.linspace(-0.01, 0.03, 100).reshape(10, 10)
+    m.has_seg[4:6, 4:6] = 1
+    m.bc[int(Face.TOP)][:] = int(BC.CIRCUIT)
+    arr = wl.particles(0, 200)
+    km, pk = _run_pair([m], wl.charge, wl.mass, wl.dt, [arr], 4)
+    assert km.slow, "the segment box must have caught particles"
+
+
+def test_oracle_matches_python_restatement_mesh_handoff():
+    """Two RZ meshes side by side in z (j): MESH faces hand particles over (KM:708-722, :131-142)."""
+    a = UniformMesh(9, 9, (0.0, 0.0), (1e-3, 1e-3), DomainType.RZ)
+    b = UniformMesh(5, 9, (0.0, 8e-3), (2e-3, 0.5e-3), DomainType.RZ)
+    a.setMeshBCType(Face.LEFT, BC.SYMMETRY)
+    b.setMeshBCType(Face.LEFT, BC.SYMMETRY)
+    for i in range(a.ni):
+        a.setNeighbor(Face.TOP, i, 0, 1)
+    for i in range(b.ni):
+        b.setNeighbor(Face.BOTTOM, i, 0, 0)
+    wl = S.Workload("t", a, 1e-7, S.QE, 16 * S.AMU, 11, vth_cells=0.3, drift_cells=(0.0, 0.9), kick_frac=0.0)
+    arr = wl.particles(0, 150)
+    arr["x"] = np.abs(arr["x"]) * 0.8 + 1e-5
+    km, pk = _run_pair([a, b], wl.charge, wl.mass, wl.dt, [arr, None], 12, check_sums=False)
+    assert km.getNp(1) > 0, "particles must have crossed into the second mesh"
