@@ -68,7 +68,8 @@ extern "C" {
                                        moved by the transfer sweeps of the next sfgpu_step          */
 
 /* sfgpu_step flags */
-#define SFGPU_STEP_GENERIC 1u  /* force the generic (untiled, global-atomic) kernels            */
+#define SFGPU_STEP_GENERIC 1u  /* cross-check mode: no cell sort, no warp tiles; every particle gathers
+                                  and deposits straight from / to global memory (FP64 REDs)         */
 #define SFGPU_STEP_DEFER_FINISH 2u /* do not close the step: the host still has slow-path survivors to
                                       re-inject (SFGPU_INJECT_DEPOSIT_NOW); it calls sfgpu_finish_step */
 
@@ -170,6 +171,8 @@ int sfgpu_upload(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t first, con
 
 /* explicit cell sort + compaction (sortParticlesToCells, KM:1150-1179: order only, no result change) */
 int sfgpu_sort(sfgpu_ctx *ctx, int32_t sp);
+/* sfgpu_step re-sorts the store by cell every `steps` steps (default 4, env SFGPU_SORT_EVERY) */
+int sfgpu_set_sort_interval(sfgpu_ctx *ctx, int32_t steps);
 
 /* ---- multi GPU: particles are partitioned over contexts, meshes replicated ------------- */
 /* 128-byte NCCL unique id, created on one rank and distributed by the host */

@@ -55,6 +55,7 @@ EXPORTS = {
     "sfgpu_download": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(Particles)]),
     "sfgpu_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(Particles)]),
     "sfgpu_sort": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sfgpu_set_sort_interval": (C.c_int, [C.c_void_p, C.c_int32]),
     "sfgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
     "sfgpu_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "sfgpu_deposit_device_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),

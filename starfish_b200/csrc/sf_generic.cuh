@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256)
 k_generic_step(const MeshDev *__restrict__ meshes, int mesh_id, double qm, double charge, double dt, int transfer,
                RecPtrs in, unsigned long long n_in, RecPtrs out, unsigned long long *__restrict__ out_cursor,
                unsigned long long out_cap, const XferDev *__restrict__ xfer, SlowPtrs slow, double *__restrict__ dep,
-               StepCounters *__restrict__ c)
+               StepCounters *__restrict__ c, FastPtrs fs, unsigned long long fast_cap)
 {
     const MeshDev m = meshes[mesh_id];
     const GlobalFieldGather fg;
@@ -102,8 +102,21 @@ k_generic_step(const MeshDev *__restrict__ meshes, int mesh_id, double qm, doubl
                 sE += p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w);
             }
         }
-        const unsigned long long slot = warp_claim(out_cursor, alive);
-        if (alive) {
+        // a survivor that is a normal particle again (lc == XtoL(pos), dt == 0) moves to the fast store's tail
+        bool to_fast = alive && exact && p.dt == 0 && p.mpw == p.mpw && fast_cap > 0;
+        const unsigned long long fslot = warp_claim(&c->fast_n[mesh_id], to_fast);
+        if (to_fast && fslot >= fast_cap) to_fast = false;
+        if (to_fast) {
+            fs.x[fslot] = p.x; fs.y[fslot] = p.y; fs.z[fslot] = p.z;
+            fs.u[fslot] = p.u; fs.v[fslot] = p.v; fs.w[fslot] = p.w;
+            fs.mpw[fslot] = p.mpw;
+            fs.tag[fslot] = tag;
+        }
+        const unsigned nfast = __ballot_sync(0xffffffffu, to_fast);
+        if ((threadIdx.x & 31) == 0 && nfast) atomicAdd((unsigned long long *)&c->fast_delta[mesh_id], (unsigned long long)__popc(nfast));
+        const bool to_rec = alive && !to_fast;
+        const unsigned long long slot = warp_claim(out_cursor, to_rec);
+        if (to_rec) {
             if (slot < out_cap) rec_store(out, slot, p, tag);
             else atomicAdd(&c->overflow, 1ULL);
         }

@@ -6,12 +6,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <dlfcn.h>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/sfgpu.h"
+#include <cub/device/device_scan.cuh>
+
+#include "sf_fast.cuh"
 #include "sf_generic.cuh"
 #include "sf_store.cuh"
 
@@ -93,6 +97,35 @@ static void rec_bind(Records &r, char *slab, int64_t cap)
     r.cap = cap;
 }
 
+struct FastStore { // cell-sorted SoA store of the normal particles of one species on one mesh
+    FastPtrs p{}, alt{};
+    char *slab = nullptr, *alt_slab = nullptr;
+    int64_t cap = 0, alt_cap = 0;
+    int64_t n = 0;        // physical length (vacant slots included)
+    int64_t n_sorted = 0; // prefix covered by the work items of the last sort
+    int64_t alive = 0;    // live particles
+    bool dirty = false;   // has vacant slots
+    int steps_since_sort = 0;
+    unsigned *keys = nullptr, *ranks = nullptr; // per particle, sort scratch
+    int64_t kr_cap = 0;
+    unsigned *hist = nullptr, *offs = nullptr;  // per cell key (+1)
+    WorkItem *items = nullptr;
+    unsigned *d_nitems = nullptr;
+    unsigned max_items = 0, n_items = 0;
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    int nti = 0, ntj = 0;
+    unsigned nkeys = 0;
+};
+
+static void fast_bind(FastPtrs &p, char *slab, int64_t cap)
+{
+    double **arr[7] = {&p.x, &p.y, &p.z, &p.u, &p.v, &p.w, &p.mpw};
+    for (int k = 0; k < 7; k++) *arr[k] = (double *)(slab + (size_t)k * cap * sizeof(double));
+    p.tag = (int2 *)(slab + (size_t)7 * cap * sizeof(double));
+}
+#define SF_FAST_BYTES_PER_PARTICLE (7 * sizeof(double) + sizeof(int2))
+
 struct MeshHost {
     MeshDev dev{}; // device pointers inside
     int8_t *bc[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -104,7 +137,8 @@ struct MeshHost {
 };
 
 struct Pop { // one species on one mesh: MeshData, KM:1314-1427
-    Records cur, nxt;  // particle_block lists (this step / next step)
+    FastStore fast;    // normal particles (the bulk)
+    Records cur, nxt;  // exceptional particles as full records (this step / next step)
     Records xin, xout; // transfer_particles (being moved / being filled)
     double *dep = nullptr; // packed [SFGPU_NFIELDS][ni][nj] raw per-step deposit
 };
@@ -142,6 +176,10 @@ struct sfgpu_ctx {
     int nranks = 1, rank = 0;
     int last_launches = 0;
     bool timing_valid = false;
+    int sort_every = 4;      // steps between cell sorts of the fast store
+    int fast_grid = 0;       // CTAs of the tiled kernel (persistent)
+    Records tmp;             // staging records for download / upload of the fast store
+    unsigned long long last_fallback = 0, last_flush = 0;
     std::string err;
 };
 
@@ -199,6 +237,132 @@ static int stage_reserve(sfgpu_ctx *ctx, size_t bytes)
     CU(cudaMallocHost(&ctx->stage, want));
     ctx->stage_bytes = want;
     return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// fast store
+// ---------------------------------------------------------------------------------------------
+static int fast_reserve(sfgpu_ctx *ctx, FastStore &f, int64_t need)
+{
+    if (need <= f.cap) return 0;
+    int64_t cap = f.cap + f.cap / 4;
+    if (cap < need) cap = need;
+    if (cap < 4096) cap = 4096;
+    cap = (cap + 255) & ~int64_t(255);
+    char *slab = nullptr;
+    CU(cudaMalloc(&slab, (size_t)cap * SF_FAST_BYTES_PER_PARTICLE));
+    FastPtrs np_{};
+    fast_bind(np_, slab, cap);
+    if (f.n > 0) {
+        const double *src[7] = {f.p.x, f.p.y, f.p.z, f.p.u, f.p.v, f.p.w, f.p.mpw};
+        double *dst[7] = {np_.x, np_.y, np_.z, np_.u, np_.v, np_.w, np_.mpw};
+        for (int k = 0; k < 7; k++)
+            CU(cudaMemcpyAsync(dst[k], src[k], (size_t)f.n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(np_.tag, f.p.tag, (size_t)f.n * sizeof(int2), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (f.slab) CU(cudaFree(f.slab));
+    f.slab = slab;
+    f.p = np_;
+    f.cap = cap;
+    return 0;
+}
+
+static void fast_free(FastStore &f)
+{
+    void *ptrs[] = {f.slab, f.alt_slab, f.keys, f.ranks, f.hist, f.offs, f.items, f.d_nitems, f.cub_tmp};
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    f = FastStore();
+}
+
+static int fast_init_geometry(sfgpu_ctx *ctx, FastStore &f, const MeshDev &m)
+{
+    f.nti = (m.ni - 1 + SF_TILE - 1) / SF_TILE;
+    f.ntj = (m.nj - 1 + SF_TILE - 1) / SF_TILE;
+    f.nkeys = (unsigned)f.nti * f.ntj * SF_TILE * SF_TILE;
+    CU(cudaMalloc(&f.hist, ((size_t)f.nkeys + 1) * sizeof(unsigned)));
+    CU(cudaMalloc(&f.offs, ((size_t)f.nkeys + 1) * sizeof(unsigned)));
+    CU(cudaMalloc(&f.d_nitems, sizeof(unsigned)));
+    CU(cudaMemset(f.d_nitems, 0, sizeof(unsigned)));
+    f.cub_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, f.cub_bytes, f.hist, f.offs, (int)(f.nkeys + 1), ctx->stream));
+    CU(cudaMalloc(&f.cub_tmp, f.cub_bytes ? f.cub_bytes : 16));
+    return 0;
+}
+
+// K3: counting sort of the fast store by cell key (tile-major) + compaction of vacant slots, out of place;
+// rebuilds the work items of the tiled kernel.  sortParticlesToCells (KM:1150-1179) is the closest reference
+// member: order only, no result changes beyond summation order.
+static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
+{
+    f.steps_since_sort = 0;
+    if (f.n == 0) {
+        f.n_sorted = 0; f.n_items = 0; f.dirty = false;
+        CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
+        return 0;
+    }
+    if ((uint64_t)f.n >= 0xfffffff0ull) return fail(ctx, SFGPU_EINVAL, "more than 2^32 particles of one species on one GPU mesh are not supported");
+    if (f.alt_cap < f.cap) {
+        if (f.alt_slab) CU(cudaFree(f.alt_slab));
+        f.alt_slab = nullptr; f.alt_cap = 0;
+        CU(cudaMalloc(&f.alt_slab, (size_t)f.cap * SF_FAST_BYTES_PER_PARTICLE));
+        f.alt_cap = f.cap;
+        fast_bind(f.alt, f.alt_slab, f.alt_cap);
+    }
+    if (f.kr_cap < f.n) {
+        if (f.keys) CU(cudaFree(f.keys));
+        if (f.ranks) CU(cudaFree(f.ranks));
+        f.keys = f.ranks = nullptr; f.kr_cap = 0;
+        CU(cudaMalloc(&f.keys, (size_t)f.cap * sizeof(unsigned)));
+        CU(cudaMalloc(&f.ranks, (size_t)f.cap * sizeof(unsigned)));
+        f.kr_cap = f.cap;
+    }
+    const unsigned want_items = (unsigned)(f.n / SF_ITEM_MAX + (int64_t)f.nti * f.ntj + 1);
+    if (f.max_items < want_items) {
+        if (f.items) CU(cudaFree(f.items));
+        f.items = nullptr; f.max_items = 0;
+        CU(cudaMalloc(&f.items, (size_t)want_items * sizeof(WorkItem)));
+        f.max_items = want_items;
+    }
+    const unsigned grid = (unsigned)((f.n + 255) / 256);
+    CU(cudaMemsetAsync(f.hist, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
+    k_sort_count<<<grid, 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, (unsigned long long)f.n, f.ntj, f.hist, f.keys, f.ranks);
+    CU(cudaGetLastError());
+    CU(cub::DeviceScan::ExclusiveSum(f.cub_tmp, f.cub_bytes, f.hist, f.offs, (int)(f.nkeys + 1), ctx->stream));
+    k_sort_scatter<<<grid, 256, 0, ctx->stream>>>(f.p, f.alt, (unsigned long long)f.n, f.offs, f.keys, f.ranks);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
+    const int n_tiles = f.nti * f.ntj;
+    k_build_items<<<(n_tiles + 127) / 128, 128, 0, ctx->stream>>>(f.offs, n_tiles, f.items, f.d_nitems, f.max_items);
+    CU(cudaGetLastError());
+    ctx->launch_total += 4; // count, scan (cub: counted as one), scatter, build_items
+    ctx->last_launches += 4;
+    unsigned tot[2] = {0, 0};
+    CU(cudaMemcpyAsync(&tot[0], f.offs + f.nkeys, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&tot[1], f.d_nitems, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if ((int64_t)tot[0] != f.alive)
+        return fail(ctx, SFGPU_ESTATE, "internal: sort kept %u particles, store tracked %lld", tot[0], (long long)f.alive);
+    std::swap(f.p, f.alt);
+    std::swap(f.slab, f.alt_slab);
+    std::swap(f.cap, f.alt_cap);
+    f.n = f.n_sorted = (int64_t)tot[0];
+    f.n_items = tot[1] < f.max_items ? tot[1] : f.max_items;
+    f.dirty = false;
+    return 0;
+}
+
+static FastStepArgs fast_args(sfgpu_ctx *ctx, Species &s, int m, double dt, const SlowPtrs &slow)
+{
+    Pop &pop = s.pops[m];
+    FastStepArgs a{};
+    a.meshes = ctx->d_meshes; a.mesh_id = m; a.qm = s.qm; a.charge = s.charge; a.dt = dt;
+    a.fs = pop.fast.p; a.items = pop.fast.items; a.n_items = pop.fast.d_nitems; a.ntj = pop.fast.ntj;
+    a.exc = pop.nxt.p; a.exc_cap = (unsigned long long)pop.nxt.cap;
+    a.xfer = ctx->d_xfer; a.slow = slow; a.dep = pop.dep; a.c = ctx->d_cnt;
+    return a;
 }
 
 static int sync_meshes(sfgpu_ctx *ctx)
@@ -270,6 +434,13 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
         CU(cudaMallocHost(&ctx->h_cnt, sizeof(StepCounters)));
         CU(cudaMalloc(&ctx->d_xfer, sizeof(XferDev) * SF_MAX_MESHES));
+        if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
+        CU(cudaFuncSetAttribute(k_fast_step, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
+        int nsm = 0, per_sm = 0;
+        CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_step, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
+        if (per_sm < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
+        ctx->fast_grid = nsm * per_sm;
         // bit-parity self test: a*b+c must round twice
         double *d = nullptr, h = 0;
         CU(cudaMalloc(&d, sizeof(double)));
@@ -301,6 +472,7 @@ extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
     for (auto &s : ctx->species) {
         for (auto &p : s.pops) {
             rec_free(p.cur); rec_free(p.nxt); rec_free(p.xin); rec_free(p.xout);
+            fast_free(p.fast);
             if (p.dep) cudaFree(p.dep);
         }
         rec_free(s.slow);
@@ -316,6 +488,7 @@ extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
         if (m.fields) cudaFree(m.fields);
         if (m.node_vol) cudaFree(m.node_vol);
     }
+    rec_free(ctx->tmp);
     if (ctx->d_meshes) cudaFree(ctx->d_meshes);
     if (ctx->d_cnt) cudaFree(ctx->d_cnt);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
@@ -445,6 +618,8 @@ extern "C" int sfgpu_species_add(sfgpu_ctx *ctx, double charge, double mass, int
         const size_t plane = (size_t)ctx->meshes[k].dev.ni * ctx->meshes[k].dev.nj;
         CU(cudaMalloc(&s.pops[k].dep, SFGPU_NFIELDS * plane * sizeof(double)));
         CU(cudaMemset(s.pops[k].dep, 0, SFGPU_NFIELDS * plane * sizeof(double)));
+        int rc = fast_init_geometry(ctx, s.pops[k].fast, ctx->meshes[k].dev);
+        if (rc) return rc;
     }
     ctx->species.push_back(s);
     *sp = (int)ctx->species.size() - 1;
@@ -536,6 +711,66 @@ static int download_records(sfgpu_ctx *ctx, const RecPtrs &r, int64_t first, con
     return 0;
 }
 
+
+// bulk addParticle into the fast store (the common case: lc == null, KM:760-774): chunks of 1M through the
+// pinned stage, k_inject_fast applies XtoL + the -0.5dt rewind; the rare particle the fast store cannot
+// represent lands in the record list.
+static int inject_fast(sfgpu_ctx *ctx, Species &s, int mesh_id, const sfgpu_particles *p, double dt_step, uint32_t flags, int64_t *n_added)
+{
+    Pop &pop = s.pops[mesh_id];
+    FastStore &f = pop.fast;
+    const int64_t chunk = 1 << 20;
+    int64_t want = f.n + p->n;
+    if (f.n == 0 && s.capacity_hint > want) want = s.capacity_hint;
+    int rc = fast_reserve(ctx, f, want);
+    if (rc) return rc;
+    rc = stage_reserve(ctx, (size_t)chunk * SF_FAST_BYTES_PER_PARTICLE);
+    if (rc) return rc;
+    const bool assign_ids = p->id == nullptr;
+    const double *src[7] = {p->x, p->y, p->z, p->u, p->v, p->w, p->mpw};
+    double *dst[7] = {f.p.x, f.p.y, f.p.z, f.p.u, f.p.v, f.p.w, f.p.mpw};
+    int64_t added = 0;
+    for (int64_t off = 0; off < p->n; off += chunk) {
+        const int64_t c = (p->n - off < chunk) ? p->n - off : chunk;
+        rc = rec_reserve(ctx, pop.cur, pop.cur.n + c, true);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream)); // stage reuse
+        for (int k = 0; k < 7; k++) {
+            double *st = (double *)ctx->stage + (size_t)k * chunk;
+            memcpy(st, src[k] + off, (size_t)c * sizeof(double));
+            CU(cudaMemcpyAsync(dst[k] + f.n, st, (size_t)c * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        int2 *tg = (int2 *)((double *)ctx->stage + (size_t)7 * chunk);
+        for (int64_t q = 0; q < c; q++) {
+            tg[q].x = assign_ids ? (int32_t)(s.id_counter + off + q) : p->id[off + q];
+            tg[q].y = p->born_it ? p->born_it[off + q] : 0;
+        }
+        CU(cudaMemcpyAsync(f.p.tag + f.n, tg, (size_t)c * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(&ctx->d_cnt->n_bad, 0, sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(&ctx->d_cnt->n_exc[mesh_id], 0, sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(&ctx->d_cnt->overflow, 0, sizeof(unsigned long long), ctx->stream));
+        k_inject_fast<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, s.qm, dt_step, (flags & SFGPU_INJECT_REWIND) ? 1 : 0,
+                                                                               f.p, (unsigned long long)f.n, (unsigned long long)c, pop.cur.p,
+                                                                               (unsigned long long)pop.cur.n, (unsigned long long)pop.cur.cap, ctx->d_cnt);
+        ctx->launch_total++;
+        CU(cudaGetLastError());
+        int rc2 = 0;
+        CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(StepCounters), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_cnt->overflow) return fail(ctx, SFGPU_EOVERFLOW, "internal: record list overflow during injection");
+        (void)rc2;
+        const int64_t n_exc = (int64_t)ctx->h_cnt->n_exc[mesh_id], n_bad = (int64_t)ctx->h_cnt->n_bad;
+        pop.cur.n += n_exc;
+        f.n += c;
+        f.alive += c - n_exc - n_bad;
+        if (n_exc || n_bad) f.dirty = true;
+        added += c - n_bad;
+    }
+    if (assign_ids) s.id_counter += (int32_t)p->n; // KM:797
+    if (n_added) *n_added = added;
+    return 0;
+}
+
 extern "C" int sfgpu_inject(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const sfgpu_particles *p, double dt_step,
                             uint32_t flags, int64_t *n_added)
 {
@@ -553,11 +788,11 @@ extern "C" int sfgpu_inject(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const s
     if (rc) return rc;
     Species &s = ctx->species[sp];
     Pop &pop = s.pops[mesh_id];
+    if (!p->li && !p->dt && !(flags & (SFGPU_INJECT_TRANSFER | SFGPU_INJECT_DEPOSIT_NOW)))
+        return inject_fast(ctx, s, mesh_id, p, dt_step, flags, n_added);
     Records &r = (flags & SFGPU_INJECT_TRANSFER) ? pop.xout : pop.cur;
     const int64_t first = r.n;
-    int64_t want = first + p->n;
-    if (first == 0 && s.capacity_hint > want) want = s.capacity_hint;
-    rc = rec_reserve(ctx, r, want, true);
+    rc = rec_reserve(ctx, r, first + p->n, true);
     if (rc) return rc;
     const bool assign_ids = p->id == nullptr;
     rc = upload_records(ctx, r, first, p, s.id_counter, assign_ids);
@@ -645,10 +880,12 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     const int nmesh = (int)ctx->meshes.size();
     if (s.slow_n) return fail(ctx, SFGPU_ESTATE, "take the slow-path particles of the previous step first");
     if (s.step_open) return fail(ctx, SFGPU_ESTATE, "previous step was deferred: call sfgpu_finish_step first");
+    const bool untiled = (flags & SFGPU_STEP_GENERIC) != 0;
+    ctx->last_launches = 0;
     int64_t n_total = 0;
     bool needs_slow = false;
     for (int m = 0; m < nmesh; m++) {
-        n_total += s.pops[m].cur.n;
+        n_total += s.pops[m].cur.n + s.pops[m].fast.alive;
         needs_slow = needs_slow || ctx->meshes[m].needs_slow;
     }
     if (needs_slow) {
@@ -666,37 +903,72 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         rc = push_xfer_table(ctx, s);
         if (rc) return rc;
     }
-    ctx->last_launches = 0;
-    CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
-    // pre-seed the transfer cursors with particles the host put on the transfer lists
-    if (multi) {
-        unsigned long long pre[SF_MAX_MESHES] = {0};
-        bool any = false;
-        for (int m = 0; m < nmesh; m++) {
-            pre[m] = (unsigned long long)s.pops[m].xout.n;
-            any = any || pre[m];
-        }
-        if (any) {
-            CU(cudaMemcpyAsync(ctx->d_cnt->xfer_n, pre, sizeof(unsigned long long) * nmesh, cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
+    // K3: periodic cell sort + compaction of the fast store (keeps the tiled kernel's accesses coherent)
+    for (int m = 0; m < nmesh; m++) {
+        FastStore &f = s.pops[m].fast;
+        if (untiled || f.n == 0) continue;
+        const int64_t tail = f.n - f.n_sorted;
+        if (f.n_sorted == 0 || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n) {
+            rc = fast_sort(ctx, m, f);
+            if (rc) return rc;
         }
     }
+    for (int m = 0; m < nmesh; m++) {
+        Pop &pop = s.pops[m];
+        // room for every record survivor plus fast-store particles that turn exceptional in this step
+        const int64_t exc_room = pop.fast.alive < (1 << 20) ? pop.fast.alive : (1 << 20) + pop.fast.alive / 8;
+        rc = rec_reserve(ctx, pop.nxt, pop.cur.n + exc_room + 1024, false);
+        if (rc) return rc;
+        // records that are normal particles again move to the fast store's tail
+        if (pop.cur.n > 0 || multi) {
+            rc = fast_reserve(ctx, pop.fast, pop.fast.n + pop.cur.n + (multi ? n_total : 0));
+            if (rc) return rc;
+        }
+    }
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
+    {
+        // cursors that do not start at zero: transfer lists pre-filled by the host, fast-store tails
+        unsigned long long pre[2 * SF_MAX_MESHES] = {0};
+        for (int m = 0; m < nmesh; m++) {
+            pre[m] = (unsigned long long)s.pops[m].xout.n;
+            pre[SF_MAX_MESHES + m] = (unsigned long long)s.pops[m].fast.n;
+        }
+        memcpy(ctx->h_cnt->xfer_n, pre, sizeof(unsigned long long) * SF_MAX_MESHES);
+        memcpy(ctx->h_cnt->fast_n, pre + SF_MAX_MESHES, sizeof(unsigned long long) * SF_MAX_MESHES);
+        CU(cudaMemcpyAsync(ctx->d_cnt->xfer_n, ctx->h_cnt->xfer_n, sizeof(unsigned long long) * SF_MAX_MESHES, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_cnt->fast_n, ctx->h_cnt->fast_n, sizeof(unsigned long long) * SF_MAX_MESHES, cudaMemcpyHostToDevice, ctx->stream));
+    }
     const SlowPtrs slow = slow_ptrs(s);
-    // moveParticles(false), KM:126
     for (int m = 0; m < nmesh; m++) {
         const size_t plane = (size_t)ctx->meshes[m].dev.ni * ctx->meshes[m].dev.nj;
         CU(cudaMemsetAsync(s.pops[m].dep, 0, SFGPU_NFIELDS * plane * sizeof(double), ctx->stream));
-        rc = rec_reserve(ctx, s.pops[m].nxt, s.pops[m].cur.n, false);
-        if (rc) return rc;
     }
+    // moveParticles(false), KM:126, fused with the deposit
     CU(cudaEventRecord(ctx->evk0, ctx->stream));
     for (int m = 0; m < nmesh; m++) {
         Pop &pop = s.pops[m];
+        FastStore &f = pop.fast;
+        if (f.n > 0) {
+            const FastStepArgs a = fast_args(ctx, s, m, dt, slow);
+            int64_t tail_first = 0;
+            if (!untiled && f.n_sorted > 0 && f.n_items > 0) {
+                k_fast_step<<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a);
+                CU(cudaGetLastError());
+                { ctx->last_launches++; ctx->launch_total++; }
+                tail_first = f.n_sorted;
+            }
+            if (f.n > tail_first) {
+                k_fast_tail<<<grid_for(f.n - tail_first, 256, 148 * 32), 256, 0, ctx->stream>>>(a, (unsigned long long)tail_first, (unsigned long long)(f.n - tail_first));
+                CU(cudaGetLastError());
+                { ctx->last_launches++; ctx->launch_total++; }
+            }
+            f.steps_since_sort++;
+        }
         if (pop.cur.n == 0) continue;
         k_generic_step<<<grid_for(pop.cur.n, 256, 148 * 32), 256, 0, ctx->stream>>>(
             ctx->d_meshes, m, s.qm, s.charge, dt, 0, pop.cur.p, (unsigned long long)pop.cur.n, pop.nxt.p,
-            &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt);
+            &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt, f.p, (unsigned long long)f.cap);
         CU(cudaGetLastError());
         { ctx->last_launches++; ctx->launch_total++; }
     }
@@ -731,7 +1003,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                 if (pop.xin.n == 0) continue;
                 k_generic_step<<<grid_for(pop.xin.n, 256, 148 * 32), 256, 0, ctx->stream>>>(
                     ctx->d_meshes, m, s.qm, s.charge, dt, 1, pop.xin.p, (unsigned long long)pop.xin.n, pop.nxt.p,
-                    &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt);
+                    &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt, pop.fast.p,
+                    (unsigned long long)pop.fast.cap);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
                 pop.xin.n = 0;
@@ -743,16 +1016,25 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         for (int m = 0; m < nmesh; m++) s.pops[m].xout.n = (int64_t)ctx->h_cnt->xfer_n[m];
     }
     if (ctx->h_cnt->overflow)
-        return fail(ctx, SFGPU_EOVERFLOW, "%llu particles did not fit an internal list (slow path / mesh hand-off)", ctx->h_cnt->overflow);
+        return fail(ctx, SFGPU_EOVERFLOW, "%llu particles did not fit an internal list (records / slow path / mesh hand-off)", ctx->h_cnt->overflow);
     for (int m = 0; m < nmesh; m++) {
         Pop &pop = s.pops[m];
+        FastStore &f = pop.fast;
         pop.nxt.n = (int64_t)ctx->h_cnt->n_out[m];
         std::swap(pop.cur, pop.nxt);
         pop.nxt.n = 0;
+        int64_t fn = (int64_t)ctx->h_cnt->fast_n[m];
+        if (fn > f.cap) fn = f.cap;
+        if (fn < f.n) fn = f.n;
+        f.n = fn;
+        const long long delta = ctx->h_cnt->fast_delta[m];
+        f.alive += delta;
+        if (f.alive != f.n) f.dirty = true;
     }
     s.n_exited = (int64_t)ctx->h_cnt->n_exited;
     s.n_removed = (int64_t)ctx->h_cnt->n_removed;
     s.slow_n = (int64_t)ctx->h_cnt->n_slow;
+    ctx->last_fallback = ctx->h_cnt->n_fallback;
     s.step_open = true;
     if (flags & SFGPU_STEP_DEFER_FINISH) return 0;
     return sfgpu_finish_step(ctx, sp);
@@ -846,7 +1128,7 @@ extern "C" int sfgpu_get_sums(sfgpu_ctx *ctx, int32_t sp, double sums5[5], int64
     if (sums5) for (int k = 0; k < 5; k++) sums5[k] = s.sums[k];
     if (np_alive) {
         int64_t n = 0;
-        for (auto &p : s.pops) n += p.cur.n;
+        for (auto &p : s.pops) n += p.cur.n + p.fast.alive;
         *np_alive = n;
     }
     if (n_exited) *n_exited = s.n_exited;
@@ -862,12 +1144,12 @@ extern "C" int sfgpu_np(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t *np
     Species &s = ctx->species[sp];
     if (mesh_id < 0) {
         int64_t n = 0;
-        for (auto &p : s.pops) n += p.cur.n;
+        for (auto &p : s.pops) n += p.cur.n + p.fast.alive;
         *np = n;
         return 0;
     }
     CHECK_MESH();
-    *np = s.pops[mesh_id].cur.n;
+    *np = s.pops[mesh_id].cur.n + s.pops[mesh_id].fast.alive;
     return 0;
 }
 
@@ -898,6 +1180,16 @@ extern "C" int sfgpu_take_slowpath(sfgpu_ctx *ctx, int32_t sp, int64_t max, sfgp
     return 0;
 }
 
+// the particle store seen by iterators / output / restart / collisions: the fast store in device order
+// (compacted first, so logical index == slot), then the exceptional records
+static int compact_if_dirty(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
+{
+    if (!f.dirty) return 0;
+    int rc = sync_meshes(ctx);
+    if (rc) return rc;
+    return fast_sort(ctx, mesh_id, f);
+}
+
 extern "C" int sfgpu_download(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t first, sfgpu_particles *out)
 {
     CHECK_CTX();
@@ -905,10 +1197,48 @@ extern "C" int sfgpu_download(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64
     CHECK_MESH();
     if (!out) return fail(ctx, SFGPU_EINVAL, "out is null");
     Pop &pop = ctx->species[sp].pops[mesh_id];
-    if (first < 0 || out->n < 0 || first + out->n > pop.cur.n)
-        return fail(ctx, SFGPU_EINVAL, "sfgpu_download: range [%lld,%lld) outside [0,%lld)", (long long)first, (long long)(first + out->n), (long long)pop.cur.n);
+    int rc = compact_if_dirty(ctx, mesh_id, pop.fast);
+    if (rc) return rc;
+    rc = sync_meshes(ctx);
+    if (rc) return rc;
+    const int64_t total = pop.fast.n + pop.cur.n;
+    if (first < 0 || out->n < 0 || first + out->n > total)
+        return fail(ctx, SFGPU_EINVAL, "sfgpu_download: range [%lld,%lld) outside [0,%lld)", (long long)first, (long long)(first + out->n), (long long)total);
     if (out->n == 0) return 0;
-    return download_records(ctx, pop.cur.p, first, out);
+    const int64_t chunk = 1 << 20;
+    int64_t done = 0;
+    // part 1: fast store -> records -> host
+    const int64_t f_end = std::min<int64_t>(first + out->n, pop.fast.n);
+    for (int64_t q = first; q < f_end; q += chunk) {
+        const int64_t c = std::min<int64_t>(chunk, f_end - q);
+        rc = rec_reserve(ctx, ctx->tmp, chunk, false);
+        if (rc) return rc;
+        k_fast_to_records<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, pop.fast.p, (unsigned long long)q, (unsigned long long)c, ctx->tmp.p);
+        ctx->launch_total++;
+        CU(cudaGetLastError());
+        sfgpu_particles v = *out;
+        double **arr[SF_REC_NDOUBLES] = {&v.x, &v.y, &v.z, &v.u, &v.v, &v.w, &v.mpw, &v.li, &v.lj, &v.dt};
+        for (auto a : arr) if (*a) *a += done;
+        if (v.id) v.id += done;
+        if (v.born_it) v.born_it += done;
+        v.n = c;
+        rc = download_records(ctx, ctx->tmp.p, 0, &v);
+        if (rc) return rc;
+        done += c;
+    }
+    // part 2: records
+    if (done < out->n) {
+        const int64_t r_first = first + done - pop.fast.n;
+        sfgpu_particles v = *out;
+        double **arr[SF_REC_NDOUBLES] = {&v.x, &v.y, &v.z, &v.u, &v.v, &v.w, &v.mpw, &v.li, &v.lj, &v.dt};
+        for (auto a : arr) if (*a) *a += done;
+        if (v.id) v.id += done;
+        if (v.born_it) v.born_it += done;
+        v.n = out->n - done;
+        rc = download_records(ctx, pop.cur.p, r_first, &v);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int sfgpu_upload(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t first, const sfgpu_particles *in)
@@ -918,19 +1248,78 @@ extern "C" int sfgpu_upload(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t
     CHECK_MESH();
     if (!in) return fail(ctx, SFGPU_EINVAL, "in is null");
     Pop &pop = ctx->species[sp].pops[mesh_id];
-    if (first < 0 || in->n < 0 || first + in->n > pop.cur.n)
+    if (pop.fast.dirty) return fail(ctx, SFGPU_ESTATE, "sfgpu_upload: indices are only stable right after sfgpu_download / sfgpu_sort");
+    const int64_t total = pop.fast.n + pop.cur.n;
+    if (first < 0 || in->n < 0 || first + in->n > total)
         return fail(ctx, SFGPU_EINVAL, "sfgpu_upload: range outside the store");
     if (!in->x || !in->y || !in->z || !in->u || !in->v || !in->w || !in->mpw || !in->li || !in->lj || !in->dt || !in->id || !in->born_it)
         return fail(ctx, SFGPU_EINVAL, "sfgpu_upload: every array is required");
     if (in->n == 0) return 0;
-    return upload_records(ctx, pop.cur, first, in, 0, false);
+    int rc = sync_meshes(ctx);
+    if (rc) return rc;
+    const int64_t f_end = std::min<int64_t>(first + in->n, pop.fast.n);
+    const int64_t n_fast = f_end > first ? f_end - first : 0;
+    auto view = [&](int64_t off, int64_t n) {
+        sfgpu_particles v = *in;
+        double **arr[SF_REC_NDOUBLES] = {&v.x, &v.y, &v.z, &v.u, &v.v, &v.w, &v.mpw, &v.li, &v.lj, &v.dt};
+        for (auto a : arr) *a += off;
+        v.id += off;
+        v.born_it += off;
+        v.n = n;
+        return v;
+    };
+    // records part first: the fast part may append records behind it
+    if (in->n > n_fast) {
+        const sfgpu_particles v = view(n_fast, in->n - n_fast);
+        rc = upload_records(ctx, pop.cur, first + n_fast - pop.fast.n, &v, 0, false);
+        if (rc) return rc;
+    }
+    const int64_t chunk = 1 << 20;
+    for (int64_t off = 0; off < n_fast; off += chunk) {
+        const int64_t c = std::min<int64_t>(chunk, n_fast - off);
+        rc = rec_reserve(ctx, ctx->tmp, chunk, false);
+        if (rc) return rc;
+        rc = rec_reserve(ctx, pop.cur, pop.cur.n + c, true);
+        if (rc) return rc;
+        const sfgpu_particles v = view(off, c);
+        rc = upload_records(ctx, ctx->tmp, 0, &v, 0, false);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(&ctx->d_cnt->n_exc[mesh_id], 0, sizeof(unsigned long long), ctx->stream));
+        k_records_to_fast<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, ctx->tmp.p, (unsigned long long)c, pop.fast.p,
+                                                                                   (unsigned long long)(first + off), pop.cur.p, (unsigned long long)pop.cur.n,
+                                                                                   (unsigned long long)pop.cur.cap, ctx->d_cnt);
+        ctx->launch_total++;
+        CU(cudaGetLastError());
+        unsigned long long n_exc = 0;
+        CU(cudaMemcpyAsync(&n_exc, &ctx->d_cnt->n_exc[mesh_id], sizeof n_exc, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        pop.cur.n += (int64_t)n_exc;
+        pop.fast.alive -= (int64_t)n_exc;
+        if (n_exc) pop.fast.dirty = true;
+    }
+    return 0;
 }
 
 extern "C" int sfgpu_sort(sfgpu_ctx *ctx, int32_t sp)
 {
     CHECK_CTX();
     CHECK_SP();
-    return 0; // order is not observable in the generic store; the tiled store sorts as part of every step
+    int rc = sync_meshes(ctx);
+    if (rc) return rc;
+    Species &s = ctx->species[sp];
+    for (int m = 0; m < (int)s.pops.size(); m++) {
+        rc = fast_sort(ctx, m, s.pops[m].fast);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int sfgpu_set_sort_interval(sfgpu_ctx *ctx, int32_t steps)
+{
+    CHECK_CTX();
+    if (steps < 1) return fail(ctx, SFGPU_EINVAL, "sort interval must be >= 1");
+    ctx->sort_every = steps;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

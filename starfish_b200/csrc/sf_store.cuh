@@ -11,6 +11,26 @@ struct RecPtrs {
 };
 #define SF_REC_NDOUBLES 10
 
+// Fast store: what a NORMAL particle needs between steps (lc == XtoL(pos) and dt == 0 are implied, so they are
+// not stored): 7 doubles = 56 B read per push, 6 written back in place -> the 104 algorithmic bytes of SURVEY 8d.
+// tag {id, born_it} rides along but is only touched by the sort.  A slot with mpw == NaN is vacant.
+struct FastPtrs {
+    double *x, *y, *z, *u, *v, *w, *mpw;
+    int2 *tag;
+};
+
+// one unit of work of the tiled step kernel: a run of the cell-sorted fast store that lies in one tile
+struct WorkItem {
+    unsigned long long begin;
+    int count;
+    int tile; // ti * ntj + tj
+};
+
+#define SF_TILE 8       // cells per tile edge
+#define SF_HALO 2       // extra cells kept around the tile in the warp-private accumulation tile
+#define SF_NT (SF_TILE + 2 * SF_HALO + 1) // nodes per edge of the accumulation tile
+#define SF_ITEM_MAX 2048 // particles per work item
+
 // slow-path hand-over list: record + ProcessBoundary arguments
 struct SlowPtrs {
     RecPtrs rec;
@@ -36,5 +56,11 @@ struct StepCounters {
     unsigned long long overflow;  // a list ran out of room
     unsigned long long n_bad;     // non-finite velocity on inject (KM:1357-1361)
     unsigned long long xfer_n[16]; // per-mesh transfer list length (SF_MAX_MESHES)
+    unsigned long long n_exc[16];  // per-mesh: records appended by k_inject_fast / k_records_to_fast
+    unsigned long long fast_n[16]; // per-mesh: fast-store length cursor (records that became normal are appended)
+    unsigned long long n_fallback; // deposits that missed the warp tile and went to global atomics
+    unsigned long long n_flush;    // segment flushes of the tiled kernel (diagnostic)
+    long long fast_delta[16];      // per-mesh change of the number of live fast-store particles
+    unsigned int queue[16];        // per-mesh work-item queue head of the tiled kernel
 };
 #define SF_MAX_MESHES 16

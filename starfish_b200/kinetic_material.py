@@ -310,6 +310,13 @@ class KineticMaterial:
     def sync(self):
         self._check(self.lib.sfgpu_sync(self._ctx))
 
+    def sort(self):
+        """Explicit cell sort + compaction of the device store (sfgpu_sort)."""
+        self._check(self.lib.sfgpu_sort(self._ctx, self._sp))
+
+    def setSortInterval(self, steps):
+        self._check(self.lib.sfgpu_set_sort_interval(self._ctx, int(steps)))
+
     def timerStart(self):
         self._check(self.lib.sfgpu_timer_start(self._ctx))
 

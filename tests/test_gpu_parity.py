@@ -193,6 +193,44 @@ def test_injection_every_step_zero_weight_and_edges(flags):
             compare_fields(km, ok)
 
 
+@pytest.mark.parametrize("flags", PATHS)
+def test_explicit_lc_injection_goes_through_records(flags):
+    """addParticle(md, part) with a caller-supplied lc and residual dt (restart load, KM:953-1000): full records."""
+    m = S.make_mesh(40, 33, DomainType.XY, 1e-3, "symmetry")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 8, vth_cells=0.6, kick_frac=0.1)
+    arr = wl.particles(0, 6000)
+    arr["li"] = (arr["x"] - m.x0[0]) / m.dh[0]
+    arr["lj"] = (arr["y"] - m.x0[1]) / m.dh[1]
+    arr["li"][::3] = np.floor(arr["li"][::3])  # stale lc: differs from XtoL(pos)
+    arr["dt"] = np.zeros(6000)
+    km = KineticMaterial("ion", wl.charge, wl.mass, [m], DomainType.XY, step_flags=flags)
+    ok = O.OracleKM(wl.charge, wl.mass, [m])
+    km.dt = wl.dt
+    with km:
+        assert km.addParticles(m, to_particles(arr), wl.dt) == ok.addParticles(0, arr, wl.dt)
+        compare_state(km, ok)
+        for _ in range(4):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            compare_state(km, ok)
+            compare_fields(km, ok)
+
+
+@pytest.mark.parametrize("every", [1, 3, 100])
+def test_sort_interval_does_not_change_results(every):
+    m = S.make_mesh(70, 50, DomainType.XY, 1e-3, "periodic")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 4, vth_cells=0.9, kick_frac=0.1)
+    arr = wl.particles(0, 30000)
+    km, ok = make_pair([m], wl, [arr], 0)
+    with km:
+        km.setSortInterval(every)
+        for _ in range(7):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+        compare_state(km, ok)
+        compare_fields(km, ok)
+
+
 def test_download_upload_round_trip():
     m = S.make_mesh(16, 16, DomainType.XY, 1e-3, "periodic")
     wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 1)
