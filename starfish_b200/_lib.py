@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstarfish_gpu.so")
+LIB_PATH = os.environ.get("SFGPU_LIB_PATH") or os.path.join(_HERE, "libstarfish_gpu.so")  # env: kernel-variant experiments
 
 NFIELDS = 8
 FIELD_NAMES = ("den", "u", "v", "w", "uu", "vv", "ww", "mpc")

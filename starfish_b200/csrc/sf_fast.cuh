@@ -20,9 +20,15 @@
 #include "sf_generic.cuh"
 
 #define SF_FAST_WARPS 4 // warps per CTA of the tiled kernel
-#define SF_WROW 34      // padded row of the per-warp scratch (doubles): conflict-free 128-bit reads
+#ifndef SF_PPT
+#define SF_PPT 1        // particles per lane and batch (independent instruction streams hide FP64 latency)
+#endif
+#ifndef SF_FAST_MIN_CTAS
+#define SF_FAST_MIN_CTAS 3
+#endif
+#define SF_WROW (32 * SF_PPT + 2) // padded row of the per-warp scratch (doubles): conflict-free 128-bit reads
 #define SF_TILE_DOUBLES (SFGPU_NFIELDS * SF_NT * SF_NT)
-#define SF_SCRATCH_DOUBLES (12 * SF_WROW)
+#define SF_SCRATCH_DOUBLES (2 + 13 * SF_WROW + 16 * SF_PPT + 2 * 7 * 32 * SF_PPT)
 #define SF_WARP_SMEM_BYTES ((SF_TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8)
 
 __device__ __forceinline__ double sf_vacant() { return __longlong_as_double(0x7ff8000000000001LL); }
@@ -38,7 +44,8 @@ __device__ __forceinline__ unsigned sf_cell_key(const MeshDev &m, double li, dou
 }
 
 struct FastStepArgs {
-    const MeshDev *meshes;
+    MeshDev m;                // the mesh of this launch, by value: kernel parameters live in the constant bank
+    const MeshDev *meshes;    // all meshes (neighbour lookup of the MESH hand-off)
     int mesh_id;
     double qm, charge, dt;
     FastPtrs fs;
@@ -129,31 +136,137 @@ __device__ __forceinline__ bool fast_load_move(const FastStepArgs &a, const Mesh
     return true;
 }
 
+// everything that is not the common case (boundaries, B field, segments, removal), out of line so that its
+// register needs do not inflate the hot loop.  Returns true when the particle still deposits in this step.
+__device__ __noinline__ bool fast_general(const FastStepArgs *__restrict__ ga, unsigned long long q, PState *pp, double z0, long long w0bits)
+{
+    const FastStepArgs &a = *ga;
+    MoveAux aux;
+    bool exact = true, deposit = false;
+    const GlobalFieldGather fg;
+    PState p = *pp;
+    const int st = sf_move(a.m, a.meshes, a.qm, a.charge, a.dt, false, p, aux, exact, fg);
+    fast_epilogue(a, a.m, q, st, exact, p, aux, z0, w0bits, make_int2(0, 0), deposit);
+    *pp = p;
+    return deposit;
+}
+
+// sums of a particle that deposits outside the warp tile (KM:406-413)
+__device__ __noinline__ void fast_sums_direct(StepCounters *c, const PState *pp)
+{
+    const PState &p = *pp;
+    atomicAdd(&c->sums[0], p.mpw);
+    atomicAdd(&c->sums[1], p.mpw * p.u);
+    atomicAdd(&c->sums[2], p.mpw * p.v);
+    atomicAdd(&c->sums[3], p.mpw * p.w);
+    atomicAdd(&c->sums[4], p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w));
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// tiled kernel: persistent warps pull work items from a queue
+// straight-line common case of sf_move(): one substep, no B field, no segments, the particle starts and ends
+// strictly inside the mesh.  No branches, so the compiler interleaves the SF_PPT independent particles a lane
+// carries (FP64 latency hiding).  Every expression is the one sf_move() evaluates, in the same order, so the two
+// paths are bit-identical; `ok` false means "not the common case": the caller re-runs the particle through
+// sf_move() from its original state.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SF_FAST_WARPS * 32)
-k_fast_step(FastStepArgs a)
+__device__ __forceinline__ bool sf_move_simple(const MeshDev &m, double qm, double dt, PState &p)
+{
+    const int ni = m.ni, nj = m.nj;
+    const int i = sf_j2i(p.li), j = sf_j2i(p.lj);
+    bool ok = (p.mpw > 0) && i >= 0 && j >= 0 && i < ni - 1 && j < nj - 1;
+    const int ic = min(max(i, 0), ni - 2), jc = min(max(j, 0), nj - 2); // safe addresses when !ok
+    const double di = p.li - i, dj = p.lj - j;
+    const size_t n00 = (size_t)ic * nj + jc;
+    const double *fi = m.efi + n00, *fj = m.efj + n00;
+    const double w00 = (1 - di) * (1 - dj), w10 = di * (1 - dj), w11 = di * dj, w01 = (1 - di) * dj; // F2D:345-348
+    double ex = w00 * __ldg(fi);
+    ex += w10 * __ldg(fi + nj);
+    ex += w11 * __ldg(fi + nj + 1);
+    ex += w01 * __ldg(fi + 1);
+    double ey = w00 * __ldg(fj);
+    ey += w10 * __ldg(fj + nj);
+    ey += w11 * __ldg(fj + nj + 1);
+    ey += w01 * __ldg(fj + 1);
+    const double u = p.u + qm * ex * dt; // KM:345-346 with part.dt = 0 + dt
+    const double v = p.v + qm * ey * dt;
+    double x = p.x + u * dt; // KM:369-370
+    double y = p.y + v * dt;
+    double z, un = u, vn = v, wn = p.w;
+    if (m.domain == SFGPU_XY) {
+        z = p.z + p.w * dt; // KM:380
+    } else if (m.domain == SFGPU_RZ) { // KM:424-442
+        const double A = p.w * dt, B = x, R = sqrt(A * A + B * B);
+        const double c = B / R, s = A / R;
+        z = p.z - asin(s);
+        x = R;
+        un = c * u + s * p.w;
+        wn = -s * u + c * p.w;
+    } else { // KM:444-462
+        const double A = p.w * dt, B = y, R = sqrt(A * A + B * B);
+        const double c = B / R, s = A / R;
+        z = p.z + acos(c);
+        y = R;
+        vn = c * v + s * p.w;
+        wn = -s * v + c * p.w;
+    }
+    const double li = (x - m.x0) / m.dhx; // UM:158-159
+    const double lj = (y - m.y0) / m.dhy;
+    ok = ok && li >= 0 && lj >= 0 && li < ni - 1 && lj < nj - 1; // KM:606 (a NaN takes the general path)
+    if (ok) {
+        p.x = x; p.y = y; p.z = z; p.u = un; p.v = vn; p.w = wn; p.li = li; p.lj = lj;
+    }
+    return ok;
+}
+
+// asynchronous global -> shared copy of one batch (7 state doubles per particle, each lane fetches the slots it will
+// read back itself, so no cross-lane synchronisation is needed): LDGSTS, no registers held while in flight
+__device__ __forceinline__ void sf_prefetch_batch(const FastPtrs &fs, double *stage, size_t begin, int b, int count, int lane)
+{
+    const double *src[7] = {fs.x, fs.y, fs.z, fs.u, fs.v, fs.w, fs.mpw};
+#pragma unroll
+    for (int j = 0; j < SF_PPT; j++) {
+        const int o = b + j * 32 + lane;
+        if (o < count) {
+#pragma unroll
+            for (int f = 0; f < 7; f++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + f * 32 * SF_PPT + j * 32 + lane);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src[f] + begin + o) : "memory");
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tiled kernel: persistent warps pull work items from a queue; every lane carries SF_PPT particles per batch
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SF_FAST_WARPS * 32, SF_FAST_MIN_CTAS)
+k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restrict__ ga)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *tile = reinterpret_cast<double *>(smem_raw + (size_t)wid * SF_WARP_SMEM_BYTES);
-    double *sW = tile + SF_TILE_DOUBLES; // [4][SF_WROW] weights, then [8][SF_WROW] values
+    double *sW = tile + SF_TILE_DOUBLES + 2; // tile, the warp's energy sum, then [4][SF_WROW] weights, [9][SF_WROW] values
     double *sV = sW + 4 * SF_WROW;
-    const MeshDev m = a.meshes[a.mesh_id];
+    int *sKey = reinterpret_cast<int *>(sV + 9 * SF_WROW); // [32 * SF_PPT] tile-local cell of each row
+    double *sIn = reinterpret_cast<double *>(sKey + 32 * SF_PPT); // [2 stages][7][32 * SF_PPT] prefetched particle state
+    const MeshDev &m = a.m;
     const size_t plane = (size_t)m.ni * m.nj;
+    const bool simple_ok = !m.has_b && !m.any_seg && a.dt > 0;
 
-    for (int k = lane; k < SF_TILE_DOUBLES; k += 32) tile[k] = 0.0;
+    for (int k = lane; k < SF_TILE_DOUBLES + 2; k += 32) tile[k] = 0.0;
 
-    // role of this lane in the reduction: node n (w00,w10,w11,w01) x field f (7 moments + the cell count)
+    // role of this lane in the reduction: node n (w00,w10,w11,w01) x field f (7 moments; f == 7: n == 0 counts the
+    // particles of the cell (mpc), n == 1 sums mpw*|vel| of the whole work item (energy sum, KM:412))
     const int rn = lane >> 3, rf = lane & 7;
     const int noff = (rn == 0) ? 0 : (rn == 1) ? SF_NT : (rn == 2) ? SF_NT + 1 : 1;
-    const double *rw = (rf == 7) ? (sV + 7 * SF_WROW) : (sW + rn * SF_WROW); // count lane: 1.0 * 1.0
-    const double *rv = sV + rf * SF_WROW;
-    double *racc = tile + rf * (SF_NT * SF_NT) + ((rf == 7) ? 0 : noff);
-    const bool rflush = (rf < 7) || (rn == 0);
+    const double *rw = (rf == 7) ? (sV + 7 * SF_WROW) : (sW + rn * SF_WROW); // f == 7 lanes: weight 1.0
+    const double *rv = sV + ((rf == 7 && rn == 1) ? 8 : rf) * SF_WROW;
+    const bool renergy = rf == 7 && rn == 1;
+    double *racc = renergy ? (tile + SF_TILE_DOUBLES) : (tile + rf * (SF_NT * SF_NT) + ((rf == 7) ? 0 : noff));
+    const int rmul = renergy ? 0 : 1;
+    const bool rflush = (rf < 7) || (rn <= 1);
 
-    double sN = 0, sPx = 0, sPy = 0, sPz = 0, sE = 0;
     const unsigned n_items = *a.n_items;
     for (;;) {
         unsigned it = 0;
@@ -163,80 +276,144 @@ k_fast_step(FastStepArgs a)
         const WorkItem wi = a.items[it];
         const int ti0 = (wi.tile / a.ntj) * SF_TILE - SF_HALO; // first node row / column held by the tile
         const int tj0 = (wi.tile % a.ntj) * SF_TILE - SF_HALO;
-        for (int b = 0; b < wi.count; b += 32) {
-            const bool valid = b + lane < wi.count;
-            const size_t q = (size_t)wi.begin + b + lane;
-            PState p;
-            MoveAux aux;
-            int st = SF_REMOVED;
-            bool exact = true, present = false, deposit = false;
-            double z0 = 0;
-            long long w0bits = 0;
-            if (valid) present = fast_load_move(a, m, q, p, aux, st, exact, z0, w0bits);
-            if (present) fast_epilogue(a, m, q, st, exact, p, aux, z0, w0bits, make_int2(0, 0), deposit);
-            // ---- deposit ----
-            int key = -1;
-            DepW d;
-            double val[7];
-            if (deposit) {
-                sN += p.mpw;
-                sPx += p.mpw * p.u;
-                sPy += p.mpw * p.v;
-                sPz += p.mpw * p.w;
-                sE += p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w);
-                const bool in = sf_deposit_weights(m, p.li, p.lj, d);
-                const int li_ = d.i - ti0, lj_ = d.j - tj0;
-                if (in && li_ >= 0 && lj_ >= 0 && li_ < SF_NT - 1 && lj_ < SF_NT - 1) {
-                    key = li_ * SF_NT + lj_;
-                    sf_deposit_values(p, val);
+        sf_prefetch_batch(a.fs, sIn, (size_t)wi.begin, 0, wi.count, lane);
+        for (int b = 0; b < wi.count; b += 32 * SF_PPT) {
+            PState p[SF_PPT];
+            bool present[SF_PPT], done[SF_PPT];
+            double z0[SF_PPT];
+            long long w0bits[SF_PPT];
+            // ---- the batch was prefetched into shared memory with cp.async while the previous one was processed;
+            //      start the next one now (global-memory latency hidden behind ~700 instructions of work) ----
+            const int stage = (b / (32 * SF_PPT)) & 1;
+            const bool more = b + 32 * SF_PPT < wi.count;
+            if (more) sf_prefetch_batch(a.fs, sIn + (stage ^ 1) * (7 * 32 * SF_PPT), (size_t)wi.begin, b + 32 * SF_PPT, wi.count, lane);
+            if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < SF_PPT; j++) {
+                const int o = b + j * 32 + lane;
+                present[j] = o < wi.count;
+                p[j].mpw = sf_vacant();
+                if (present[j]) {
+                    const double *in = sIn + stage * (7 * 32 * SF_PPT) + j * 32 + lane;
+                    p[j].x = in[0 * 32 * SF_PPT]; p[j].y = in[1 * 32 * SF_PPT]; p[j].z = in[2 * 32 * SF_PPT];
+                    p[j].u = in[3 * 32 * SF_PPT]; p[j].v = in[4 * 32 * SF_PPT]; p[j].w = in[5 * 32 * SF_PPT];
+                    p[j].mpw = in[6 * 32 * SF_PPT];
+                }
+            }
+            // ---- common case, branch free ----
+#pragma unroll
+            for (int j = 0; j < SF_PPT; j++) {
+                present[j] = present[j] && (p[j].mpw == p[j].mpw);
+                z0[j] = p[j].z;
+                w0bits[j] = __double_as_longlong(p[j].w);
+                p[j].li = (p[j].x - m.x0) / m.dhx; // the stored lc of a normal particle is exactly XtoL(pos)
+                p[j].lj = (p[j].y - m.y0) / m.dhy;
+                p[j].dt = 0;
+                done[j] = present[j] && simple_ok && sf_move_simple(m, a.qm, a.dt, p[j]);
+            }
+            int key[SF_PPT];
+            DepW dw[SF_PPT];
+#pragma unroll
+            for (int j = 0; j < SF_PPT; j++) {
+                const size_t q = (size_t)wi.begin + b + j * 32 + lane;
+                bool deposit = false;
+                if (done[j]) { // alive, exact lc, dt == 0: in-place store
+                    a.fs.x[q] = p[j].x;
+                    a.fs.y[q] = p[j].y;
+                    if (p[j].z != z0[j]) a.fs.z[q] = p[j].z;
+                    a.fs.u[q] = p[j].u;
+                    a.fs.v[q] = p[j].v;
+                    if (__double_as_longlong(p[j].w) != w0bits[j]) a.fs.w[q] = p[j].w;
+                    deposit = true;
+                } else if (present[j]) { // general path (boundaries, B field, segments, removal)
+                    deposit = fast_general(ga, q, &p[j], z0[j], w0bits[j]);
+                }
+                // ---- deposit: weights and the tile-local cell of this particle ----
+                key[j] = -1;
+                if (deposit) {
+                    const bool in = sf_deposit_weights(m, p[j].li, p[j].lj, dw[j]);
+                    const int li_ = dw[j].i - ti0, lj_ = dw[j].j - tj0;
+                    if (in && li_ >= 0 && lj_ >= 0 && li_ < SF_NT - 1 && lj_ < SF_NT - 1) {
+                        key[j] = li_ * SF_NT + lj_;
+                    } else {
+                        deposit_global(m, p[j], a.dep);
+                        fast_sums_direct(a.c, &p[j]);
+                        atomicAdd(&a.c->n_fallback, 1ULL);
+                    }
+                }
+            }
+            // ---- group the 32 particles of each set by cell inside the warp: row = position in cell order ----
+            unsigned bmask[SF_PPT];
+#pragma unroll
+            for (int j = 0; j < SF_PPT; j++) {
+                const unsigned grp = __match_any_sync(0xffffffffu, key[j]);
+                const int leader = __ffs(grp) - 1;
+                const int rank = __popc(grp & ((1u << lane) - 1u));
+                const bool isl = lane == leader;
+                int x = isl ? __popc(grp) : 0; // inclusive scan of the group sizes over the leaders, lane order
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= d) x += y;
+                }
+                const int off = __shfl_sync(0xffffffffu, x, leader) - __popc(grp);
+                const int row = j * 32 + off + rank;
+                bmask[j] = __reduce_or_sync(0xffffffffu, isl ? (1u << off) : 0u);
+                sKey[row] = key[j];
+                if (key[j] >= 0) {
+                    double val[7];
+                    sf_deposit_values(p[j], val);
+                    sW[0 * SF_WROW + row] = dw[j].w00;
+                    sW[1 * SF_WROW + row] = dw[j].w10;
+                    sW[2 * SF_WROW + row] = dw[j].w11;
+                    sW[3 * SF_WROW + row] = dw[j].w01;
+#pragma unroll
+                    for (int f = 0; f < 7; f++) sV[f * SF_WROW + row] = val[f];
+                    sV[7 * SF_WROW + row] = 1.0;
+                    sV[8 * SF_WROW + row] = p[j].mpw * sqrt(p[j].u * p[j].u + p[j].v * p[j].v + p[j].w * p[j].w); // KM:412
                 } else {
-                    deposit_global(m, p, a.dep);
-                    atomicAdd(&a.c->n_fallback, 1ULL);
+#pragma unroll
+                    for (int f = 0; f < 4; f++) sW[f * SF_WROW + row] = 0.0;
+#pragma unroll
+                    for (int f = 0; f < 9; f++) sV[f * SF_WROW + row] = 0.0;
                 }
             }
-            if (key >= 0) {
-                sW[0 * SF_WROW + lane] = d.w00;
-                sW[1 * SF_WROW + lane] = d.w10;
-                sW[2 * SF_WROW + lane] = d.w11;
-                sW[3 * SF_WROW + lane] = d.w01;
-#pragma unroll
-                for (int f = 0; f < 7; f++) sV[f * SF_WROW + lane] = val[f];
-                sV[7 * SF_WROW + lane] = 1.0;
-            } else {
-#pragma unroll
-                for (int f = 0; f < 4; f++) sW[f * SF_WROW + lane] = 0.0;
-#pragma unroll
-                for (int f = 0; f < 8; f++) sV[f * SF_WROW + lane] = 0.0;
-            }
-            const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-            const unsigned bmask = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
-            const unsigned any = __ballot_sync(0xffffffffu, key >= 0);
             __syncwarp();
-            if (any) {
-                double acc = 0.0;
-                int cur = __shfl_sync(0xffffffffu, key, 0);
+            // ---- lane (n,f) walks the rows; the running sum is added to the private tile when the cell changes ----
+            double acc = 0.0;
+            int cur = -1;
 #pragma unroll
+            for (int j = 0; j < SF_PPT; j++) {
+#pragma unroll 8
                 for (int k = 0; k < 32; k += 2) {
-                    const double2 w2 = *reinterpret_cast<const double2 *>(rw + k);
-                    const double2 v2 = *reinterpret_cast<const double2 *>(rv + k);
-                    if (k > 0 && ((bmask >> k) & 1u)) {
-                        if (cur >= 0 && rflush) racc[cur] += acc;
-                        acc = 0.0;
-                        cur = __shfl_sync(0xffffffffu, key, k);
+                    const double2 w2 = *reinterpret_cast<const double2 *>(rw + j * 32 + k);
+                    const double2 v2 = *reinterpret_cast<const double2 *>(rv + j * 32 + k);
+                    if ((bmask[j] >> k) & 3u) { // a new cell starts at row k or k+1
+                        if ((bmask[j] >> k) & 1u) {
+                            if (cur >= 0 && rflush) racc[cur * rmul] += acc;
+                            acc = 0.0;
+                            cur = sKey[j * 32 + k];
+                        }
+                        acc = __fma_rn(w2.x, v2.x, acc);
+                        if ((bmask[j] >> (k + 1)) & 1u) {
+                            if (cur >= 0 && rflush) racc[cur * rmul] += acc;
+                            acc = 0.0;
+                            cur = sKey[j * 32 + k + 1];
+                        }
+                        acc = __fma_rn(w2.y, v2.y, acc);
+                    } else {
+                        acc = __fma_rn(w2.x, v2.x, acc);
+                        acc = __fma_rn(w2.y, v2.y, acc);
                     }
-                    acc = __fma_rn(w2.x, v2.x, acc);
-                    if ((bmask >> (k + 1)) & 1u) {
-                        if (cur >= 0 && rflush) racc[cur] += acc;
-                        acc = 0.0;
-                        cur = __shfl_sync(0xffffffffu, key, k + 1);
-                    }
-                    acc = __fma_rn(w2.y, v2.y, acc);
                 }
-                if (cur >= 0 && rflush) racc[cur] += acc;
             }
+            if (cur >= 0 && rflush) racc[cur * rmul] += acc;
             __syncwarp();
         }
-        // ---- add the warp tile to the global deposit and clear it ----
+        // ---- add the warp tile to the global deposit and clear it; the mover sums N, Px, Py, Pz (KM:406-411) of the
+        //      particles that went through the tile are the tile totals of Den, U, V, W (bilinear weights sum to 1) ----
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
         for (int k = lane; k < SF_TILE_DOUBLES; k += 32) {
             const double v = tile[k];
             if (v != 0.0) {
@@ -244,14 +421,19 @@ k_fast_step(FastStepArgs a)
                 const int gi = ti0 + r / SF_NT, gj = tj0 + r % SF_NT;
                 if (gi >= 0 && gj >= 0 && gi < m.ni && gj < m.nj) atomicAdd(a.dep + f * plane + (size_t)gi * m.nj + gj, v);
                 tile[k] = 0.0;
+                if (f == 0) s0 += v;
+                else if (f == 1) s1 += v;
+                else if (f == 2) s2 += v;
+                else if (f == 3) s3 += v;
             }
         }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        if (lane == 0 && s0 != 0) {
+            atomicAdd(&a.c->sums[0], s0); atomicAdd(&a.c->sums[1], s1); atomicAdd(&a.c->sums[2], s2);
+            atomicAdd(&a.c->sums[3], s3); atomicAdd(&a.c->sums[4], tile[SF_TILE_DOUBLES]);
+            tile[SF_TILE_DOUBLES] = 0.0;
+        }
         __syncwarp();
-    }
-    sN = warp_sum(sN); sPx = warp_sum(sPx); sPy = warp_sum(sPy); sPz = warp_sum(sPz); sE = warp_sum(sE);
-    if (lane == 0 && sN != 0) {
-        atomicAdd(&a.c->sums[0], sN); atomicAdd(&a.c->sums[1], sPx); atomicAdd(&a.c->sums[2], sPy);
-        atomicAdd(&a.c->sums[3], sPz); atomicAdd(&a.c->sums[4], sE);
     }
 }
 
@@ -259,9 +441,9 @@ k_fast_step(FastStepArgs a)
 // tail kernel: fast-store particles appended since the last sort (injection) -- same arithmetic, global deposit
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_fast_tail(FastStepArgs a, unsigned long long first, unsigned long long n)
+k_fast_tail(const __grid_constant__ FastStepArgs a, unsigned long long first, unsigned long long n)
 {
-    const MeshDev m = a.meshes[a.mesh_id];
+    const MeshDev &m = a.m;
     double sN = 0, sPx = 0, sPy = 0, sPz = 0, sE = 0;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long q0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < n; q0 += stride) {

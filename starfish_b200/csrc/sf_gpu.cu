@@ -168,6 +168,7 @@ struct sfgpu_ctx {
     std::vector<Species> species;
     StepCounters *d_cnt = nullptr, *h_cnt = nullptr; // device / pinned host
     XferDev *d_xfer = nullptr;
+    FastStepArgs *d_args = nullptr; // per-mesh copy of the tiled kernel's arguments for its out-of-line slow path
     char *stage = nullptr; // pinned staging
     size_t stage_bytes = 0;
     double *d_tmp = nullptr; // moments scratch
@@ -358,7 +359,7 @@ static FastStepArgs fast_args(sfgpu_ctx *ctx, Species &s, int m, double dt, cons
 {
     Pop &pop = s.pops[m];
     FastStepArgs a{};
-    a.meshes = ctx->d_meshes; a.mesh_id = m; a.qm = s.qm; a.charge = s.charge; a.dt = dt;
+    a.m = ctx->meshes[m].dev; a.meshes = ctx->d_meshes; a.mesh_id = m; a.qm = s.qm; a.charge = s.charge; a.dt = dt;
     a.fs = pop.fast.p; a.items = pop.fast.items; a.n_items = pop.fast.d_nitems; a.ntj = pop.fast.ntj;
     a.exc = pop.nxt.p; a.exc_cap = (unsigned long long)pop.nxt.cap;
     a.xfer = ctx->d_xfer; a.slow = slow; a.dep = pop.dep; a.c = ctx->d_cnt;
@@ -434,6 +435,7 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
         CU(cudaMallocHost(&ctx->h_cnt, sizeof(StepCounters)));
         CU(cudaMalloc(&ctx->d_xfer, sizeof(XferDev) * SF_MAX_MESHES));
+        CU(cudaMalloc(&ctx->d_args, sizeof(FastStepArgs) * SF_MAX_MESHES));
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
         CU(cudaFuncSetAttribute(k_fast_step, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         int nsm = 0, per_sm = 0;
@@ -493,6 +495,7 @@ extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
     if (ctx->d_cnt) cudaFree(ctx->d_cnt);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     if (ctx->d_xfer) cudaFree(ctx->d_xfer);
+    if (ctx->d_args) cudaFree(ctx->d_args);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -953,7 +956,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             const FastStepArgs a = fast_args(ctx, s, m, dt, slow);
             int64_t tail_first = 0;
             if (!untiled && f.n_sorted > 0 && f.n_items > 0) {
-                k_fast_step<<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a);
+                CU(cudaMemcpyAsync(ctx->d_args + m, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
+                k_fast_step<<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
                 tail_first = f.n_sorted;
