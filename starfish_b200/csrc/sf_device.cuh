@@ -34,6 +34,8 @@ struct MeshDev {
     int has_b;   // bfi/bfj present
     double x0, y0, dhx, dhy;
     double lenx, leny; // xd - x0 with xd = x0 + (n-1)*dh, UM:131-135, KM:700-706
+    double rdhx, rdhy; // RN(1/dh) for sf_div_exact
+    int fastdiv;       // dh is a divisor sf_div_exact is proven for (host check in sfgpu_mesh_add)
     const int8_t *bc[4];
     const int *nbr[4];
     const uint8_t *has_seg;
@@ -54,6 +56,26 @@ struct MoveAux {
 };
 
 __device__ __forceinline__ int sf_j2i(double d) { return __double2int_rz(d); }
+
+// XtoL's true division (UM:158-159) without the hardware division sequence.  With r = RN(1/b):
+//   q0 = a*r is within 1.5 ulp of a/b; one residual correction q1 = q0 + (a - q0*b)*r is faithful; a second one
+//   is the correctly rounded quotient (Markstein's theorem: r within 1/2 ulp of 1/b, q1 faithful, residual exact
+//   through FMA).  The FMAs here are part of the division algorithm, not a contraction of reference arithmetic:
+//   the result is bit-identical to IEEE a/b, which tools/div_check.c verifies on 1.2e9 dividends including
+//   neighbours of rounding midpoints.  Outside the guarded range the IEEE division is used.
+__device__ __noinline__ double sf_div_ieee(double a, double b) { return a / b; }
+__device__ __forceinline__ double sf_div_exact(double a, double b, double r, bool fast)
+{
+    const double m = fabs(a);
+    if (fast && m < 0x1p500 && m > 0x1p-500) {
+        const double q0 = a * r;
+        const double e0 = __fma_rn(-q0, b, a);
+        const double q1 = __fma_rn(e0, r, q0);
+        const double e1 = __fma_rn(-q1, b, a);
+        return __fma_rn(e1, r, q1);
+    }
+    return sf_div_ieee(a, b);
+}
 
 // F2D:371-390
 __device__ __forceinline__ double sf_gather_safe(const double *__restrict__ d, int ni, int nj, double fi, double fj)

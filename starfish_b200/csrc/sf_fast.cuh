@@ -209,8 +209,8 @@ __device__ __forceinline__ bool sf_move_simple(const MeshDev &m, double qm, doub
         vn = c * v + s * p.w;
         wn = -s * v + c * p.w;
     }
-    const double li = (x - m.x0) / m.dhx; // UM:158-159
-    const double lj = (y - m.y0) / m.dhy;
+    const double li = sf_div_exact(x - m.x0, m.dhx, m.rdhx, m.fastdiv); // UM:158-159
+    const double lj = sf_div_exact(y - m.y0, m.dhy, m.rdhy, m.fastdiv);
     ok = ok && li >= 0 && lj >= 0 && li < ni - 1 && lj < nj - 1; // KM:606 (a NaN takes the general path)
     if (ok) {
         p.x = x; p.y = y; p.z = z; p.u = un; p.v = vn; p.w = wn; p.li = li; p.lj = lj;
@@ -307,8 +307,8 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                 present[j] = present[j] && (p[j].mpw == p[j].mpw);
                 z0[j] = p[j].z;
                 w0bits[j] = __double_as_longlong(p[j].w);
-                p[j].li = (p[j].x - m.x0) / m.dhx; // the stored lc of a normal particle is exactly XtoL(pos)
-                p[j].lj = (p[j].y - m.y0) / m.dhy;
+                p[j].li = sf_div_exact(p[j].x - m.x0, m.dhx, m.rdhx, m.fastdiv); // the stored lc of a normal particle is exactly XtoL(pos)
+                p[j].lj = sf_div_exact(p[j].y - m.y0, m.dhy, m.rdhy, m.fastdiv);
                 p[j].dt = 0;
                 done[j] = present[j] && simple_ok && sf_move_simple(m, a.qm, a.dt, p[j]);
             }
@@ -327,7 +327,9 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                     if (__double_as_longlong(p[j].w) != w0bits[j]) a.fs.w[q] = p[j].w;
                     deposit = true;
                 } else if (present[j]) { // general path (boundaries, B field, segments, removal)
-                    deposit = fast_general(ga, q, &p[j], z0[j], w0bits[j]);
+                    PState t = p[j]; // only the copy has its address taken: p[] stays in registers
+                    deposit = fast_general(ga, q, &t, z0[j], w0bits[j]);
+                    p[j] = t;
                 }
                 // ---- deposit: weights and the tile-local cell of this particle ----
                 key[j] = -1;
@@ -338,7 +340,8 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                         key[j] = li_ * SF_NT + lj_;
                     } else {
                         deposit_global(m, p[j], a.dep);
-                        fast_sums_direct(a.c, &p[j]);
+                        const PState t = p[j];
+                        fast_sums_direct(a.c, &t);
                         atomicAdd(&a.c->n_fallback, 1ULL);
                     }
                 }
@@ -385,26 +388,37 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
             int cur = -1;
 #pragma unroll
             for (int j = 0; j < SF_PPT; j++) {
-#pragma unroll 8
-                for (int k = 0; k < 32; k += 2) {
-                    const double2 w2 = *reinterpret_cast<const double2 *>(rw + j * 32 + k);
-                    const double2 v2 = *reinterpret_cast<const double2 *>(rv + j * 32 + k);
-                    if ((bmask[j] >> k) & 3u) { // a new cell starts at row k or k+1
-                        if ((bmask[j] >> k) & 1u) {
-                            if (cur >= 0 && rflush) racc[cur * rmul] += acc;
-                            acc = 0.0;
-                            cur = sKey[j * 32 + k];
+#pragma unroll
+                for (int k0 = 0; k0 < 32; k0 += 8) {
+                    double2 w2[4], v2[4]; // operands of 8 rows fetched up front: one shared-memory latency per chunk
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        w2[h] = *reinterpret_cast<const double2 *>(rw + j * 32 + k0 + 2 * h);
+                        v2[h] = *reinterpret_cast<const double2 *>(rv + j * 32 + k0 + 2 * h);
+                    }
+                    if ((bmask[j] >> k0) & 0xffu) { // a new cell starts inside this chunk
+#pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            const int k = k0 + 2 * h;
+                            if ((bmask[j] >> k) & 1u) {
+                                if (cur >= 0 && rflush) racc[cur * rmul] += acc;
+                                acc = 0.0;
+                                cur = sKey[j * 32 + k];
+                            }
+                            acc = __fma_rn(w2[h].x, v2[h].x, acc);
+                            if ((bmask[j] >> (k + 1)) & 1u) {
+                                if (cur >= 0 && rflush) racc[cur * rmul] += acc;
+                                acc = 0.0;
+                                cur = sKey[j * 32 + k + 1];
+                            }
+                            acc = __fma_rn(w2[h].y, v2[h].y, acc);
                         }
-                        acc = __fma_rn(w2.x, v2.x, acc);
-                        if ((bmask[j] >> (k + 1)) & 1u) {
-                            if (cur >= 0 && rflush) racc[cur * rmul] += acc;
-                            acc = 0.0;
-                            cur = sKey[j * 32 + k + 1];
-                        }
-                        acc = __fma_rn(w2.y, v2.y, acc);
                     } else {
-                        acc = __fma_rn(w2.x, v2.x, acc);
-                        acc = __fma_rn(w2.y, v2.y, acc);
+#pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            acc = __fma_rn(w2[h].x, v2[h].x, acc);
+                            acc = __fma_rn(w2[h].y, v2[h].y, acc);
+                        }
                     }
                 }
             }

@@ -528,6 +528,14 @@ extern "C" int sfgpu_mesh_add(sfgpu_ctx *ctx, int32_t ni, int32_t nj, const doub
     const double xd0 = x0[0] + (ni - 1) * dh[0], xd1 = x0[1] + (nj - 1) * dh[1];
     d.lenx = xd0 - x0[0];
     d.leny = xd1 - x0[1];
+    d.rdhx = 1.0 / dh[0];
+    d.rdhy = 1.0 / dh[1];
+    d.fastdiv = 1;
+    for (int k = 0; k < 2; k++) { // sf_div_exact: normal divisor well inside the exponent range, significand not all ones
+        int e = 0;
+        const double fr = frexp(dh[k], &e);
+        if (e < -200 || e > 200 || fr >= 1.0 - 0x1p-52 || getenv("SFGPU_NO_FASTDIV")) d.fastdiv = 0;
+    }
     const size_t plane = (size_t)ni * nj;
     for (int f = 0; f < 4; f++) {
         const int len = (f == SFGPU_FACE_RIGHT || f == SFGPU_FACE_LEFT) ? nj : ni;
