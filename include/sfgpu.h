@@ -22,6 +22,7 @@
 #ifndef SFGPU_H
 #define SFGPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -116,6 +117,11 @@ void sfgpu_destroy(sfgpu_ctx *ctx);
 /* ctx may be NULL: returns the last error of the calling thread's most recent failing call */
 const char *sfgpu_last_error(sfgpu_ctx *ctx);
 
+/* page-locked host memory: field / moment buffers allocated here are copied by DMA without staging (Java:
+ * wrap the pointer in a direct ByteBuffer / MemorySegment).  Any other host pointer works too, through a staged copy. */
+int sfgpu_host_alloc(size_t bytes, void **out);
+void sfgpu_host_free(void *p);
+
 /* ---- mesh and fields (replaces the reads of UniformMesh / Mesh state on the path) ------- */
 /* UM:33-43 geometry; bc[f]: DomainBoundaryType per node of face f (MESH:215), nj entries for
  * RIGHT/LEFT, ni for TOP/BOTTOM; nbr[f] (nullable): 2 neighbour mesh ids per node or -1
@@ -147,6 +153,11 @@ int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp);
 
 /* raw per-step sums, each ni*nj, any pointer nullable: order SFGPU_F_* */
 int sfgpu_get_deposit(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, double *const out[SFGPU_NFIELDS]);
+/* running velocity-moment sums of updateSamples (KM:1570-1595), accumulated on the device at the end of every step:
+ * order SFGPU_F_* = count-sum, u-sum, v-sum, w-sum, uu-sum, vv-sum, ww-sum, mpc-sum; any pointer nullable; out
+ * itself nullable to read only num_samples (KM:1557).  sfgpu_clear_samples = clearSamples(), KM:1509-1528. */
+int sfgpu_get_samples(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, double *const out[SFGPU_NFIELDS], int64_t *num_samples);
+int sfgpu_clear_samples(sfgpu_ctx *ctx, int32_t sp);
 /* nd,u,v,w after KM:190-196 (U,V,W /= Den; Den /= node_vol); needs node_vol; any nullable */
 int sfgpu_get_moments(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, double *nd, double *u, double *v,
                       double *w);
@@ -187,6 +198,9 @@ int sfgpu_deposit_device_ptr(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, void *
  * whole step (memsets, kernels, collective), ms_kernel only the fused move+deposit kernel(s) of the main
  * pass; launches = kernels launched by the step.  Any pointer nullable. */
 int sfgpu_last_step_timing(sfgpu_ctx *ctx, float *ms_total, float *ms_kernel, int32_t *launches);
+/* diagnostics of the last step: particles whose deposit missed the warp tile of their sort position and went
+ * through global atomics instead (grows between cell sorts; the step re-sorts early when it passes 1/64) */
+int sfgpu_last_step_counters(sfgpu_ctx *ctx, int64_t *n_fallback);
 /* cudaStreamSynchronize on the context's stream */
 int sfgpu_sync(sfgpu_ctx *ctx);
 /* bracket any sequence of calls with CUDA events on the context's stream (the stream every kernel of the

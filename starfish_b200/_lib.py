@@ -48,6 +48,10 @@ EXPORTS = {
     "sfgpu_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_uint32]),
     "sfgpu_finish_step": (C.c_int, [C.c_void_p, C.c_int32]),
     "sfgpu_get_deposit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "sfgpu_get_samples": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),
+    "sfgpu_clear_samples": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sfgpu_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "sfgpu_host_free": (None, [C.c_void_p]),
     "sfgpu_get_moments": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfgpu_get_sums": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_int64_p, c_int64_p, c_int64_p]),
     "sfgpu_np": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_int64_p]),
@@ -60,6 +64,7 @@ EXPORTS = {
     "sfgpu_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "sfgpu_deposit_device_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),
     "sfgpu_last_step_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), c_int32_p]),
+    "sfgpu_last_step_counters": (C.c_int, [C.c_void_p, c_int64_p]),
     "sfgpu_sync": (C.c_int, [C.c_void_p]),
     "sfgpu_timer_start": (C.c_int, [C.c_void_p]),
     "sfgpu_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

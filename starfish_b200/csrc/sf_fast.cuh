@@ -28,7 +28,7 @@
 #endif
 #define SF_WROW (32 * SF_PPT + 2) // padded row of the per-warp scratch (doubles): conflict-free 128-bit reads
 #define SF_TILE_DOUBLES (SFGPU_NFIELDS * SF_NT * SF_NT)
-#define SF_SCRATCH_DOUBLES (2 + 13 * SF_WROW + 16 * SF_PPT + 2 * 7 * 32 * SF_PPT)
+#define SF_SCRATCH_DOUBLES (8 + 13 * SF_WROW + 16 * SF_PPT + 2 * 7 * 32 * SF_PPT)
 #define SF_WARP_SMEM_BYTES ((SF_TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8)
 
 __device__ __forceinline__ double sf_vacant() { return __longlong_as_double(0x7ff8000000000001LL); }
@@ -151,15 +151,18 @@ __device__ __noinline__ bool fast_general(const FastStepArgs *__restrict__ ga, u
     return deposit;
 }
 
-// sums of a particle that deposits outside the warp tile (KM:406-413)
-__device__ __noinline__ void fast_sums_direct(StepCounters *c, const PState *pp)
+// a particle that deposits outside the warp tile (drifted since the last sort): global FP64 REDs for the fields,
+// and its mover sums (KM:406-413) into the warp's shared-memory slots (CAS atomics: only lanes of this warp contend)
+__device__ __noinline__ void fast_fallback(const MeshDev *mp, const PState *pp, double *dep, double *extra)
 {
     const PState &p = *pp;
-    atomicAdd(&c->sums[0], p.mpw);
-    atomicAdd(&c->sums[1], p.mpw * p.u);
-    atomicAdd(&c->sums[2], p.mpw * p.v);
-    atomicAdd(&c->sums[3], p.mpw * p.w);
-    atomicAdd(&c->sums[4], p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w));
+    deposit_global(*mp, p, dep);
+    atomicAdd(extra + 1, p.mpw);
+    atomicAdd(extra + 2, p.mpw * p.u);
+    atomicAdd(extra + 3, p.mpw * p.v);
+    atomicAdd(extra + 4, p.mpw * p.w);
+    atomicAdd(extra + 5, p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w));
+    atomicAdd(extra + 6, 1.0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -246,7 +249,7 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *tile = reinterpret_cast<double *>(smem_raw + (size_t)wid * SF_WARP_SMEM_BYTES);
-    double *sW = tile + SF_TILE_DOUBLES + 2; // tile, the warp's energy sum, then [4][SF_WROW] weights, [9][SF_WROW] values
+    double *sW = tile + SF_TILE_DOUBLES + 8; // tile, 8 extra sums of the warp (energy, fallback N/P/E/count), then [4][SF_WROW] weights, [9][SF_WROW] values
     double *sV = sW + 4 * SF_WROW;
     int *sKey = reinterpret_cast<int *>(sV + 9 * SF_WROW); // [32 * SF_PPT] tile-local cell of each row
     double *sIn = reinterpret_cast<double *>(sKey + 32 * SF_PPT); // [2 stages][7][32 * SF_PPT] prefetched particle state
@@ -254,7 +257,7 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     const size_t plane = (size_t)m.ni * m.nj;
     const bool simple_ok = !m.has_b && !m.any_seg && a.dt > 0;
 
-    for (int k = lane; k < SF_TILE_DOUBLES + 2; k += 32) tile[k] = 0.0;
+    for (int k = lane; k < SF_TILE_DOUBLES + 8; k += 32) tile[k] = 0.0;
 
     // role of this lane in the reduction: node n (w00,w10,w11,w01) x field f (7 moments; f == 7: n == 0 counts the
     // particles of the cell (mpc), n == 1 sums mpw*|vel| of the whole work item (energy sum, KM:412))
@@ -339,10 +342,8 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                     if (in && li_ >= 0 && lj_ >= 0 && li_ < SF_NT - 1 && lj_ < SF_NT - 1) {
                         key[j] = li_ * SF_NT + lj_;
                     } else {
-                        deposit_global(m, p[j], a.dep);
                         const PState t = p[j];
-                        fast_sums_direct(a.c, &t);
-                        atomicAdd(&a.c->n_fallback, 1ULL);
+                        fast_fallback(&ga->m, &t, a.dep, tile + SF_TILE_DOUBLES);
                     }
                 }
             }
@@ -442,10 +443,15 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
             }
         }
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-        if (lane == 0 && s0 != 0) {
-            atomicAdd(&a.c->sums[0], s0); atomicAdd(&a.c->sums[1], s1); atomicAdd(&a.c->sums[2], s2);
-            atomicAdd(&a.c->sums[3], s3); atomicAdd(&a.c->sums[4], tile[SF_TILE_DOUBLES]);
-            tile[SF_TILE_DOUBLES] = 0.0;
+        if (lane == 0) {
+            double *ex = tile + SF_TILE_DOUBLES;
+            if (s0 != 0 || ex[6] != 0) {
+                atomicAdd(&a.c->sums[0], s0 + ex[1]); atomicAdd(&a.c->sums[1], s1 + ex[2]); atomicAdd(&a.c->sums[2], s2 + ex[3]);
+                atomicAdd(&a.c->sums[3], s3 + ex[4]); atomicAdd(&a.c->sums[4], ex[0] + ex[5]);
+                if (ex[6] != 0) atomicAdd(&a.c->n_fallback, (unsigned long long)ex[6]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) ex[k] = 0.0;
         }
         __syncwarp();
     }

@@ -237,5 +237,12 @@ __global__ void k_moments(const double *__restrict__ dep, const double *__restri
     out4[3 * plane + k] = w;
 }
 
+// running sums of updateSamples (KM:1584-1593): sums += this step's raw deposit
+__global__ void k_accumulate(double *__restrict__ sums, const double *__restrict__ dep, size_t n)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) sums[k] += dep[k];
+}
+
 // fails the context when the compiler contracted a*b+c (would break bit parity with Java)
 __global__ void k_selftest_fmad(double a, double b, double c, double *out) { out[0] = a * b + c; }

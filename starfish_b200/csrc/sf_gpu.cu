@@ -141,6 +141,7 @@ struct Pop { // one species on one mesh: MeshData, KM:1314-1427
     Records cur, nxt;  // exceptional particles as full records (this step / next step)
     Records xin, xout; // transfer_particles (being moved / being filled)
     double *dep = nullptr; // packed [SFGPU_NFIELDS][ni][nj] raw per-step deposit
+    double *samp = nullptr; // packed running velocity-moment sums (count,u,v,w,uu,vv,ww,mpc), KM:1570-1595
 };
 
 struct Species {
@@ -155,6 +156,7 @@ struct Species {
     int64_t n_exited = 0, n_removed = 0;
     int64_t capacity_hint = 0;
     bool step_open = false; // sfgpu_step ran, sfgpu_finish_step pending
+    int64_t num_samples = 0; // KM:1557
 };
 
 struct sfgpu_ctx {
@@ -181,6 +183,7 @@ struct sfgpu_ctx {
     int fast_grid = 0;       // CTAs of the tiled kernel (persistent)
     Records tmp;             // staging records for download / upload of the fast store
     unsigned long long last_fallback = 0, last_flush = 0;
+    bool force_sort = false;
     std::string err;
 };
 
@@ -366,6 +369,18 @@ static FastStepArgs fast_args(sfgpu_ctx *ctx, Species &s, int m, double dt, cons
     return a;
 }
 
+// caller buffers from sfgpu_host_alloc (or any page-locked memory) take direct DMA copies, everything else is staged
+static bool is_pinned(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 static int sync_meshes(sfgpu_ctx *ctx)
 {
     if (!ctx->meshes_dirty) return 0;
@@ -476,6 +491,7 @@ extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
             rec_free(p.cur); rec_free(p.nxt); rec_free(p.xin); rec_free(p.xout);
             fast_free(p.fast);
             if (p.dep) cudaFree(p.dep);
+            if (p.samp) cudaFree(p.samp);
         }
         rec_free(s.slow);
         if (s.slow_extra_d) cudaFree(s.slow_extra_d);
@@ -590,6 +606,19 @@ extern "C" int sfgpu_set_fields(sfgpu_ctx *ctx, int32_t mesh_id, const double *e
     if (!efi || !efj) return fail(ctx, SFGPU_EINVAL, "sfgpu_set_fields: efi/efj are required");
     if ((bfi == nullptr) != (bfj == nullptr)) return fail(ctx, SFGPU_EINVAL, "sfgpu_set_fields: give both bfi and bfj or neither");
     const int nf = bfi ? 4 : 2;
+    if (is_pinned(efi) && is_pinned(efj) && (!bfi || (is_pinned(bfi) && is_pinned(bfj)))) {
+        const double *src[4] = {efi, efj, bfi, bfj};
+        for (int k = 0; k < nf; k++)
+            CU(cudaMemcpyAsync(m.fields + k * plane, src[k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (!bfi && m.dev.has_b) CU(cudaMemsetAsync(m.fields + 2 * plane, 0, 2 * bytes, ctx->stream));
+        const int hb = bfi ? 1 : 0;
+        if (hb != m.dev.has_b) {
+            m.dev.has_b = hb;
+            ctx->meshes_dirty = true;
+        }
+        CU(cudaStreamSynchronize(ctx->stream)); // the caller may reuse its buffers on return
+        return 0;
+    }
     int rc = stage_reserve(ctx, nf * bytes);
     if (rc) return rc;
     // the stage may still feed an earlier async copy
@@ -629,6 +658,8 @@ extern "C" int sfgpu_species_add(sfgpu_ctx *ctx, double charge, double mass, int
         const size_t plane = (size_t)ctx->meshes[k].dev.ni * ctx->meshes[k].dev.nj;
         CU(cudaMalloc(&s.pops[k].dep, SFGPU_NFIELDS * plane * sizeof(double)));
         CU(cudaMemset(s.pops[k].dep, 0, SFGPU_NFIELDS * plane * sizeof(double)));
+        CU(cudaMalloc(&s.pops[k].samp, SFGPU_NFIELDS * plane * sizeof(double)));
+        CU(cudaMemset(s.pops[k].samp, 0, SFGPU_NFIELDS * plane * sizeof(double)));
         int rc = fast_init_geometry(ctx, s.pops[k].fast, ctx->meshes[k].dev);
         if (rc) return rc;
     }
@@ -919,7 +950,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         FastStore &f = s.pops[m].fast;
         if (untiled || f.n == 0) continue;
         const int64_t tail = f.n - f.n_sorted;
-        if (f.n_sorted == 0 || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n) {
+        if (f.n_sorted == 0 || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n || ctx->force_sort) {
             rc = fast_sort(ctx, m, f);
             if (rc) return rc;
         }
@@ -1047,6 +1078,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     s.n_removed = (int64_t)ctx->h_cnt->n_removed;
     s.slow_n = (int64_t)ctx->h_cnt->n_slow;
     ctx->last_fallback = ctx->h_cnt->n_fallback;
+    // too many particles drifted out of their warp tiles: sort before the next step instead of waiting for the interval
+    ctx->force_sort = !untiled && (int64_t)ctx->last_fallback * 64 > n_total;
     s.step_open = true;
     if (flags & SFGPU_STEP_DEFER_FINISH) return 0;
     return sfgpu_finish_step(ctx, sp);
@@ -1070,6 +1103,14 @@ extern "C" int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp)
         int r = g_nccl.AllReduce(ctx->d_cnt->sums, ctx->d_cnt->sums, 5, SF_NCCL_FLOAT64, SF_NCCL_SUM, ctx->comm, ctx->stream);
         if (r) return fail(ctx, SFGPU_ENCCL, "ncclAllReduce(sums): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     }
+    // updateSamples, KM:1570-1595: the per-step increments of the running sums are the raw deposit
+    for (int m = 0; m < nmesh; m++) {
+        const size_t cnt = (size_t)SFGPU_NFIELDS * ctx->meshes[m].dev.ni * ctx->meshes[m].dev.nj;
+        k_accumulate<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(s.pops[m].samp, s.pops[m].dep, cnt);
+        ctx->launch_total++;
+        CU(cudaGetLastError());
+    }
+    s.num_samples++;
     CU(cudaMemcpyAsync(ctx->h_cnt->sums, ctx->d_cnt->sums, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1082,25 +1123,63 @@ extern "C" int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp)
 // ---------------------------------------------------------------------------------------------
 // results
 // ---------------------------------------------------------------------------------------------
+// device planes -> caller buffers: straight DMA into page-locked destinations, staged copy otherwise
+static int download_planes(sfgpu_ctx *ctx, const double *src, size_t plane, int nplanes, double *const *out)
+{
+    const size_t bytes = plane * sizeof(double);
+    bool any = false, all_pinned = true;
+    for (int f = 0; f < nplanes; f++)
+        if (out[f]) { any = true; all_pinned = all_pinned && is_pinned(out[f]); }
+    if (!any) return 0;
+    if (all_pinned) {
+        for (int f = 0; f < nplanes; f++)
+            if (out[f]) CU(cudaMemcpyAsync(out[f], src + (size_t)f * plane, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    int rc = stage_reserve(ctx, nplanes * bytes);
+    if (rc) return rc;
+    int lo = -1, hi = -1; // contiguous run of requested planes -> one copy
+    for (int f = 0; f < nplanes; f++)
+        if (out[f]) { if (lo < 0) lo = f; hi = f; }
+    CU(cudaMemcpyAsync(ctx->stage + lo * bytes, src + (size_t)lo * plane, (hi - lo + 1) * bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int f = lo; f <= hi; f++)
+        if (out[f]) memcpy(out[f], ctx->stage + f * bytes, bytes);
+    return 0;
+}
+
 extern "C" int sfgpu_get_deposit(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, double *const out[SFGPU_NFIELDS])
 {
     CHECK_CTX();
     CHECK_SP();
     CHECK_MESH();
     if (!out) return fail(ctx, SFGPU_EINVAL, "out is null");
-    const size_t plane = (size_t)ctx->meshes[mesh_id].dev.ni * ctx->meshes[mesh_id].dev.nj, bytes = plane * sizeof(double);
-    int rc = stage_reserve(ctx, SFGPU_NFIELDS * bytes);
-    if (rc) return rc;
-    Pop &pop = ctx->species[sp].pops[mesh_id];
-    // contiguous run of requested fields -> one copy
-    int lo = -1, hi = -1;
-    for (int f = 0; f < SFGPU_NFIELDS; f++)
-        if (out[f]) { if (lo < 0) lo = f; hi = f; }
-    if (lo < 0) return 0;
-    CU(cudaMemcpyAsync(ctx->stage + lo * bytes, pop.dep + lo * plane, (hi - lo + 1) * bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    for (int f = lo; f <= hi; f++)
-        if (out[f]) memcpy(out[f], ctx->stage + f * bytes, bytes);
+    const size_t plane = (size_t)ctx->meshes[mesh_id].dev.ni * ctx->meshes[mesh_id].dev.nj;
+    return download_planes(ctx, ctx->species[sp].pops[mesh_id].dep, plane, SFGPU_NFIELDS, out);
+}
+
+extern "C" int sfgpu_get_samples(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, double *const out[SFGPU_NFIELDS], int64_t *num_samples)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    if (num_samples) *num_samples = ctx->species[sp].num_samples;
+    if (!out) return 0;
+    const size_t plane = (size_t)ctx->meshes[mesh_id].dev.ni * ctx->meshes[mesh_id].dev.nj;
+    return download_planes(ctx, ctx->species[sp].pops[mesh_id].samp, plane, SFGPU_NFIELDS, out);
+}
+
+extern "C" int sfgpu_clear_samples(sfgpu_ctx *ctx, int32_t sp)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    Species &s = ctx->species[sp];
+    for (size_t m = 0; m < s.pops.size(); m++) {
+        const size_t plane = (size_t)ctx->meshes[m].dev.ni * ctx->meshes[m].dev.nj;
+        CU(cudaMemsetAsync(s.pops[m].samp, 0, SFGPU_NFIELDS * plane * sizeof(double), ctx->stream));
+    }
+    s.num_samples = 0;
     return 0;
 }
 
@@ -1119,17 +1198,25 @@ extern "C" int sfgpu_get_moments(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, do
         CU(cudaMalloc(&ctx->d_tmp, 4 * bytes));
         ctx->tmp_bytes = 4 * bytes;
     }
-    int rc = stage_reserve(ctx, 4 * bytes);
-    if (rc) return rc;
     k_moments<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(ctx->species[sp].pops[mesh_id].dep, m.node_vol, plane, ctx->d_tmp);
     ctx->launch_total++;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(ctx->stage, ctx->d_tmp, 4 * bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    double *dst[4] = {nd, u, v, w};
-    for (int k = 0; k < 4; k++)
-        if (dst[k]) memcpy(dst[k], ctx->stage + k * bytes, bytes);
+    double *const out[4] = {nd, u, v, w};
+    return download_planes(ctx, ctx->d_tmp, plane, 4, out);
+}
+
+extern "C" int sfgpu_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(nullptr, SFGPU_EINVAL, "out is null");
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(nullptr, SFGPU_ENOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
     return 0;
+}
+
+extern "C" void sfgpu_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int sfgpu_get_sums(sfgpu_ctx *ctx, int32_t sp, double sums5[5], int64_t *np_alive, int64_t *n_exited, int64_t *n_slow)
@@ -1421,5 +1508,12 @@ extern "C" int sfgpu_launch_count(sfgpu_ctx *ctx, int64_t *n)
     CHECK_CTX();
     if (!n) return fail(ctx, SFGPU_EINVAL, "n is null");
     *n = ctx->launch_total;
+    return 0;
+}
+
+extern "C" int sfgpu_last_step_counters(sfgpu_ctx *ctx, int64_t *n_fallback)
+{
+    CHECK_CTX();
+    if (n_fallback) *n_fallback = (int64_t)ctx->last_fallback;
     return 0;
 }

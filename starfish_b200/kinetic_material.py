@@ -72,6 +72,36 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+_SAMPLE_NAMES = ("count-sum", "u-sum", "v-sum", "w-sum", "uu-sum", "vv-sum", "ww-sum", "mpc-sum")
+
+
+class _Fields(dict):
+    """Per-mesh result fields.  nd/u/v/w are refreshed by every updateFields(); the running velocity-moment sums live
+    on the device (KM:1570-1595) and are fetched when somebody reads them, like Java's computeFields() every 10 steps."""
+
+    def __init__(self, km, k):
+        super().__init__()
+        self._km, self._k = km, k
+
+    def __getitem__(self, name):
+        if name in _SAMPLE_NAMES:
+            self._km._fetch_samples(self._k)
+        return super().__getitem__(name)
+
+
+class _LazyDeposit:
+    """last_deposit[k]: the raw per-step sums [8][ni][nj] of mesh k, downloaded on first access after a step."""
+
+    def __init__(self, km):
+        self._km = km
+
+    def __getitem__(self, k):
+        return self._km._fetch_deposit(k)
+
+    def __len__(self):
+        return len(self._km.meshes)
+
+
 class KineticMaterial:
     """One kinetic species on one GPU.  ``meshes`` is the ordered mesh list (Starfish.getMeshList())."""
 
@@ -110,12 +140,19 @@ class KineticMaterial:
         self._sp = sp.value
         for m in self.meshes:
             self.setFields(m)
-        # per-mesh result fields, double[ni][nj] like Field2D.data
-        z = lambda m: np.zeros((m.ni, m.nj))
-        self.fields = [{k: z(m) for k in ("nd", "u", "v", "w", "count-sum", "u-sum", "v-sum", "w-sum", "uu-sum", "vv-sum",
-                                           "ww-sum", "mpc-sum")} for m in self.meshes]
-        self.last_deposit = [None] * len(self.meshes)
-        self.num_samples = 0
+        # per-mesh result fields, double[ni][nj] like Field2D.data, in page-locked memory (direct DMA, no staging)
+        self._pinned = []
+        self.fields = []
+        for k, m in enumerate(self.meshes):
+            f = _Fields(self, k)
+            for name in ("nd", "u", "v", "w") + _SAMPLE_NAMES:
+                dict.__setitem__(f, name, self.hostArray((m.ni, m.nj)))
+            self.fields.append(f)
+        self._dep = [self.hostArray((NFIELDS, m.ni, m.nj)) for m in self.meshes]
+        self._dep_step = [-1] * len(self.meshes)
+        self._samp_step = [-1] * len(self.meshes)
+        self._step_no = 0
+        self.last_deposit = _LazyDeposit(self)
         self.mass_sum = 0.0
         self.momentum_sum = np.zeros(3)
         self.energy_sum = 0.0
@@ -129,10 +166,32 @@ class KineticMaterial:
         if rc:
             raise SfgpuError(rc, self.lib.sfgpu_last_error(self._ctx).decode())
 
+    def hostArray(self, shape):
+        """Zeroed float64 array in page-locked host memory (sfgpu_host_alloc): what a Java host would hold as a
+        direct buffer for its Field2D mirrors.  Lives until close()."""
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        rc = self.lib.sfgpu_host_alloc(n * 8, C.byref(p))
+        if rc:
+            raise SfgpuError(rc, self.lib.sfgpu_last_error(None).decode())
+        self._pinned.append(p)
+        a = np.ctypeslib.as_array((C.c_double * n).from_address(p.value)).reshape(shape)
+        a[...] = 0.0
+        return a
+
+    @property
+    def num_samples(self):
+        n = C.c_int64()
+        self._check(self.lib.sfgpu_get_samples(self._ctx, self._sp, 0, None, C.byref(n)))
+        return n.value
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             self.lib.sfgpu_destroy(self._ctx)
             self._ctx = C.c_void_p()
+            for p in getattr(self, "_pinned", []):
+                self.lib.sfgpu_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -200,31 +259,31 @@ class KineticMaterial:
         self.momentum_sum = np.array([sums[1], sums[2], sums[3]]) * self.mass
         self.energy_sum = sums[4] * self.mass
         self.n_exited, self.n_slow = n_exit.value, n_slow.value
-        for k, m in enumerate(self.meshes):
-            dep = np.empty((NFIELDS, m.ni, m.nj))
+        self._step_no += 1
+        for k in range(len(self.meshes)):
+            f = self.fields[k]
+            # nd,u,v,w of updateFields(MeshData), KM:168-197: what the rest of Starfish reads every step
+            self._check(self.lib.sfgpu_get_moments(self._ctx, self._sp, k, *[C.c_void_p(dict.__getitem__(f, q).ctypes.data)
+                                                                              for q in ("nd", "u", "v", "w")]))
+
+    def _fetch_deposit(self, k):
+        if self._dep_step[k] != self._step_no:
+            dep = self._dep[k]
             ptrs = (C.c_void_p * NFIELDS)(*[dep[f].ctypes.data for f in range(NFIELDS)])
             self._check(self.lib.sfgpu_get_deposit(self._ctx, self._sp, k, ptrs))
-            self.last_deposit[k] = dep
+            self._dep_step[k] = self._step_no
+        return self._dep[k]
+
+    def _fetch_samples(self, k):
+        if self._samp_step[k] != self._step_no:
             f = self.fields[k]
-            mom = np.empty((4, m.ni, m.nj))
-            self._check(self.lib.sfgpu_get_moments(self._ctx, self._sp, k, *[C.c_void_p(mom[q].ctypes.data) for q in range(4)]))
-            f["nd"], f["u"], f["v"], f["w"] = mom[0], mom[1], mom[2], mom[3]
-            # updateSamples, KM:1584-1593: the per-step increments are the raw deposit
-            f["count-sum"] += dep[0]
-            f["u-sum"] += dep[1]
-            f["v-sum"] += dep[2]
-            f["w-sum"] += dep[3]
-            f["uu-sum"] += dep[4]
-            f["vv-sum"] += dep[5]
-            f["ww-sum"] += dep[6]
-            f["mpc-sum"] += dep[7]
-        self.num_samples += 1  # KM:1557
+            ptrs = (C.c_void_p * NFIELDS)(*[dict.__getitem__(f, name).ctypes.data for name in _SAMPLE_NAMES])
+            self._check(self.lib.sfgpu_get_samples(self._ctx, self._sp, k, ptrs, None))
+            self._samp_step[k] = self._step_no
 
     def clearSamples(self):  # KM:1509-1528
-        for f in self.fields:
-            for k in ("count-sum", "u-sum", "v-sum", "w-sum", "uu-sum", "vv-sum", "ww-sum", "mpc-sum"):
-                f[k][:] = 0
-        self.num_samples = 0
+        self._check(self.lib.sfgpu_clear_samples(self._ctx, self._sp))
+        self._samp_step = [-1] * len(self.meshes)
 
     # ------------------------------------------------------------------ outputs
     def getNp(self, mesh=None):  # KM:1297 / :1385
@@ -309,6 +368,11 @@ class KineticMaterial:
 
     def sync(self):
         self._check(self.lib.sfgpu_sync(self._ctx))
+
+    def lastStepFallback(self):
+        n = C.c_int64()
+        self._check(self.lib.sfgpu_last_step_counters(self._ctx, C.byref(n)))
+        return n.value
 
     def sort(self):
         """Explicit cell sort + compaction of the device store (sfgpu_sort)."""

@@ -86,6 +86,8 @@ def test_move_and_deposit_match_oracle(dom, bc, flags):
             compare_state(km, ok)
             compare_fields(km, ok)
         assert km.num_samples == ok.num_samples == 5
+        km.clearSamples()  # KM:1509-1528
+        assert km.num_samples == 0 and not km.fields[0]["count-sum"].any() and not km.fields[0]["mpc-sum"].any()
 
 
 @pytest.mark.parametrize("flags", PATHS)
