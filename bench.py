@@ -145,6 +145,7 @@ def main():
     import torch
     import torch.distributed as dist
     from starfish_b200 import KineticMaterial, Particles
+    from starfish_b200.parallel import attach_communicator
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: starfish_b200 has no CPU fallback")
@@ -164,10 +165,7 @@ def main():
         pinned = km.hostArray((m.ni, m.nj))
         pinned[...] = getattr(m, name)
         setattr(m, name, pinned)
-    if world > 1:
-        ids = [KineticMaterial.commUniqueId() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        km.commInit(world, rank, ids[0])
+    attach_communicator(km)  # NCCL communicator of the library: rank 0 makes the id, torch.distributed carries it
     # this rank's shard: particle indices [rank*n_rank, (rank+1)*n_rank) of the global population
     chunk = 1 << 22
     for first in range(0, n_rank, chunk):
@@ -203,7 +201,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+    time.sleep(0.3)
+    barrier()  # every rank enters the timed region together
     launches0 = km.launchCount()
     ker_ms, pushes, fallback = 0.0, 0, 0
     t0 = time.perf_counter()

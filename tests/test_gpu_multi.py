@@ -1,0 +1,78 @@
+"""Two GPUs: particles partitioned by index, mesh replicated, NCCL allreduce of the deposit inside sfgpu_step.
+Particle state must be bit-identical to the single-population oracle, the summed deposit within 1e-10."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from starfish_b200 import KineticMaterial, Particles, synthetic as S
+    from starfish_b200.parallel import attach_communicator, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wl = S.config_b(ni=96, nj=80, bc="open")
+        n = 200001
+        first, count = shard_bounds(n, rank, world)
+        arr = wl.particles(first, count)
+        arr["id"] = np.arange(first, first + count, dtype=np.int32)
+        with KineticMaterial("O+", wl.charge, wl.mass, [wl.mesh], wl.mesh.domain_type, device=rank) as km:
+            km.dt = wl.dt
+            attach_communicator(km)
+            km.addParticles(wl.mesh, Particles(count, **arr), wl.dt)
+            for _ in range(5):
+                km.updateFields()
+            p = km.getParticles(wl.mesh).sorted_by_id()
+            np.savez(os.path.join(out, f"rank{rank}.npz"), dep=km.last_deposit[0], nd=km.getDen(wl.mesh), id=p.id, x=p.x, y=p.y, u=p.u,
+                     v=p.v, sums=np.array([km.mass_sum, *km.momentum_sum, km.energy_sum]), np_=km.getNp(), n_exited=km.n_exited)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpus_match_single_population_oracle(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import oracle as O
+    from starfish_b200 import synthetic as S
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    wl = S.config_b(ni=96, nj=80, bc="open")
+    n = 200001
+    ok = O.OracleKM(wl.charge, wl.mass, [wl.mesh])
+    ok.addParticles(0, wl.particles(0, n), wl.dt)
+    for _ in range(5):
+        ok.updateFields(wl.dt)
+    r = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
+    assert np.array_equal(r[0]["dep"], r[1]["dep"])  # allreduce leaves the same sum on every rank
+    scale = np.abs(ok.raw[0]).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(r[0]["dep"] - ok.raw[0]) <= 1e-10 * scale)
+    assert np.array_equal(r[0]["dep"][7], ok.raw[0][7])
+    assert np.allclose(r[0]["nd"], ok.fields[0]["nd"], rtol=1e-10, atol=1e-10 * np.abs(ok.fields[0]["nd"]).max())
+    want = np.array([ok.mass_sum, *ok.momentum_sum, ok.energy_sum])
+    assert np.allclose(r[0]["sums"], want, rtol=1e-10, atol=1e-10 * abs(want[4]))
+    assert int(r[0]["np_"]) + int(r[1]["np_"]) == ok.getNp()
+    assert int(r[0]["n_exited"]) + int(r[1]["n_exited"]) == ok.n_exited
+    ids = np.concatenate([r[0]["id"], r[1]["id"]])
+    o = np.argsort(ids)
+    full = ok.sorted_parts(0)
+    assert np.array_equal(ids[o], full["id"])
+    for key in ("x", "y", "u", "v"):
+        assert np.array_equal(np.concatenate([r[0][key], r[1][key]])[o], full[key]), key
