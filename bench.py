@@ -194,9 +194,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # config C: a beam leaves through the open faces and is re-injected at z = 0+ at the same rate (a pool of
+    # pre-generated injection batches in host memory; uploading one is part of every step of this workload)
+    inject = None
+    if wname == "c":
+        n_inj = max(1, int(round(n_rank * 0.5 / (m.nj - 1))))  # drift 0.5 cells/step over nj-1 cells
+        pool = []
+        for k in range(8):
+            arr = wl.particles((world + rank) * n_rank + k * n_inj, n_inj)
+            arr["y"] = m.x0[1] + (arr["y"] - m.x0[1]) * (0.5 / (m.nj - 1))  # inside the first half cell
+            pool.append(Particles(n_inj, **arr))
+        state = {"k": 0}
+
+        def inject():
+            km.addParticles(m, pool[state["k"] % len(pool)], wl.dt)
+            state["k"] += 1
+
+    def one_step():
+        if inject:
+            inject()
+        km.step_raw(wl.dt)
+
     # ---- device-resident throughput ------------------------------------------------------------------
     for _ in range(args.warmup):
-        km.step_raw(wl.dt)
+        one_step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -208,8 +229,8 @@ def main():
     t0 = time.perf_counter()
     km.timerStart()
     for _ in range(args.steps):
-        pushes += km.getNp()
-        km.step_raw(wl.dt)
+        one_step()
+        pushes += km.getNp() + km.n_exited_last()
         _tot, ker, _n = km.lastStepTiming()
         ker_ms += ker
         fallback += km.lastStepFallback()
@@ -225,15 +246,19 @@ def main():
 
     # ---- end to end through the plugin API: E upload + step + deposit/moment download, host buffers ------
     for _ in range(2):
+        if inject:
+            inject()
         km.setFields(m)
         km.updateFields()
     barrier()
     e_pushes = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e_pushes += km.getNp()
+        if inject:
+            inject()
         km.setFields(m)       # host -> device: efi, efj of this step (the Java solver's output)
-        km.updateFields()     # step + device -> host: nd/u/v/w and the mover sums (velocity-moment sums stay on the device)
+        km.updateFields()
+        e_pushes += km.getNp() + km.n_exited     # step + device -> host: nd/u/v/w and the mover sums (velocity-moment sums stay on the device)
     barrier()
     e2e_s = allmax(time.perf_counter() - t0)
     e2e_value = allsum(float(e_pushes)) / e2e_s

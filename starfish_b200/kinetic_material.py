@@ -369,6 +369,12 @@ class KineticMaterial:
     def sync(self):
         self._check(self.lib.sfgpu_sync(self._ctx))
 
+    def n_exited_last(self):
+        """Particles that left through OPEN faces in the last step (they were pushed in it)."""
+        n = C.c_int64()
+        self._check(self.lib.sfgpu_get_sums(self._ctx, self._sp, None, None, C.byref(n), None))
+        return n.value
+
     def lastStepFallback(self):
         n = C.c_int64()
         self._check(self.lib.sfgpu_last_step_counters(self._ctx, C.byref(n)))
