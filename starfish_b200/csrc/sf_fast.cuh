@@ -19,7 +19,9 @@
 #pragma once
 #include "sf_generic.cuh"
 
+#ifndef SF_FAST_WARPS
 #define SF_FAST_WARPS 4 // warps per CTA of the tiled kernel
+#endif
 #ifndef SF_PPT
 #define SF_PPT 1        // particles per lane and batch (independent instruction streams hide FP64 latency)
 #endif
@@ -28,7 +30,11 @@
 #endif
 #define SF_WROW (32 * SF_PPT + 2) // padded row of the per-warp scratch (doubles): conflict-free 128-bit reads
 #define SF_TILE_DOUBLES (SFGPU_NFIELDS * SF_NT * SF_NT)
-#define SF_SCRATCH_DOUBLES (8 + 13 * SF_WROW + 16 * SF_PPT + 2 * 7 * 32 * SF_PPT)
+#ifndef SF_STAGE
+#define SF_STAGE 1 // 1: cp.async prefetch of the next batch through shared memory; 0: plain loads, 3.5 KB less per warp
+#endif
+#define SF_EXTRA 6 // per-warp sums next to the tile: energy, fallback N/Px/Py/Pz/E (the fallback count rides in the tag of E)
+#define SF_SCRATCH_DOUBLES (SF_EXTRA + 12 * SF_WROW + 16 * SF_PPT + 2 + SF_STAGE * 2 * 7 * 32 * SF_PPT)
 #define SF_WARP_SMEM_BYTES ((SF_TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8)
 
 __device__ __forceinline__ double sf_vacant() { return __longlong_as_double(0x7ff8000000000001LL); }
@@ -153,7 +159,7 @@ __device__ __noinline__ bool fast_general(const FastStepArgs *__restrict__ ga, u
 
 // a particle that deposits outside the warp tile (drifted since the last sort): global FP64 REDs for the fields,
 // and its mover sums (KM:406-413) into the warp's shared-memory slots (CAS atomics: only lanes of this warp contend)
-__device__ __noinline__ void fast_fallback(const MeshDev *mp, const PState *pp, double *dep, double *extra)
+__device__ __noinline__ void fast_fallback(const MeshDev *mp, const PState *pp, double *dep, double *extra, int *nfall)
 {
     const PState &p = *pp;
     deposit_global(*mp, p, dep);
@@ -162,7 +168,7 @@ __device__ __noinline__ void fast_fallback(const MeshDev *mp, const PState *pp, 
     atomicAdd(extra + 3, p.mpw * p.v);
     atomicAdd(extra + 4, p.mpw * p.w);
     atomicAdd(extra + 5, p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w));
-    atomicAdd(extra + 6, 1.0);
+    atomicAdd(nfall, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -249,22 +255,26 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *tile = reinterpret_cast<double *>(smem_raw + (size_t)wid * SF_WARP_SMEM_BYTES);
-    double *sW = tile + SF_TILE_DOUBLES + 8; // tile, 8 extra sums of the warp (energy, fallback N/P/E/count), then [4][SF_WROW] weights, [9][SF_WROW] values
+    __shared__ __align__(16) double sOnes[32 * SF_PPT]; // weight and value of the counting lane
+    double *sW = tile + SF_TILE_DOUBLES + SF_EXTRA; // tile, extra sums of the warp (energy, fallback N/P/E), then [4][SF_WROW] weights, [9][SF_WROW] values
     double *sV = sW + 4 * SF_WROW;
-    int *sKey = reinterpret_cast<int *>(sV + 9 * SF_WROW); // [32 * SF_PPT] tile-local cell of each row
-    double *sIn = reinterpret_cast<double *>(sKey + 32 * SF_PPT); // [2 stages][7][32 * SF_PPT] prefetched particle state
+    int *sKey = reinterpret_cast<int *>(sV + 8 * SF_WROW); // [32 * SF_PPT] tile-local cell of each row, then the fallback count
+    double *sIn = reinterpret_cast<double *>(sKey + 32 * SF_PPT + 4); // [2 stages][7][32 * SF_PPT] prefetched particle state
     const MeshDev &m = a.m;
     const size_t plane = (size_t)m.ni * m.nj;
     const bool simple_ok = !m.has_b && !m.any_seg && a.dt > 0;
 
-    for (int k = lane; k < SF_TILE_DOUBLES + 8; k += 32) tile[k] = 0.0;
+    for (int k = lane; k < SF_TILE_DOUBLES + SF_EXTRA; k += 32) tile[k] = 0.0;
+    if (lane == 0) sKey[32 * SF_PPT] = 0;
+    for (int k = threadIdx.x; k < 32 * SF_PPT; k += blockDim.x) sOnes[k] = 1.0;
+    __syncthreads();
 
     // role of this lane in the reduction: node n (w00,w10,w11,w01) x field f (7 moments; f == 7: n == 0 counts the
     // particles of the cell (mpc), n == 1 sums mpw*|vel| of the whole work item (energy sum, KM:412))
     const int rn = lane >> 3, rf = lane & 7;
     const int noff = (rn == 0) ? 0 : (rn == 1) ? SF_NT : (rn == 2) ? SF_NT + 1 : 1;
-    const double *rw = (rf == 7) ? (sV + 7 * SF_WROW) : (sW + rn * SF_WROW); // f == 7 lanes: weight 1.0
-    const double *rv = sV + ((rf == 7 && rn == 1) ? 8 : rf) * SF_WROW;
+    const double *rw = (rf == 7) ? sOnes : (sW + rn * SF_WROW); // f == 7 lanes: weight 1.0
+    const double *rv = (rf == 7 && rn != 1) ? sOnes : (sV + rf * SF_WROW); // row 7 of sV = mpw*|vel|
     const bool renergy = rf == 7 && rn == 1;
     double *racc = renergy ? (tile + SF_TILE_DOUBLES) : (tile + rf * (SF_NT * SF_NT) + ((rf == 7) ? 0 : noff));
     const int rmul = renergy ? 0 : 1;
@@ -279,7 +289,9 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
         const WorkItem wi = a.items[it];
         const int ti0 = (wi.tile / a.ntj) * SF_TILE - SF_HALO; // first node row / column held by the tile
         const int tj0 = (wi.tile % a.ntj) * SF_TILE - SF_HALO;
+#if SF_STAGE
         sf_prefetch_batch(a.fs, sIn, (size_t)wi.begin, 0, wi.count, lane);
+#endif
         for (int b = 0; b < wi.count; b += 32 * SF_PPT) {
             PState p[SF_PPT];
             bool present[SF_PPT], done[SF_PPT];
@@ -287,21 +299,30 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
             long long w0bits[SF_PPT];
             // ---- the batch was prefetched into shared memory with cp.async while the previous one was processed;
             //      start the next one now (global-memory latency hidden behind ~700 instructions of work) ----
+#if SF_STAGE
             const int stage = (b / (32 * SF_PPT)) & 1;
             const bool more = b + 32 * SF_PPT < wi.count;
             if (more) sf_prefetch_batch(a.fs, sIn + (stage ^ 1) * (7 * 32 * SF_PPT), (size_t)wi.begin, b + 32 * SF_PPT, wi.count, lane);
             if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
 #pragma unroll
             for (int j = 0; j < SF_PPT; j++) {
                 const int o = b + j * 32 + lane;
                 present[j] = o < wi.count;
                 p[j].mpw = sf_vacant();
                 if (present[j]) {
+#if SF_STAGE
                     const double *in = sIn + stage * (7 * 32 * SF_PPT) + j * 32 + lane;
                     p[j].x = in[0 * 32 * SF_PPT]; p[j].y = in[1 * 32 * SF_PPT]; p[j].z = in[2 * 32 * SF_PPT];
                     p[j].u = in[3 * 32 * SF_PPT]; p[j].v = in[4 * 32 * SF_PPT]; p[j].w = in[5 * 32 * SF_PPT];
                     p[j].mpw = in[6 * 32 * SF_PPT];
+#else
+                    const size_t q = (size_t)wi.begin + o;
+                    p[j].x = a.fs.x[q]; p[j].y = a.fs.y[q]; p[j].z = a.fs.z[q];
+                    p[j].u = a.fs.u[q]; p[j].v = a.fs.v[q]; p[j].w = a.fs.w[q];
+                    p[j].mpw = a.fs.mpw[q];
+#endif
                 }
             }
             // ---- common case, branch free ----
@@ -343,7 +364,7 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                         key[j] = li_ * SF_NT + lj_;
                     } else {
                         const PState t = p[j];
-                        fast_fallback(&ga->m, &t, a.dep, tile + SF_TILE_DOUBLES);
+                        fast_fallback(&ga->m, &t, a.dep, tile + SF_TILE_DOUBLES, sKey + 32 * SF_PPT);
                     }
                 }
             }
@@ -374,13 +395,12 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                     sW[3 * SF_WROW + row] = dw[j].w01;
 #pragma unroll
                     for (int f = 0; f < 7; f++) sV[f * SF_WROW + row] = val[f];
-                    sV[7 * SF_WROW + row] = 1.0;
-                    sV[8 * SF_WROW + row] = p[j].mpw * sqrt(p[j].u * p[j].u + p[j].v * p[j].v + p[j].w * p[j].w); // KM:412
+                    sV[7 * SF_WROW + row] = p[j].mpw * sqrt(p[j].u * p[j].u + p[j].v * p[j].v + p[j].w * p[j].w); // KM:412
                 } else {
 #pragma unroll
                     for (int f = 0; f < 4; f++) sW[f * SF_WROW + row] = 0.0;
 #pragma unroll
-                    for (int f = 0; f < 9; f++) sV[f * SF_WROW + row] = 0.0;
+                    for (int f = 0; f < 8; f++) sV[f * SF_WROW + row] = 0.0;
                 }
             }
             __syncwarp();
@@ -445,13 +465,15 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
         if (lane == 0) {
             double *ex = tile + SF_TILE_DOUBLES;
-            if (s0 != 0 || ex[6] != 0) {
+            const int nf = sKey[32 * SF_PPT];
+            if (s0 != 0 || nf != 0) {
                 atomicAdd(&a.c->sums[0], s0 + ex[1]); atomicAdd(&a.c->sums[1], s1 + ex[2]); atomicAdd(&a.c->sums[2], s2 + ex[3]);
                 atomicAdd(&a.c->sums[3], s3 + ex[4]); atomicAdd(&a.c->sums[4], ex[0] + ex[5]);
-                if (ex[6] != 0) atomicAdd(&a.c->n_fallback, (unsigned long long)ex[6]);
+                if (nf != 0) atomicAdd(&a.c->n_fallback, (unsigned long long)nf);
             }
 #pragma unroll
-            for (int k = 0; k < 8; k++) ex[k] = 0.0;
+            for (int k = 0; k < SF_EXTRA; k++) ex[k] = 0.0;
+            sKey[32 * SF_PPT] = 0;
         }
         __syncwarp();
     }
