@@ -458,6 +458,8 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_step, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         if (per_sm < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
         ctx->fast_grid = nsm * per_sm;
+        if (const char *e = getenv("SFGPU_FAST_GRID")) ctx->fast_grid = atoi(e) > 0 ? atoi(e) : ctx->fast_grid; // occupancy experiments
+        if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_fast_step %d CTAs/SM x %d warps, %d B dynamic smem per CTA, grid %d\n", per_sm, SF_FAST_WARPS, (int)(SF_FAST_WARPS * SF_WARP_SMEM_BYTES), ctx->fast_grid);
         // bit-parity self test: a*b+c must round twice
         double *d = nullptr, h = 0;
         CU(cudaMalloc(&d, sizeof(double)));

@@ -26,8 +26,12 @@ struct WorkItem {
     int tile; // ti * ntj + tj
 };
 
+#ifndef SF_TILE
 #define SF_TILE 8       // cells per tile edge
+#endif
+#ifndef SF_HALO
 #define SF_HALO 2       // extra cells kept around the tile in the warp-private accumulation tile
+#endif
 #define SF_NT (SF_TILE + 2 * SF_HALO + 1) // nodes per edge of the accumulation tile
 #define SF_ITEM_MAX 2048 // particles per work item
 
