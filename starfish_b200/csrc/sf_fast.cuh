@@ -423,12 +423,14 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                             const int k = k0 + 2 * h;
                             if ((bmask[j] >> k) & 1u) {
                                 if (cur >= 0 && rflush) racc[cur * rmul] += acc;
+                                __syncwarp(); // the next run may touch the same node from another lane
                                 acc = 0.0;
                                 cur = sKey[j * 32 + k];
                             }
                             acc = __fma_rn(w2[h].x, v2[h].x, acc);
                             if ((bmask[j] >> (k + 1)) & 1u) {
                                 if (cur >= 0 && rflush) racc[cur * rmul] += acc;
+                                __syncwarp();
                                 acc = 0.0;
                                 cur = sKey[j * 32 + k + 1];
                             }
