@@ -363,6 +363,28 @@ class KM:
                 keep.append(part)
         return keep, [N, P0, P1, P2, E]
 
+    def finish_slow(self, m, part, old, old_lc, bounces):
+        """What the Java host does with a particle handed over by sfgpu_take_slowpath: ProcessBoundary on the
+        pre-ProcessBoundary state (KM:387), then the remaining sub-steps of the mover loop (KM:360-398).
+        Returns True if the particle is still alive in mesh m."""
+        mesh = self.meshes[m]
+        res = self.process_boundary(m, part, old, old_lc)
+        while res == "alive" and part.dt > 0 and bounces < 10:
+            bounces += 1
+            old = [part.pos[0], part.pos[1]]
+            old_lc = [part.lc[0], part.lc[1]]
+            part.pos[0] += part.vel[0] * part.dt
+            part.pos[1] += part.vel[1] * part.dt
+            if mesh.domain_type == XY:
+                part.pos[2] += part.vel[2] * part.dt
+            else:
+                raise NotImplementedError("finish_slow: XY only in this test helper")
+            part.lc = mesh.XtoL(part.pos)
+            res = self.process_boundary(m, part, old, old_lc)
+        if res == "dead":
+            self.n_exited += 1
+        return res == "alive"
+
     def updateFields(self, dt):  # KM:117-163
         self.slow, self.n_exited = [], 0
         self.sums = [0.0] * 5

@@ -172,6 +172,59 @@ def test_slow_path_classification(flags):
 
 
 @pytest.mark.parametrize("flags", PATHS)
+def test_slow_path_round_trip_with_survivors(flags):
+    """Full slow-path protocol: sfgpu_step(DEFER_FINISH) -> sfgpu_take_slowpath -> the host runs ProcessBoundary and the
+    remaining sub-steps (here: the Python restatement of the Java, with segment nodes that carry no real segment) ->
+    sfgpu_inject(DEPOSIT_NOW) -> sfgpu_finish_step.  With fictitious segments the end state must equal a run on a
+    mesh without any segment node, bit for bit."""
+    import pyref
+    m = S.make_mesh(36, 30, DomainType.XY, 1e-3, "symmetry")
+    m.has_seg[10:14, 8:12] = 1
+    m.has_seg[25, :] = 1
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 77, vth_cells=1.3, kick_frac=0.1)
+    arr = wl.particles(0, 8000)
+    plain = S.make_mesh(36, 30, DomainType.XY, 1e-3, "symmetry")  # same mesh, no segment nodes
+    plain.efi, plain.efj = m.efi, m.efj
+    km = KineticMaterial("ion", wl.charge, wl.mass, [m], DomainType.XY, step_flags=flags)
+    ok = O.OracleKM(wl.charge, wl.mass, [plain])
+    km.dt = wl.dt
+    pm = pyref.Mesh(m.ni, m.nj, m.x0, m.dh, 0)
+    for f in range(4):
+        pm.bc[f] = [int(v) for v in m.bc[f]]
+    host = pyref.KM(wl.charge, wl.mass, [pm])  # has_seg all zero: no real segments anywhere
+    handed = []
+
+    def handler(_km, slow, extra):
+        keep = []
+        for q in range(slow.n):
+            part = pyref.Particle([slow.x[q], slow.y[q], slow.z[q]], [slow.u[q], slow.v[q], slow.w[q]], slow.mpw[q], int(slow.id[q]))
+            part.lc, part.dt = [slow.li[q], slow.lj[q]], slow.dt[q]
+            if host.finish_slow(0, part, [extra["old_x"][q], extra["old_y"][q]], [extra["old_li"][q], extra["old_lj"][q]], int(extra["bounces"][q])):
+                keep.append((part, int(slow.born_it[q])))
+        handed.append(slow.n)
+        n = len(keep)
+        col = lambda f: np.array([f(p) for p, _b in keep], dtype=np.float64)
+        surv = Particles(n, x=col(lambda p: p.pos[0]), y=col(lambda p: p.pos[1]), z=col(lambda p: p.pos[2]), u=col(lambda p: p.vel[0]),
+                         v=col(lambda p: p.vel[1]), w=col(lambda p: p.vel[2]), mpw=col(lambda p: p.mpw), li=col(lambda p: p.lc[0]),
+                         lj=col(lambda p: p.lc[1]), dt=col(lambda p: p.dt), id=np.array([p.id for p, _b in keep], np.int32),
+                         born_it=np.array([b for _p, b in keep], np.int32))
+        return [(0, surv)]
+
+    km.slow_path_handler = handler
+    with km:
+        assert km.addParticles(m, to_particles(arr), wl.dt) == ok.addParticles(0, arr, wl.dt)
+        for _ in range(4):
+            host.n_exited = 0
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            assert km.n_exited + host.n_exited == ok.n_exited
+            km.n_exited = ok.n_exited  # exits seen by the host are the host's to count
+            compare_state(km, ok)
+            compare_fields(km, ok)
+        assert sum(handed) > 100, "the case must send particles through the slow path"
+
+
+@pytest.mark.parametrize("flags", PATHS)
 def test_injection_every_step_zero_weight_and_edges(flags):
     m = S.make_mesh(30, 20, DomainType.XY, 1e-3, "open")
     wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 33, vth_cells=0.8, kick_frac=0.1)
