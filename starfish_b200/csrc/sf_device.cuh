@@ -34,6 +34,7 @@ struct MeshDev {
     int has_b;   // bfi/bfj present
     double x0, y0, dhx, dhy;
     double lenx, leny; // xd - x0 with xd = x0 + (n-1)*dh, UM:131-135, KM:700-706
+    double nim1, njm1; // (double)(ni-1), (double)(nj-1): the KM:606 bounds without a conversion per particle
     double rdhx, rdhy; // RN(1/dh) for sf_div_exact
     int fastdiv;       // dh is a divisor sf_div_exact is proven for (host check in sfgpu_mesh_add)
     const int8_t *bc[4];

@@ -220,7 +220,7 @@ __device__ __forceinline__ bool sf_move_simple(const MeshDev &m, double qm, doub
     }
     const double li = sf_div_exact(x - m.x0, m.dhx, m.rdhx, m.fastdiv); // UM:158-159
     const double lj = sf_div_exact(y - m.y0, m.dhy, m.rdhy, m.fastdiv);
-    ok = ok && li >= 0 && lj >= 0 && li < ni - 1 && lj < nj - 1; // KM:606 (a NaN takes the general path)
+    ok = ok && li >= 0 && lj >= 0 && li < m.nim1 && lj < m.njm1; // KM:606 (a NaN takes the general path)
     if (ok) {
         p.x = x; p.y = y; p.z = z; p.u = un; p.v = vn; p.w = wn; p.li = li; p.lj = lj;
     }
@@ -417,30 +417,34 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                         w2[h] = *reinterpret_cast<const double2 *>(rw + j * 32 + k0 + 2 * h);
                         v2[h] = *reinterpret_cast<const double2 *>(rv + j * 32 + k0 + 2 * h);
                     }
-                    if ((bmask[j] >> k0) & 0xffu) { // a new cell starts inside this chunk
 #pragma unroll
-                        for (int h = 0; h < 4; h++) {
-                            const int k = k0 + 2 * h;
-                            if ((bmask[j] >> k) & 1u) {
-                                if (cur >= 0 && rflush) racc[cur * rmul] += acc;
-                                __syncwarp(); // the next run may touch the same node from another lane
-                                acc = 0.0;
-                                cur = sKey[j * 32 + k];
-                            }
-                            acc = __fma_rn(w2[h].x, v2[h].x, acc);
-                            if ((bmask[j] >> (k + 1)) & 1u) {
-                                if (cur >= 0 && rflush) racc[cur * rmul] += acc;
-                                __syncwarp();
-                                acc = 0.0;
-                                cur = sKey[j * 32 + k + 1];
-                            }
-                            acc = __fma_rn(w2[h].y, v2[h].y, acc);
-                        }
-                    } else {
+                    for (int g = 0; g < 2; g++) { // 4 rows per test: most groups of 4 hold no cell boundary once sorted
+                        const unsigned b4 = (bmask[j] >> (k0 + 4 * g)) & 0xfu;
+                        if (b4) {
 #pragma unroll
-                        for (int h = 0; h < 4; h++) {
-                            acc = __fma_rn(w2[h].x, v2[h].x, acc);
-                            acc = __fma_rn(w2[h].y, v2[h].y, acc);
+                            for (int h = 2 * g; h < 2 * g + 2; h++) {
+                                const int k = k0 + 2 * h;
+                                if ((bmask[j] >> k) & 1u) {
+                                    if (cur >= 0 && rflush) racc[cur * rmul] += acc;
+                                    __syncwarp(); // the next run may touch the same node from another lane
+                                    acc = 0.0;
+                                    cur = sKey[j * 32 + k];
+                                }
+                                acc = __fma_rn(w2[h].x, v2[h].x, acc);
+                                if ((bmask[j] >> (k + 1)) & 1u) {
+                                    if (cur >= 0 && rflush) racc[cur * rmul] += acc;
+                                    __syncwarp();
+                                    acc = 0.0;
+                                    cur = sKey[j * 32 + k + 1];
+                                }
+                                acc = __fma_rn(w2[h].y, v2[h].y, acc);
+                            }
+                        } else {
+#pragma unroll
+                            for (int h = 2 * g; h < 2 * g + 2; h++) {
+                                acc = __fma_rn(w2[h].x, v2[h].x, acc);
+                                acc = __fma_rn(w2[h].y, v2[h].y, acc);
+                            }
                         }
                     }
                 }

@@ -546,6 +546,8 @@ extern "C" int sfgpu_mesh_add(sfgpu_ctx *ctx, int32_t ni, int32_t nj, const doub
     const double xd0 = x0[0] + (ni - 1) * dh[0], xd1 = x0[1] + (nj - 1) * dh[1];
     d.lenx = xd0 - x0[0];
     d.leny = xd1 - x0[1];
+    d.nim1 = (double)(ni - 1);
+    d.njm1 = (double)(nj - 1);
     d.rdhx = 1.0 / dh[0];
     d.rdhy = 1.0 / dh[1];
     d.fastdiv = 1;
