@@ -180,6 +180,15 @@ int sfgpu_take_slowpath(sfgpu_ctx *ctx, int32_t sp, int64_t max, sfgpu_particles
 int sfgpu_download(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t first, sfgpu_particles *out);
 int sfgpu_upload(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t first, const sfgpu_particles *in);
 
+/* restart.bin, particle section of one mesh (KineticMaterial.saveRestartData / loadRestartData, KM:904-1000): the
+ * exact DataOutputStream bytes -- long np, then per particle pos/vel interleaved, lc, dt, mpw, mass, born_it, id, all
+ * big endian (96 bytes per particle), packed on the device.  save: buf NULL => only *bytes_needed is returned.
+ * load: goes through addParticle(md, part) like the reference (caller-supplied lc, -0.5dt rewind re-applied, ids
+ * re-assigned); *bytes_used tells the caller where the field section of the stream starts. */
+int sfgpu_restart_save(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, void *buf, int64_t buf_bytes, int64_t *bytes_needed);
+int sfgpu_restart_load(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const void *buf, int64_t buf_bytes, double dt_step,
+                       int64_t *bytes_used, int64_t *n_loaded);
+
 /* explicit cell sort + compaction (sortParticlesToCells, KM:1150-1179: order only, no result change) */
 int sfgpu_sort(sfgpu_ctx *ctx, int32_t sp);
 /* sfgpu_step re-sorts the store by cell every `steps` steps (default 4, env SFGPU_SORT_EVERY) */

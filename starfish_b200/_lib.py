@@ -58,6 +58,8 @@ EXPORTS = {
     "sfgpu_take_slowpath": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(Particles), C.POINTER(SlowExtra), c_int64_p]),
     "sfgpu_download": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(Particles)]),
     "sfgpu_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(Particles)]),
+    "sfgpu_restart_save": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, c_int64_p]),
+    "sfgpu_restart_load": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_double, c_int64_p, c_int64_p]),
     "sfgpu_sort": (C.c_int, [C.c_void_p, C.c_int32]),
     "sfgpu_set_sort_interval": (C.c_int, [C.c_void_p, C.c_int32]),
     "sfgpu_comm_unique_id": (C.c_int, [C.c_void_p]),

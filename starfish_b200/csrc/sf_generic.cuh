@@ -237,6 +237,30 @@ __global__ void k_moments(const double *__restrict__ dep, const double *__restri
     out4[3 * plane + k] = w;
 }
 
+// restart.bin particle records (KineticMaterial.saveRestartData, KM:904-924): per particle, big-endian (DataOutputStream),
+//   pos[0],vel[0],pos[1],vel[1],pos[2],vel[2], lc[0],lc[1], dt, mpw, mass (11 doubles), born_it, id (2 ints) = 96 bytes
+#define SF_RESTART_RECORD_BYTES 96
+__device__ __forceinline__ unsigned sf_bswap32(unsigned x) { return __byte_perm(x, 0, 0x0123); }
+__device__ __forceinline__ unsigned long long sf_be64(double d)
+{
+    const unsigned long long v = (unsigned long long)__double_as_longlong(d);
+    return ((unsigned long long)sf_bswap32((unsigned)v) << 32) | sf_bswap32((unsigned)(v >> 32));
+}
+__global__ void k_restart_pack(RecPtrs r, unsigned long long first, unsigned long long n, double mass, unsigned long long *__restrict__ out)
+{
+    const unsigned long long q0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q0 >= n) return;
+    const size_t q = first + q0;
+    unsigned long long *o = out + q0 * (SF_RESTART_RECORD_BYTES / 8);
+    o[0] = sf_be64(r.x[q]); o[1] = sf_be64(r.u[q]);
+    o[2] = sf_be64(r.y[q]); o[3] = sf_be64(r.v[q]);
+    o[4] = sf_be64(r.z[q]); o[5] = sf_be64(r.w[q]);
+    o[6] = sf_be64(r.li[q]); o[7] = sf_be64(r.lj[q]);
+    o[8] = sf_be64(r.dt[q]); o[9] = sf_be64(r.mpw[q]); o[10] = sf_be64(mass);
+    const int2 tag = r.tag[q]; // {id, born_it}; the stream holds born_it first
+    o[11] = ((unsigned long long)sf_bswap32((unsigned)tag.x) << 32) | sf_bswap32((unsigned)tag.y);
+}
+
 // running sums of updateSamples (KM:1584-1593): sums += this step's raw deposit
 __global__ void k_accumulate(double *__restrict__ sums, const double *__restrict__ dep, size_t n)
 {

@@ -1403,6 +1403,107 @@ extern "C" int sfgpu_upload(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// restart.bin particle section: KineticMaterial.saveRestartData / loadRestartData, KM:904-1000
+// ---------------------------------------------------------------------------------------------
+static inline uint64_t host_be64(uint64_t v) { return __builtin_bswap64(v); }
+
+extern "C" int sfgpu_restart_save(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, void *buf, int64_t buf_bytes, int64_t *bytes_needed)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    Species &s = ctx->species[sp];
+    Pop &pop = s.pops[mesh_id];
+    int rc = compact_if_dirty(ctx, mesh_id, pop.fast);
+    if (rc) return rc;
+    rc = sync_meshes(ctx);
+    if (rc) return rc;
+    const int64_t np = pop.fast.n + pop.cur.n;
+    const int64_t need = 8 + np * SF_RESTART_RECORD_BYTES;
+    if (bytes_needed) *bytes_needed = need;
+    if (!buf) return 0; // size query
+    if (buf_bytes < need) return fail(ctx, SFGPU_EINVAL, "sfgpu_restart_save: buffer of %lld bytes, %lld needed", (long long)buf_bytes, (long long)need);
+    unsigned char *out = (unsigned char *)buf;
+    const uint64_t np_be = host_be64((uint64_t)np); // out.writeLong(getNp()), KM:909
+    memcpy(out, &np_be, 8);
+    out += 8;
+    const int64_t chunk = 1 << 20;
+    rc = stage_reserve(ctx, (size_t)chunk * SF_RESTART_RECORD_BYTES);
+    if (rc) return rc;
+    if (ctx->tmp_bytes < (size_t)chunk * SF_RESTART_RECORD_BYTES) {
+        if (ctx->d_tmp) CU(cudaFree(ctx->d_tmp));
+        ctx->d_tmp = nullptr;
+        ctx->tmp_bytes = 0;
+        CU(cudaMalloc(&ctx->d_tmp, (size_t)chunk * SF_RESTART_RECORD_BYTES));
+        ctx->tmp_bytes = (size_t)chunk * SF_RESTART_RECORD_BYTES;
+    }
+    for (int64_t q = 0; q < np;) {
+        // a chunk never straddles the two stores; stream order = fast store, then the exceptional records
+        const bool in_fast = q < pop.fast.n;
+        const int64_t c = std::min<int64_t>(chunk, (in_fast ? pop.fast.n : np) - q);
+        if (in_fast) {
+            rc = rec_reserve(ctx, ctx->tmp, chunk, false);
+            if (rc) return rc;
+            k_fast_to_records<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, pop.fast.p, (unsigned long long)q, (unsigned long long)c, ctx->tmp.p);
+            CU(cudaGetLastError());
+            k_restart_pack<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(ctx->tmp.p, 0ULL, (unsigned long long)c, s.mass, (unsigned long long *)ctx->d_tmp);
+        } else {
+            k_restart_pack<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(pop.cur.p, (unsigned long long)(q - pop.fast.n), (unsigned long long)c, s.mass, (unsigned long long *)ctx->d_tmp);
+        }
+        CU(cudaGetLastError());
+        ctx->launch_total += in_fast ? 2 : 1;
+        CU(cudaMemcpyAsync(ctx->stage, ctx->d_tmp, (size_t)c * SF_RESTART_RECORD_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        memcpy(out + q * SF_RESTART_RECORD_BYTES, ctx->stage, (size_t)c * SF_RESTART_RECORD_BYTES);
+        q += c;
+    }
+    return 0;
+}
+
+extern "C" int sfgpu_restart_load(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const void *buf, int64_t buf_bytes, double dt_step, int64_t *bytes_used, int64_t *n_loaded)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    if (!buf || buf_bytes < 8) return fail(ctx, SFGPU_EINVAL, "sfgpu_restart_load: truncated stream");
+    const unsigned char *in = (const unsigned char *)buf;
+    uint64_t np_be;
+    memcpy(&np_be, in, 8);
+    const int64_t np = (int64_t)host_be64(np_be);
+    if (np < 0 || buf_bytes < 8 + np * SF_RESTART_RECORD_BYTES) return fail(ctx, SFGPU_EINVAL, "sfgpu_restart_load: %lld records announced, stream too short", (long long)np);
+    in += 8;
+    if (bytes_used) *bytes_used = 8 + np * SF_RESTART_RECORD_BYTES;
+    int64_t loaded = 0;
+    const int64_t chunk = 1 << 18;
+    std::vector<double> col((size_t)std::min<int64_t>(chunk, std::max<int64_t>(np, 1)) * 10);
+    std::vector<int32_t> born((size_t)std::min<int64_t>(chunk, std::max<int64_t>(np, 1)));
+    for (int64_t q = 0; q < np; q += chunk) {
+        const int64_t c = std::min<int64_t>(chunk, np - q);
+        double *x = col.data(), *y = x + c, *z = y + c, *u = z + c, *v = u + c, *w = v + c, *mpw = w + c, *li = mpw + c, *lj = li + c, *dtp = lj + c;
+        for (int64_t k = 0; k < c; k++) {
+            const unsigned char *r = in + (q + k) * SF_RESTART_RECORD_BYTES;
+            uint64_t d[12];
+            memcpy(d, r, SF_RESTART_RECORD_BYTES);
+            auto dbl = [&](int i) { const uint64_t b = host_be64(d[i]); double o; memcpy(&o, &b, 8); return o; };
+            x[k] = dbl(0); u[k] = dbl(1); y[k] = dbl(2); v[k] = dbl(3); z[k] = dbl(4); w[k] = dbl(5);
+            li[k] = dbl(6); lj[k] = dbl(7); dtp[k] = dbl(8); mpw[k] = dbl(9); // d[10] = mass: the species constant
+            born[k] = (int32_t)__builtin_bswap32((uint32_t)(d[11] & 0xffffffffu)); // born_it is written first
+        }
+        // loadRestartData goes through addParticle(md, part) (KM:978): caller-supplied lc, the -0.5dt rewind is applied
+        // again and ids are re-assigned from part_id_counter (reference quirk)
+        sfgpu_particles pv{};
+        pv.n = c; pv.x = x; pv.y = y; pv.z = z; pv.u = u; pv.v = v; pv.w = w; pv.mpw = mpw; pv.li = li; pv.lj = lj; pv.dt = dtp;
+        pv.id = nullptr; pv.born_it = born.data();
+        int64_t added = 0;
+        int rc = sfgpu_inject(ctx, sp, mesh_id, &pv, dt_step, SFGPU_INJECT_REWIND, &added);
+        if (rc) return rc;
+        loaded += added;
+    }
+    if (n_loaded) *n_loaded = loaded;
+    return 0;
+}
+
 extern "C" int sfgpu_sort(sfgpu_ctx *ctx, int32_t sp)
 {
     CHECK_CTX();

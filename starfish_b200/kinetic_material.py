@@ -325,6 +325,21 @@ class KineticMaterial:
         v = parts.view()
         self._check(self.lib.sfgpu_upload(self._ctx, self._sp, mesh.index, int(first), C.byref(v)))
 
+    def saveRestartParticles(self, mesh) -> bytes:
+        """Particle section of saveRestartData for one mesh (KM:907-924): the exact DataOutputStream bytes."""
+        need = C.c_int64()
+        self._check(self.lib.sfgpu_restart_save(self._ctx, self._sp, mesh.index, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        self._check(self.lib.sfgpu_restart_save(self._ctx, self._sp, mesh.index, buf, need.value, None))
+        return buf.raw
+
+    def loadRestartParticles(self, mesh, data: bytes, dt=None):
+        """loadRestartData's particle loop (KM:961-979) from the stream bytes; returns (bytes consumed, particles added)."""
+        used, added = C.c_int64(), C.c_int64()
+        dt = self.dt if dt is None else dt
+        self._check(self.lib.sfgpu_restart_load(self._ctx, self._sp, mesh.index, data, len(data), float(dt), C.byref(used), C.byref(added)))
+        return used.value, added.value
+
     def takeSlowPath(self):
         n_slow = C.c_int64()
         self._check(self.lib.sfgpu_get_sums(self._ctx, self._sp, None, None, None, C.byref(n_slow)))

@@ -286,6 +286,41 @@ def test_sort_interval_does_not_change_results(every):
         compare_fields(km, ok)
 
 
+def test_restart_records_round_trip():
+    """restart.bin particle section (KM:904-1000): the saved bytes are the DataOutputStream layout (checked with Python's
+    big-endian struct), and loading them goes through addParticle like the reference (rewind re-applied, ids renumbered)."""
+    import struct
+    m = S.make_mesh(6, 5, DomainType.XY, 1e-3, "symmetry")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 55, vth_cells=25.0, kick_frac=0.05)  # >10 bounces: records with residual dt
+    arr = wl.particles(0, 5000)
+    km, ok = make_pair([m], wl, [arr], 0)
+    with km:
+        for _ in range(3):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+        data = km.saveRestartParticles(m)
+        p = km.getParticles(m)  # same store order as the stream
+        (np_,) = struct.unpack(">q", data[:8])
+        assert np_ == p.n == ok.getNp() and len(data) == 8 + 96 * p.n
+        rec = np.frombuffer(data, dtype=np.dtype([("d", ">f8", 11), ("born", ">i4"), ("id", ">i4")]), offset=8)
+        for col, key in enumerate(("x", "u", "y", "v", "z", "w", "li", "lj", "dt", "mpw")):
+            assert np.array_equal(rec["d"][:, col], getattr(p, key)), key
+        assert np.all(rec["d"][:, 10] == wl.mass) and np.array_equal(rec["id"], p.id) and np.array_equal(rec["born"], p.born_it)
+        assert (p.dt > 0).any() or (p.li != (p.x - m.x0[0]) / m.dh[0]).any(), "case should include exceptional records"
+        # load into a fresh material and into a fresh oracle through addParticle(md, part)
+        km2, ok2 = make_pair([m], wl, [None], 0)
+        with km2:
+            used, added = km2.loadRestartParticles(m, data + b"FIELDS...", wl.dt)
+            assert used == len(data)
+            src = {k: np.ascontiguousarray(getattr(p, k)) for k in ("x", "y", "z", "u", "v", "w", "mpw", "li", "lj", "dt")}
+            assert added == ok2.addParticles(0, src, wl.dt, rewind=True, born_it=p.born_it)
+            compare_state(km2, ok2)
+            km2.updateFields()
+            ok2.updateFields(wl.dt)
+            compare_state(km2, ok2)
+            compare_fields(km2, ok2)
+
+
 def test_download_upload_round_trip():
     m = S.make_mesh(16, 16, DomainType.XY, 1e-3, "periodic")
     wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 1)
