@@ -591,7 +591,8 @@ __global__ void k_build_items(const unsigned *__restrict__ offs, int n_tiles, Wo
 // Particles the fast store cannot represent (plus-edge clamp KM:770-773, NaN weight) go to the record list.
 __global__ void __launch_bounds__(256)
 k_inject_fast(const MeshDev *__restrict__ meshes, int mesh_id, double qm, double dt_step, int rewind, FastPtrs fs, unsigned long long first,
-              unsigned long long n, RecPtrs rec, unsigned long long rec_first, unsigned long long rec_cap, StepCounters *__restrict__ c)
+              unsigned long long n, RecPtrs rec, unsigned long long rec_first, unsigned long long rec_cap, StepCounters *__restrict__ c,
+              unsigned *__restrict__ hist, int ntj)
 {
     const MeshDev m = meshes[mesh_id];
     const GlobalFieldGather fg;
@@ -614,6 +615,7 @@ k_inject_fast(const MeshDev *__restrict__ meshes, int mesh_id, double qm, double
     }
     if (normal) {
         fs.u[q] = p.u; fs.v[q] = p.v; fs.w[q] = p.w;
+        if (hist) atomicAdd(&hist[sf_cell_key(m, p.li, p.lj, ntj)], 1u); // streaming store: population per cell key
         return;
     }
     const unsigned long long s = rec_first + atomicAdd(&c->n_exc[mesh_id], 1ULL);

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256)
 k_generic_step(const MeshDev *__restrict__ meshes, int mesh_id, double qm, double charge, double dt, int transfer,
                RecPtrs in, unsigned long long n_in, RecPtrs out, unsigned long long *__restrict__ out_cursor,
                unsigned long long out_cap, const XferDev *__restrict__ xfer, SlowPtrs slow, double *__restrict__ dep,
-               StepCounters *__restrict__ c, FastPtrs fs, unsigned long long fast_cap)
+               StepCounters *__restrict__ c, FastPtrs fs, unsigned long long fast_cap, unsigned *__restrict__ hist, int ntj)
 {
     const MeshDev m = meshes[mesh_id];
     const GlobalFieldGather fg;
@@ -111,6 +111,10 @@ k_generic_step(const MeshDev *__restrict__ meshes, int mesh_id, double qm, doubl
             fs.u[fslot] = p.u; fs.v[fslot] = p.v; fs.w[fslot] = p.w;
             fs.mpw[fslot] = p.mpw;
             fs.tag[fslot] = tag;
+            if (hist) { // streaming store: the per-cell population the next launch lays its output out by
+                const int ci = min(max(sf_j2i(p.li), 0), m.ni - 2), cj = min(max(sf_j2i(p.lj), 0), m.nj - 2);
+                atomicAdd(&hist[(unsigned)((ci / SF_TILE) * ntj + (cj / SF_TILE)) * (SF_TILE * SF_TILE) + (unsigned)((ci % SF_TILE) * SF_TILE + (cj % SF_TILE))], 1u);
+            }
         }
         const unsigned nfast = __ballot_sync(0xffffffffu, to_fast);
         if ((threadIdx.x & 31) == 0 && nfast) atomicAdd((unsigned long long *)&c->fast_delta[mesh_id], (unsigned long long)__popc(nfast));

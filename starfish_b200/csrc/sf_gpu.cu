@@ -16,6 +16,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "sf_fast.cuh"
+#include "sf_stream.cuh"
 #include "sf_generic.cuh"
 #include "sf_store.cuh"
 
@@ -108,7 +109,10 @@ struct FastStore { // cell-sorted SoA store of the normal particles of one speci
     int steps_since_sort = 0;
     unsigned *keys = nullptr, *ranks = nullptr; // per particle, sort scratch
     int64_t kr_cap = 0;
-    unsigned *hist = nullptr, *offs = nullptr;  // per cell key (+1)
+    unsigned *hist = nullptr, *offs = nullptr;  // per cell key (+1): live particles per key; segment offsets of the sorted prefix
+    // streaming step (sf_stream.cuh): histogram accumulated for the next launch, output segment offsets, output cursors
+    unsigned *hist_next = nullptr, *offs_out = nullptr, *cursor = nullptr;
+    bool stream_ok = false; // hist counts every live particle of p[0,n) and offs describes p[0,n_sorted)
     WorkItem *items = nullptr;
     unsigned *d_nitems = nullptr;
     unsigned max_items = 0, n_items = 0;
@@ -181,6 +185,10 @@ struct sfgpu_ctx {
     bool timing_valid = false;
     int sort_every = 4;      // steps between cell sorts of the fast store
     int fast_grid = 0;       // CTAs of the tiled kernel (persistent)
+    int path = 1;            // 1: streaming step (sf_stream.cuh), 0: tiled in-place step + periodic sort (sf_fast.cuh)
+    int stream_grid = 0;     // CTAs of the streaming kernel (persistent)
+    bool stream_check = false; // debug: verify the output cursors after every streaming launch
+    unsigned long long *d_bad = nullptr;
     Records tmp;             // staging records for download / upload of the fast store
     unsigned long long last_fallback = 0, last_flush = 0;
     bool force_sort = false;
@@ -275,7 +283,7 @@ static int fast_reserve(sfgpu_ctx *ctx, FastStore &f, int64_t need)
 
 static void fast_free(FastStore &f)
 {
-    void *ptrs[] = {f.slab, f.alt_slab, f.keys, f.ranks, f.hist, f.offs, f.items, f.d_nitems, f.cub_tmp};
+    void *ptrs[] = {f.slab, f.alt_slab, f.keys, f.ranks, f.hist, f.offs, f.items, f.d_nitems, f.cub_tmp, f.hist_next, f.offs_out, f.cursor};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     f = FastStore();
@@ -288,6 +296,9 @@ static int fast_init_geometry(sfgpu_ctx *ctx, FastStore &f, const MeshDev &m)
     f.nkeys = (unsigned)f.nti * f.ntj * SF_TILE * SF_TILE;
     CU(cudaMalloc(&f.hist, ((size_t)f.nkeys + 1) * sizeof(unsigned)));
     CU(cudaMalloc(&f.offs, ((size_t)f.nkeys + 1) * sizeof(unsigned)));
+    CU(cudaMalloc(&f.hist_next, ((size_t)f.nkeys + 1) * sizeof(unsigned)));
+    CU(cudaMalloc(&f.offs_out, ((size_t)f.nkeys + 1) * sizeof(unsigned)));
+    CU(cudaMalloc(&f.cursor, ((size_t)f.nkeys + 1) * sizeof(unsigned)));
     CU(cudaMalloc(&f.d_nitems, sizeof(unsigned)));
     CU(cudaMemset(f.d_nitems, 0, sizeof(unsigned)));
     f.cub_bytes = 0;
@@ -305,6 +316,9 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     if (f.n == 0) {
         f.n_sorted = 0; f.n_items = 0; f.dirty = false;
         CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
+        CU(cudaMemsetAsync(f.hist, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
+        CU(cudaMemsetAsync(f.offs, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
+        f.stream_ok = true;
         return 0;
     }
     if ((uint64_t)f.n >= 0xfffffff0ull) return fail(ctx, SFGPU_EINVAL, "more than 2^32 particles of one species on one GPU mesh are not supported");
@@ -324,7 +338,7 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
         f.kr_cap = f.cap;
     }
     const unsigned want_items = (unsigned)(f.n / SF_ITEM_MAX + (int64_t)f.nti * f.ntj + 1);
-    if (f.max_items < want_items) {
+    if (f.max_items < want_items) { // (the streaming step re-sizes the list for its own, smaller chunks)
         if (f.items) CU(cudaFree(f.items));
         f.items = nullptr; f.max_items = 0;
         CU(cudaMalloc(&f.items, (size_t)want_items * sizeof(WorkItem)));
@@ -355,6 +369,22 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     f.n = f.n_sorted = (int64_t)tot[0];
     f.n_items = tot[1] < f.max_items ? tot[1] : f.max_items;
     f.dirty = false;
+    f.stream_ok = true; // hist = live particles per key, offs = their segment offsets
+    return 0;
+}
+
+// second slab of the fast store: sort target / output of the streaming step
+static int fast_reserve_alt(sfgpu_ctx *ctx, FastStore &f)
+{
+    if (f.alt_cap >= f.cap) return 0;
+    if (f.alt_slab) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(f.alt_slab));
+    }
+    f.alt_slab = nullptr; f.alt_cap = 0;
+    CU(cudaMalloc(&f.alt_slab, (size_t)f.cap * SF_FAST_BYTES_PER_PARTICLE));
+    f.alt_cap = f.cap;
+    fast_bind(f.alt, f.alt_slab, f.alt_cap);
     return 0;
 }
 
@@ -459,6 +489,16 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         if (per_sm < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
         ctx->fast_grid = nsm * per_sm;
         if (const char *e = getenv("SFGPU_FAST_GRID")) ctx->fast_grid = atoi(e) > 0 ? atoi(e) : ctx->fast_grid; // occupancy experiments
+        CU(cudaFuncSetAttribute(k_stream_step, cudaFuncAttributeMaxDynamicSharedMemorySize, SFS_SMEM_BYTES));
+        int per_sm_s = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_stream_step, SFS_THREADS, SFS_SMEM_BYTES));
+        if (per_sm_s < 1) return fail(ctx, SFGPU_ECUDA, "k_stream_step does not fit on this device");
+        ctx->stream_grid = nsm * per_sm_s;
+        if (const char *e = getenv("SFGPU_STREAM_GRID")) ctx->stream_grid = atoi(e) > 0 ? atoi(e) : ctx->stream_grid;
+        if (const char *e = getenv("SFGPU_PATH")) ctx->path = strcmp(e, "tiled") == 0 ? 0 : 1;
+        ctx->stream_check = getenv("SFGPU_STREAM_CHECK") != nullptr;
+        CU(cudaMalloc(&ctx->d_bad, sizeof(unsigned long long)));
+        if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_stream_step %d CTAs/SM x %d threads, %d B dynamic smem per CTA, grid %d, path %s\n", per_sm_s, SFS_THREADS, (int)SFS_SMEM_BYTES, ctx->stream_grid, ctx->path ? "stream" : "tiled");
         if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_fast_step %d CTAs/SM x %d warps, %d B dynamic smem per CTA, grid %d\n", per_sm, SF_FAST_WARPS, (int)(SF_FAST_WARPS * SF_WARP_SMEM_BYTES), ctx->fast_grid);
         // bit-parity self test: a*b+c must round twice
         double *d = nullptr, h = 0;
@@ -514,6 +554,7 @@ extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     if (ctx->d_xfer) cudaFree(ctx->d_xfer);
     if (ctx->d_args) cudaFree(ctx->d_args);
+    if (ctx->d_bad) cudaFree(ctx->d_bad);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -797,7 +838,8 @@ static int inject_fast(sfgpu_ctx *ctx, Species &s, int mesh_id, const sfgpu_part
         CU(cudaMemsetAsync(&ctx->d_cnt->overflow, 0, sizeof(unsigned long long), ctx->stream));
         k_inject_fast<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, s.qm, dt_step, (flags & SFGPU_INJECT_REWIND) ? 1 : 0,
                                                                                f.p, (unsigned long long)f.n, (unsigned long long)c, pop.cur.p,
-                                                                               (unsigned long long)pop.cur.n, (unsigned long long)pop.cur.cap, ctx->d_cnt);
+                                                                               (unsigned long long)pop.cur.n, (unsigned long long)pop.cur.cap, ctx->d_cnt,
+                                                                               f.stream_ok ? f.hist : nullptr, f.ntj);
         ctx->launch_total++;
         CU(cudaGetLastError());
         int rc2 = 0;
@@ -949,14 +991,26 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         rc = push_xfer_table(ctx, s);
         if (rc) return rc;
     }
-    // K3: periodic cell sort + compaction of the fast store (keeps the tiled kernel's accesses coherent)
+    const bool stream = ctx->path == 1 && !untiled && !(flags & SFGPU_STEP_INPLACE);
+    // K3: cell sort + compaction of the fast store.  Streaming path: the step kernel itself re-sorts, a separate sort only
+    // (re-)establishes the invariant (first step, after in-place edits).  Tiled path: periodic sort.
     for (int m = 0; m < nmesh; m++) {
         FastStore &f = s.pops[m].fast;
-        if (untiled || f.n == 0) continue;
+        if (untiled) { f.stream_ok = false; continue; }
+        if (stream) {
+            if (!f.stream_ok) {
+                rc = fast_sort(ctx, m, f);
+                if (rc) return rc;
+            }
+            continue;
+        }
+        f.stream_ok = false; // the in-place step moves particles between cells without telling the histogram
+        if (f.n == 0) continue;
         const int64_t tail = f.n - f.n_sorted;
         if (f.n_sorted == 0 || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n || ctx->force_sort) {
             rc = fast_sort(ctx, m, f);
             if (rc) return rc;
+            f.stream_ok = false;
         }
     }
     for (int m = 0; m < nmesh; m++) {
@@ -970,6 +1024,20 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             rc = fast_reserve(ctx, pop.fast, pop.fast.n + pop.cur.n + (multi ? n_total : 0));
             if (rc) return rc;
         }
+        if (stream) {
+            FastStore &f = pop.fast;
+            if (f.cap > 0) {
+                rc = fast_reserve_alt(ctx, f);
+                if (rc) return rc;
+            }
+            const unsigned want_items = (unsigned)(f.n / SFS_CHUNK + (int64_t)f.nti * f.ntj + 16);
+            if (f.max_items < want_items) {
+                if (f.items) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(f.items)); }
+                f.items = nullptr; f.max_items = 0;
+                CU(cudaMalloc(&f.items, (size_t)want_items * sizeof(WorkItem)));
+                f.max_items = want_items;
+            }
+        }
     }
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
@@ -978,7 +1046,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         unsigned long long pre[2 * SF_MAX_MESHES] = {0};
         for (int m = 0; m < nmesh; m++) {
             pre[m] = (unsigned long long)s.pops[m].xout.n;
-            pre[SF_MAX_MESHES + m] = (unsigned long long)s.pops[m].fast.n;
+            pre[SF_MAX_MESHES + m] = (unsigned long long)(stream ? s.pops[m].fast.alive : s.pops[m].fast.n); // streaming: behind the re-sorted output
         }
         memcpy(ctx->h_cnt->xfer_n, pre, sizeof(unsigned long long) * SF_MAX_MESHES);
         memcpy(ctx->h_cnt->fast_n, pre + SF_MAX_MESHES, sizeof(unsigned long long) * SF_MAX_MESHES);
@@ -995,7 +1063,43 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     for (int m = 0; m < nmesh; m++) {
         Pop &pop = s.pops[m];
         FastStore &f = pop.fast;
-        if (f.n > 0) {
+        if (stream) {
+            // output layout of this launch = exclusive scan of the live population per cell key (accumulated by the previous
+            // launch, injections included); the launch accumulates the next one
+            CU(cub::DeviceScan::ExclusiveSum(f.cub_tmp, f.cub_bytes, f.hist, f.offs_out, (int)(f.nkeys + 1), ctx->stream));
+            CU(cudaMemcpyAsync(f.cursor, f.offs_out, (size_t)f.nkeys * sizeof(unsigned), cudaMemcpyDeviceToDevice, ctx->stream));
+            CU(cudaMemsetAsync(f.hist_next, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
+            { ctx->last_launches++; ctx->launch_total++; }
+            if (f.n > 0) {
+                CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
+                if (f.n_sorted > 0) {
+                    const int n_tiles = f.nti * f.ntj;
+                    k_build_chunks<<<(n_tiles + 127) / 128, 128, 0, ctx->stream>>>(f.offs, n_tiles, f.items, f.d_nitems, f.max_items);
+                    CU(cudaGetLastError());
+                    { ctx->last_launches++; ctx->launch_total++; }
+                }
+                StreamArgs sa{};
+                sa.b = fast_args(ctx, s, m, dt, slow);
+                sa.out = f.alt;
+                sa.cursor = f.cursor;
+                sa.hist_next = f.hist_next;
+                sa.tail_first = (unsigned long long)f.n_sorted;
+                sa.tail_n = (unsigned long long)(f.n - f.n_sorted);
+                sa.n_tail_items = (unsigned)((f.n - f.n_sorted + SFS_CHUNK - 1) / SFS_CHUNK);
+                CU(cudaMemcpyAsync(ctx->d_args + m, &sa.b, sizeof sa.b, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
+                k_stream_step<<<ctx->stream_grid, SFS_THREADS, SFS_SMEM_BYTES, ctx->stream>>>(sa, ctx->d_args + m);
+                CU(cudaGetLastError());
+                { ctx->last_launches++; ctx->launch_total++; }
+                if (ctx->stream_check) {
+                    CU(cudaMemsetAsync(ctx->d_bad, 0, sizeof(unsigned long long), ctx->stream));
+                    k_stream_check<<<(f.nkeys + 255) / 256, 256, 0, ctx->stream>>>(f.offs_out, f.cursor, f.nkeys, ctx->d_bad);
+                    unsigned long long bad = 0;
+                    CU(cudaMemcpyAsync(&bad, ctx->d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                    if (bad) return fail(ctx, SFGPU_ESTATE, "internal: %llu cell segments of the streaming step were not filled exactly", bad);
+                }
+            }
+        } else if (f.n > 0) {
             const FastStepArgs a = fast_args(ctx, s, m, dt, slow);
             int64_t tail_first = 0;
             if (!untiled && f.n_sorted > 0 && f.n_items > 0) {
@@ -1015,7 +1119,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         if (pop.cur.n == 0) continue;
         k_generic_step<<<grid_for(pop.cur.n, 256, 148 * 32), 256, 0, ctx->stream>>>(
             ctx->d_meshes, m, s.qm, s.charge, dt, 0, pop.cur.p, (unsigned long long)pop.cur.n, pop.nxt.p,
-            &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt, f.p, (unsigned long long)f.cap);
+            &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt, stream ? f.alt : f.p,
+            (unsigned long long)(stream ? f.alt_cap : f.cap), stream ? f.hist_next : nullptr, f.ntj);
         CU(cudaGetLastError());
         { ctx->last_launches++; ctx->launch_total++; }
     }
@@ -1050,8 +1155,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                 if (pop.xin.n == 0) continue;
                 k_generic_step<<<grid_for(pop.xin.n, 256, 148 * 32), 256, 0, ctx->stream>>>(
                     ctx->d_meshes, m, s.qm, s.charge, dt, 1, pop.xin.p, (unsigned long long)pop.xin.n, pop.nxt.p,
-                    &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt, pop.fast.p,
-                    (unsigned long long)pop.fast.cap);
+                    &ctx->d_cnt->n_out[m], (unsigned long long)pop.nxt.cap, ctx->d_xfer, slow, pop.dep, ctx->d_cnt, stream ? pop.fast.alt : pop.fast.p,
+                    (unsigned long long)(stream ? pop.fast.alt_cap : pop.fast.cap), stream ? pop.fast.hist_next : nullptr, pop.fast.ntj);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
                 pop.xin.n = 0;
@@ -1071,19 +1176,33 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         std::swap(pop.cur, pop.nxt);
         pop.nxt.n = 0;
         int64_t fn = (int64_t)ctx->h_cnt->fast_n[m];
-        if (fn > f.cap) fn = f.cap;
-        if (fn < f.n) fn = f.n;
-        f.n = fn;
+        if (stream) { // the second slab now holds the store: re-sorted live particles, then what the record kernels appended
+            const int64_t n_sorted = f.alive;
+            std::swap(f.p, f.alt);
+            std::swap(f.slab, f.alt_slab);
+            std::swap(f.cap, f.alt_cap);
+            std::swap(f.hist, f.hist_next);
+            std::swap(f.offs, f.offs_out);
+            if (fn > f.cap) fn = f.cap;
+            if (fn < n_sorted) fn = n_sorted;
+            f.n = fn;
+            f.n_sorted = n_sorted;
+            f.stream_ok = true;
+        } else {
+            if (fn > f.cap) fn = f.cap;
+            if (fn < f.n) fn = f.n;
+            f.n = fn;
+        }
         const long long delta = ctx->h_cnt->fast_delta[m];
         f.alive += delta;
-        if (f.alive != f.n) f.dirty = true;
+        f.dirty = f.alive != f.n;
     }
     s.n_exited = (int64_t)ctx->h_cnt->n_exited;
     s.n_removed = (int64_t)ctx->h_cnt->n_removed;
     s.slow_n = (int64_t)ctx->h_cnt->n_slow;
     ctx->last_fallback = ctx->h_cnt->n_fallback;
     // too many particles drifted out of their warp tiles: sort before the next step instead of waiting for the interval
-    ctx->force_sort = !untiled && (int64_t)ctx->last_fallback * 64 > n_total;
+    ctx->force_sort = !untiled && !stream && (int64_t)ctx->last_fallback * 64 > n_total;
     s.step_open = true;
     if (flags & SFGPU_STEP_DEFER_FINISH) return 0;
     return sfgpu_finish_step(ctx, sp);
@@ -1398,6 +1517,7 @@ extern "C" int sfgpu_upload(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t
         CU(cudaStreamSynchronize(ctx->stream));
         pop.cur.n += (int64_t)n_exc;
         pop.fast.alive -= (int64_t)n_exc;
+        pop.fast.stream_ok = false; // edited in place: cells may have changed
         if (n_exc) pop.fast.dirty = true;
     }
     return 0;

@@ -1,0 +1,540 @@
+// sf_stream.cuh -- the streaming step: fused gather / push / locate / deposit that re-sorts the store as it writes.
+//
+// One launch does the move (KM:298-422), the deposit (KM:168-197, :1570-1595) and the cell sort + compaction (K3):
+//   * the input store is cell-sorted as of the PREVIOUS step; a CTA takes a chunk of <= SFS_CHUNK particles of one
+//     8x8-cell tile, fetched by TMA bulk copies (cp.async.bulk + mbarrier) one chunk ahead of the arithmetic;
+//   * phase 1 (thread per particle): lc = XtoL(pos), E gather, kick, move, locate, boundaries -- the same expressions as
+//     sf_move(), so results are bit-identical to the generic kernel;
+//   * the particle is written OUT OF PLACE into the second slab at the segment of the cell it occupied BEFORE this push
+//     (segment offsets = exclusive scan of the cell histogram the previous launch accumulated), so the output is
+//     sorted by a cell that is one step old and holds no vacant slots: sort and compaction cost no extra pass;
+//   * the deposit operands (corrected di, dj, mpw, u, v, w) are counting-sorted by NEW cell inside shared memory
+//     (integer shared atomics give the rank), then warps walk cell runs: lane (slot s of 8, group g of 4) accumulates
+//     the 4 node weights x 2 fields of every 8th particle in registers, a transposed shuffle reduction leaves one
+//     (node, field) total per lane, and the per-run totals are stored -- no floating-point atomics in shared memory
+//     (FP64 shared atomics are CAS loops on sm_100a);
+//   * a last phase sums, for every node of the tile + halo, the totals of its four adjacent cells and issues one FP64
+//     RED per touched (node, field) and chunk; the cell counts give mpc (KM:1593) and the next launch's histogram.
+// Particles outside the tile + halo (fast movers, periodic wraps, freshly injected tail) use per-particle global
+// atomics for all three purposes.  Exceptional particles leave for the record lists exactly as in sf_fast.cuh.
+#pragma once
+#include "sf_fast.cuh"
+
+#ifndef SFS_CHUNK
+#define SFS_CHUNK 512   // particles per chunk
+#endif
+#ifndef SFS_PPT
+#define SFS_PPT 2       // particles per thread in phase 1
+#endif
+#define SFS_THREADS (SFS_CHUNK / SFS_PPT)
+#define SFS_WARPS (SFS_THREADS / 32)
+#ifndef SFS_MIN_CTAS
+#define SFS_MIN_CTAS 2
+#endif
+#define SFS_RC (SF_TILE + 2 * SF_HALO)  // region cells per edge
+#define SFS_NCELL (SFS_RC * SFS_RC)
+#define SFS_NN (SFS_RC + 1)             // region nodes per edge
+#ifndef SFS_PIECE
+#define SFS_PIECE 64                    // longest run a warp reduces in one go
+#endif
+#ifndef SFS_MAXP
+#define SFS_MAXP 64                     // run totals held per round
+#endif
+#define SFS_NPIECE_MAX (SFS_NCELL + SFS_CHUNK / SFS_PIECE + 2)
+#define SFS_ROW (SFS_CHUNK + 2)         // stage row (doubles): an aligned superset of the chunk
+#define SFS_DROW (SFS_CHUNK + 4)        // deposit operand row (doubles); +4 spreads the rows over the banks
+#define SFS_SROW 33                     // run-total row (doubles), padded
+#define SFS_STAGE_DOUBLES (8 * SFS_ROW)
+
+static_assert(6 * SFS_DROW <= SFS_STAGE_DOUBLES, "deposit operands overlay the consumed input stage");
+static_assert(SFS_NCELL <= SFS_THREADS - 32, "one thread per region cell besides warp 0");
+static_assert(SFS_NCELL <= 5 * 32, "warp-0 scan handles 5 cells per lane");
+
+struct StreamArgs {
+    FastStepArgs b;        // b.fs = input store, b.items / b.n_items = chunks of the sorted prefix
+    FastPtrs out;          // output store (second slab)
+    unsigned *cursor;      // [nkeys] next free output slot of every cell key (starts at the segment offset)
+    unsigned *hist_next;   // [nkeys] live particles per cell key after this step
+    unsigned long long tail_first, tail_n; // unsorted input tail (injection, records that became normal)
+    unsigned n_tail_items;
+};
+
+struct SDesc {
+    unsigned long long begin;
+    int count;
+    int tile;
+};
+
+__device__ __forceinline__ unsigned sfs_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sfs_mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sfs_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sfs_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sfs_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sfs_tma_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sfs_smem(dst)), "l"(src),
+                 "r"(bytes), "r"(sfs_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sfs_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(sfs_smem(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+// tile-major cell key of a (clamped) cell: the key of sf_cell_key()
+__device__ __forceinline__ unsigned sfs_gkey(int ci, int cj, int ntj)
+{
+    return (unsigned)((ci / SF_TILE) * ntj + (cj / SF_TILE)) * (SF_TILE * SF_TILE) + (unsigned)((ci % SF_TILE) * SF_TILE + (cj % SF_TILE));
+}
+
+// what happens to a fast-store particle that does not stay a normal particle: record list, hand-off, slow path, death
+__device__ __forceinline__ void fast_leave(const FastStepArgs &a, int st, const PState &p, const MoveAux &aux, int2 tag)
+{
+    atomicAdd((unsigned long long *)&a.c->fast_delta[a.mesh_id], ~0ULL); // -1
+    if (st == SF_ALIVE) { // stale lc or residual dt: full record, handled by the generic kernel from now on
+        const unsigned long long s = atomicAdd(&a.c->n_out[a.mesh_id], 1ULL);
+        if (s < a.exc_cap) rec_store(a.exc, s, p, tag);
+        else atomicAdd(&a.c->overflow, 1ULL);
+    } else if (st == SF_DEAD) {
+        atomicAdd(&a.c->n_exited, 1ULL);
+    } else if (st == SF_REMOVED) {
+        atomicAdd(&a.c->n_removed, 1ULL);
+    } else if (st == SF_TRANSFER) {
+        for (int k = 0; k < 2; k++) {
+            if (!(aux.xfer_mask & (1 << k))) continue;
+            const int nb = aux.xfer_mesh[k];
+            const unsigned long long s = atomicAdd(&a.c->xfer_n[nb], 1ULL);
+            if (s < a.xfer[nb].cap) {
+                PState cp = p;
+                cp.li = aux.xfer_li[k];
+                cp.lj = aux.xfer_lj[k];
+                rec_store(a.xfer[nb].rec, s, cp, tag);
+            } else {
+                atomicAdd(&a.c->overflow, 1ULL);
+            }
+            atomicAdd(&a.c->n_xfer_copies, 1ULL);
+        }
+    } else { // SF_SLOW
+        const unsigned long long s = atomicAdd(&a.c->n_slow, 1ULL);
+        if (s < a.slow.cap) {
+            rec_store(a.slow.rec, s, p, tag);
+            a.slow.old_x[s] = aux.xo; a.slow.old_y[s] = aux.yo;
+            a.slow.old_li[s] = aux.lio; a.slow.old_lj[s] = aux.ljo;
+            a.slow.bounces[s] = aux.bounces; a.slow.mesh[s] = a.mesh_id;
+        } else {
+            atomicAdd(&a.c->overflow, 1ULL);
+        }
+    }
+}
+
+// everything that is not the common case, out of line.  Returns bit 0: the particle deposits in this step,
+// bit 1: it stays a normal particle of the fast store.
+__device__ __noinline__ int stream_general(const FastStepArgs *__restrict__ ga, PState *pp, int tag_id, int tag_born)
+{
+    const FastStepArgs &a = *ga;
+    MoveAux aux;
+    bool exact = true;
+    const GlobalFieldGather fg;
+    PState p = *pp;
+    const int st = sf_move(a.m, a.meshes, a.qm, a.charge, a.dt, false, p, aux, exact, fg);
+    *pp = p;
+    if (st == SF_ALIVE && exact && p.dt == 0) return 3;
+    fast_leave(a, st, p, aux, make_int2(tag_id, tag_born));
+    return st == SF_ALIVE ? 1 : 0;
+}
+
+// deposit of a particle the shared-memory path cannot take: global FP64 REDs (F2D:290-293, KM:1593)
+__device__ __noinline__ void stream_fallback(const MeshDev *mp, const PState *pp, double *dep) { deposit_global(*mp, *pp, dep); }
+
+// the corrected in-cell offsets of F2D:262-288: the four weights are (1-di)(1-dj), di(1-dj), di*dj, (1-di)dj
+__device__ __forceinline__ void sfs_offsets(const MeshDev &m, double fi, double fj, int i, int j, double &di, double &dj)
+{
+    di = fi - i;
+    dj = fj - j;
+    if (m.domain == SFGPU_RZ) {
+        const double rp = m.x0 + (i + 1) * m.dhx, rm = m.x0 + i * m.dhx, r = m.x0 + fi * m.dhx;
+        di = 1 - (0.5 * (rp - r) * (2 * rp + 3 * rm - r) / (rp * rp - rm * rm));
+    } else if (m.domain == SFGPU_ZR) {
+        const double rp = m.y0 + (j + 1) * m.dhy, rm = m.y0 + j * m.dhy, r = m.y0 + fj * m.dhy;
+        dj = 1 - (0.5 * (rp - r) * (2 * rp + 3 * rm - r) / (rp * rp - rm * rm));
+    }
+}
+
+__device__ __forceinline__ SDesc sfs_get_desc(const StreamArgs &a, unsigned idx, unsigned n_items)
+{
+    SDesc d;
+    d.begin = 0; d.count = 0; d.tile = -1;
+    if (idx < n_items) {
+        const WorkItem w = a.b.items[idx];
+        d.begin = w.begin; d.count = w.count; d.tile = w.tile;
+    } else if (idx - n_items < a.n_tail_items) {
+        const unsigned long long o = (unsigned long long)(idx - n_items) * SFS_CHUNK;
+        d.begin = a.tail_first + o;
+        const unsigned long long left = a.tail_n - o;
+        d.count = left < SFS_CHUNK ? (int)left : SFS_CHUNK;
+    }
+    return d;
+}
+
+// 8 bulk copies (x,y,z,u,v,w,mpw,tag) of the 16-byte aligned superset of the chunk
+__device__ __forceinline__ void sfs_issue(const FastPtrs &fs, const SDesc &d, double *stage, unsigned long long *bar)
+{
+    const unsigned long long b0 = d.begin & ~1ULL;
+    const unsigned nal = (unsigned)((d.begin - b0) + d.count + 1) & ~1u;
+    const unsigned bytes = nal * 8u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the stage was read / written through the generic proxy
+    sfs_mbar_expect_tx(bar, 8u * bytes);
+    const void *src[8] = {fs.x + b0, fs.y + b0, fs.z + b0, fs.u + b0, fs.v + b0, fs.w + b0, fs.mpw + b0, fs.tag + b0};
+#pragma unroll
+    for (int r = 0; r < 8; r++) sfs_tma_load(stage + r * SFS_ROW, src[r], bytes, bar);
+}
+
+struct SPart { // what phase 1 hands to the later phases, in registers
+    double x, y, z, u, v, w, mpw, di, dj;
+    int tid, tborn;
+    int ln;      // region cell after the push (deposit + next histogram through shared memory), or -1
+    unsigned rn; // rank inside that cell
+    int lo;      // region cell before the push (output segment through shared memory), -1: `ro` is the slot, -2: nothing to write
+    unsigned ro; // rank inside that cell's share of the segment, or the absolute output slot
+};
+
+__global__ void __launch_bounds__(SFS_THREADS, SFS_MIN_CTAS)
+k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restrict__ ga)
+{
+    extern __shared__ __align__(128) unsigned char sfs_raw[];
+    double *stage = reinterpret_cast<double *>(sfs_raw);                 // [2][8][SFS_ROW]
+    double *S = stage + 2 * SFS_STAGE_DOUBLES;                            // [SFS_MAXP][SFS_SROW]
+    unsigned *cntN = reinterpret_cast<unsigned *>(S + SFS_MAXP * SFS_SROW); // [NCELL] particles per new cell
+    unsigned *cntO = cntN + SFS_NCELL;                                    // [NCELL] particles per old cell
+    unsigned *offN = cntO + SFS_NCELL;                                    // [NCELL] first sorted position of a new cell
+    unsigned *baseO = offN + SFS_NCELL;                                   // [NCELL] first output slot of this chunk's share
+    unsigned short *pcBase = reinterpret_cast<unsigned short *>(baseO + SFS_NCELL); // [NCELL] first piece of a cell
+    unsigned short *pcCell = pcBase + SFS_NCELL;                          // [NPIECE_MAX]
+    unsigned short *pcStart = pcCell + SFS_NPIECE_MAX;
+    unsigned short *pcLen = pcStart + SFS_NPIECE_MAX;
+    __shared__ __align__(8) unsigned long long sBar[2];
+    __shared__ SDesc sDesc[2];
+    __shared__ int sNPieces, sNFall;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const MeshDev &m = a.b.m;
+    const size_t plane = (size_t)m.ni * m.nj;
+    const bool simple_ok = !m.has_b && !m.any_seg && a.b.dt > 0;
+    const int ntj = a.b.ntj;
+    double sN = 0, sPx = 0, sPy = 0, sPz = 0, sE = 0; // mover sums, KM:406-413
+
+    // ---- chunk queue, three deep: index of chunk k+3 requested, descriptor of k+2 loading, data of k+1 in flight ----
+    unsigned n_items = 0, idx_next = 0;
+    if (tid == 0) {
+        n_items = *a.b.n_items;
+        sfs_mbar_init(&sBar[0], 1);
+        sfs_mbar_init(&sBar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sNFall = 0;
+        const unsigned i0 = atomicAdd(&a.b.c->queue[a.b.mesh_id], 2u);
+        const SDesc d0 = sfs_get_desc(a, i0, n_items), d1 = sfs_get_desc(a, i0 + 1, n_items);
+        sDesc[0] = d0;
+        sDesc[1] = d1;
+        if (d0.count) sfs_issue(a.b.fs, d0, stage, &sBar[0]);
+        idx_next = atomicAdd(&a.b.c->queue[a.b.mesh_id], 1u);
+    }
+    for (int k = tid; k < 2 * SFS_NCELL; k += SFS_THREADS) cntN[k] = 0; // cntN and cntO
+    __syncthreads();
+
+    for (unsigned it = 0;; it++) {
+        const int sb = it & 1;
+        const SDesc cur = sDesc[sb];
+        if (cur.count == 0) break;
+        SDesc dnn;
+        unsigned idx_nn = 0;
+        dnn.begin = 0; dnn.count = 0; dnn.tile = -1;
+        if (tid == 0) {
+            const SDesc nx = sDesc[sb ^ 1];
+            if (nx.count) sfs_issue(a.b.fs, nx, stage + (sb ^ 1) * SFS_STAGE_DOUBLES, &sBar[sb ^ 1]);
+            dnn = sfs_get_desc(a, idx_next, n_items);                  // consumed at the end of this iteration
+            idx_nn = atomicAdd(&a.b.c->queue[a.b.mesh_id], 1u);        // consumed in the next iteration
+        }
+        const double *in = stage + sb * SFS_STAGE_DOUBLES;
+        double *D = stage + sb * SFS_STAGE_DOUBLES; // deposit operands overlay the input once phase 1 has consumed it
+        const int lead = (int)(cur.begin & 1ULL);
+        const bool tiled = cur.tile >= 0;
+        const int ci0 = tiled ? (cur.tile / ntj) * SF_TILE - SF_HALO : 0; // first cell row / column of the region
+        const int cj0 = tiled ? (cur.tile % ntj) * SF_TILE - SF_HALO : 0;
+        sfs_mbar_wait(&sBar[sb], (it >> 1) & 1u);
+
+        // ================= phase 1: push =================
+        SPart sp[SFS_PPT];
+#pragma unroll
+        for (int j = 0; j < SFS_PPT; j++) {
+            SPart &q = sp[j];
+            q.ln = -1; q.lo = -2; q.rn = 0; q.ro = 0;
+            const int o = j * SFS_THREADS + tid;
+            if (o >= cur.count) continue;
+            const int s = lead + o;
+            PState p;
+            p.mpw = in[6 * SFS_ROW + s];
+            if (p.mpw != p.mpw) continue; // vacant slot (a particle that left during the previous step)
+            p.x = in[0 * SFS_ROW + s]; p.y = in[1 * SFS_ROW + s]; p.z = in[2 * SFS_ROW + s];
+            p.u = in[3 * SFS_ROW + s]; p.v = in[4 * SFS_ROW + s]; p.w = in[5 * SFS_ROW + s];
+            const int2 tag = reinterpret_cast<const int2 *>(in + 7 * SFS_ROW)[s];
+            q.tid = tag.x; q.tborn = tag.y;
+            p.li = sf_div_exact(p.x - m.x0, m.dhx, m.rdhx, m.fastdiv); // the stored lc of a normal particle is exactly XtoL(pos)
+            p.lj = sf_div_exact(p.y - m.y0, m.dhy, m.rdhy, m.fastdiv);
+            p.dt = 0;
+            // output segment: the cell the particle is in now
+            {
+                const int ci = min(max(sf_j2i(p.li), 0), m.ni - 2), cj = min(max(sf_j2i(p.lj), 0), m.nj - 2);
+                const int ri = ci - ci0, rj = cj - cj0;
+                if (tiled && ri >= 0 && rj >= 0 && ri < SFS_RC && rj < SFS_RC) {
+                    q.lo = ri * SFS_RC + rj;
+                    q.ro = atomicAdd(&cntO[q.lo], 1u);
+                } else {
+                    q.lo = -1;
+                    q.ro = atomicAdd(&a.cursor[sfs_gkey(ci, cj, ntj)], 1u);
+                }
+            }
+            int fl = 3;
+            if (!(simple_ok && sf_move_simple(m, a.b.qm, a.b.dt, p))) fl = stream_general(ga, &p, q.tid, q.tborn);
+            q.x = p.x; q.y = p.y; q.z = p.z; q.u = p.u; q.v = p.v; q.w = p.w;
+            q.mpw = (fl & 2) ? p.mpw : sf_vacant();
+            if (fl & 1) {
+                sN += p.mpw; sPx += p.mpw * p.u; sPy += p.mpw * p.v; sPz += p.mpw * p.w;
+                sE += p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w);
+                const int i = sf_j2i(p.li), jj = sf_j2i(p.lj);
+                const bool inside = i >= 0 && jj >= 0 && i < m.ni - 1 && jj < m.nj - 1; // F2D:253: scatter() returns early otherwise
+                const int ri = i - ci0, rj = jj - cj0;
+                if (fl == 3 && tiled && inside && ri >= 0 && rj >= 0 && ri < SFS_RC && rj < SFS_RC) {
+                    q.ln = ri * SFS_RC + rj;
+                    q.rn = atomicAdd(&cntN[q.ln], 1u);
+                    sfs_offsets(m, p.li, p.lj, i, jj, q.di, q.dj);
+                    q.mpw = p.mpw;
+                } else {
+                    stream_fallback(&ga->m, &p, a.b.dep);
+                    atomicAdd(&sNFall, 1);
+                    if (fl & 2) {
+                        const int ci = min(max(i, 0), m.ni - 2), cj = min(max(jj, 0), m.nj - 2);
+                        atomicAdd(&a.hist_next[sfs_gkey(ci, cj, ntj)], 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads(); // B1
+
+        // ================= phase 2a: offsets, pieces, global bookkeeping =================
+        unsigned gbase = 0;
+        if (wid == 0) {
+            unsigned cn[5], np[5], sc = 0, spc = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int c = lane * 5 + k;
+                cn[k] = c < SFS_NCELL ? cntN[c] : 0u;
+                np[k] = (cn[k] + SFS_PIECE - 1) / SFS_PIECE;
+                sc += cn[k];
+                spc += np[k];
+            }
+            unsigned ic = sc, ip = spc; // inclusive warp scans
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned yc = __shfl_up_sync(0xffffffffu, ic, d), yp = __shfl_up_sync(0xffffffffu, ip, d);
+                if (lane >= d) { ic += yc; ip += yp; }
+            }
+            unsigned oc = ic - sc, op = ip - spc;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int c = lane * 5 + k;
+                if (c < SFS_NCELL) {
+                    offN[c] = oc;
+                    pcBase[c] = (unsigned short)op;
+                    if (np[k]) {
+                        const unsigned per = (cn[k] + np[k] - 1) / np[k];
+                        for (unsigned q = 0; q < np[k]; q++) {
+                            const unsigned st = q * per, ln = min(per, cn[k] - st);
+                            pcCell[op + q] = (unsigned short)c;
+                            pcStart[op + q] = (unsigned short)(oc + st);
+                            pcLen[op + q] = (unsigned short)ln;
+                        }
+                    }
+                    oc += cn[k];
+                    op += np[k];
+                }
+            }
+            if (lane == 31) sNPieces = (int)ip;
+        } else if (tiled) {
+            const int c = SFS_THREADS - 1 - tid;
+            if (c < SFS_NCELL) {
+                const unsigned no = cntO[c], nn = cntN[c];
+                if (no | nn) {
+                    const int ci = ci0 + c / SFS_RC, cj = cj0 + c % SFS_RC;
+                    const unsigned key = sfs_gkey(ci, cj, ntj);
+                    if (no) gbase = atomicAdd(&a.cursor[key], no); // the result is needed in phase 4 only
+                    if (nn) {
+                        atomicAdd(&a.hist_next[key], nn);
+                        atomicAdd(a.b.dep + SFGPU_F_MPC * plane + (size_t)ci * m.nj + cj, (double)nn); // KM:1593
+                    }
+                }
+            }
+        }
+        __syncthreads(); // B2
+
+        // ================= phase 2b: deposit operands to their sorted position =================
+#pragma unroll
+        for (int j = 0; j < SFS_PPT; j++) {
+            const SPart &q = sp[j];
+            if (q.ln >= 0) {
+                const unsigned pos = offN[q.ln] + q.rn;
+                D[0 * SFS_DROW + pos] = q.di; D[1 * SFS_DROW + pos] = q.dj; D[2 * SFS_DROW + pos] = q.mpw;
+                D[3 * SFS_DROW + pos] = q.u; D[4 * SFS_DROW + pos] = q.v; D[5 * SFS_DROW + pos] = q.w;
+            }
+        }
+        __syncthreads(); // B3
+
+        const int npieces = sNPieces;
+        for (int p0 = 0; p0 < npieces; p0 += SFS_MAXP) {
+            const int p1 = min(npieces, p0 + SFS_MAXP);
+            // ================= phase 3: run totals =================
+            {
+                const int s = lane >> 2, g = lane & 3;
+                const double *Dv = D + (g == 0 ? 2 : 2 + g) * SFS_DROW; // velocity component of this lane's two fields
+                for (int pid = p0 + wid; pid < p1; pid += SFS_WARPS) {
+                    const int start = pcStart[pid], end = start + pcLen[pid];
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0; // [node 00,10,11,01][field lo, hi]
+                    for (int k = start + s; k < end; k += 8) {
+                        const double di = D[k], dj = D[SFS_DROW + k], mp = D[2 * SFS_DROW + k], vc = Dv[k];
+                        const double t = mp * vc;
+                        const double v1 = g == 0 ? mp : t, v2 = t * vc; // (Den | U,V,W) and (unused | UU,VV,WW), KM:1584-1590
+                        const double ai = 1 - di, bj = 1 - dj;
+                        const double b1 = bj * v1, d1 = dj * v1, b2 = bj * v2, d2 = dj * v2;
+                        a0 = __fma_rn(ai, b1, a0); a1 = __fma_rn(ai, b2, a1); // (1-di)(1-dj)
+                        a2 = __fma_rn(di, b1, a2); a3 = __fma_rn(di, b2, a3); // di(1-dj)
+                        a4 = __fma_rn(di, d1, a4); a5 = __fma_rn(di, d2, a5); // di*dj
+                        a6 = __fma_rn(ai, d1, a6); a7 = __fma_rn(ai, d2, a7); // (1-di)dj
+                    }
+                    // transposed reduction over the 8 slots: every stage halves the values a lane keeps
+                    const bool h0 = (lane & 4) != 0, h1 = (lane & 8) != 0, h2 = (lane & 16) != 0;
+                    double k0 = h0 ? a4 : a0, k1 = h0 ? a5 : a1, k2 = h0 ? a6 : a2, k3 = h0 ? a7 : a3;
+                    k0 += __shfl_xor_sync(0xffffffffu, h0 ? a0 : a4, 4);
+                    k1 += __shfl_xor_sync(0xffffffffu, h0 ? a1 : a5, 4);
+                    k2 += __shfl_xor_sync(0xffffffffu, h0 ? a2 : a6, 4);
+                    k3 += __shfl_xor_sync(0xffffffffu, h0 ? a3 : a7, 4);
+                    double m0 = h1 ? k2 : k0, m1 = h1 ? k3 : k1;
+                    m0 += __shfl_xor_sync(0xffffffffu, h1 ? k0 : k2, 8);
+                    m1 += __shfl_xor_sync(0xffffffffu, h1 ? k1 : k3, 8);
+                    double r = h2 ? m1 : m0;
+                    r += __shfl_xor_sync(0xffffffffu, h2 ? m0 : m1, 16);
+                    // this lane now holds accumulator e = 4*h0 + 2*h1 + h2 (node e>>1, field half e&1) of group g
+                    const int e = (h0 ? 4 : 0) + (h1 ? 2 : 0) + (h2 ? 1 : 0);
+                    S[(pid - p0) * SFS_SROW + e * 4 + g] = r;
+                }
+            }
+            __syncthreads(); // B4
+            // ================= phase 4: node totals -> global deposit =================
+            for (int idx = tid; idx < 7 * SFS_NN * SFS_NN; idx += SFS_THREADS) {
+                const int f = idx / (SFS_NN * SFS_NN), r2 = idx % (SFS_NN * SFS_NN);
+                const int na = r2 / SFS_NN, nb = r2 % SFS_NN;
+                const int g = f == 0 ? 0 : (f <= 3 ? f : f - 3), h = f >= 4 ? 1 : 0;
+                double sum = 0;
+                bool any = false;
+#pragma unroll
+                for (int n = 0; n < 4; n++) { // node n of cell (na - dn_i, nb - dn_j): 00, 10, 11, 01
+                    const int ca = na - ((n == 1 || n == 2) ? 1 : 0), cb = nb - ((n >= 2) ? 1 : 0);
+                    if (ca < 0 || cb < 0 || ca >= SFS_RC || cb >= SFS_RC) continue;
+                    const int c = ca * SFS_RC + cb;
+                    const unsigned cn = cntN[c];
+                    if (!cn) continue;
+                    const int q0 = pcBase[c], q1 = q0 + (int)((cn + SFS_PIECE - 1) / SFS_PIECE);
+                    for (int q = max(q0, p0); q < min(q1, p1); q++) {
+                        sum += S[(q - p0) * SFS_SROW + (n * 2 + h) * 4 + g];
+                        any = true;
+                    }
+                }
+                if (any) atomicAdd(a.b.dep + f * plane + (size_t)(ci0 + na) * m.nj + (cj0 + nb), sum);
+            }
+            if (p1 < npieces) __syncthreads(); // S is reused by the next round
+        }
+
+        // ================= output: every live input particle takes one slot of its old cell's segment =================
+        if (wid != 0 && tiled) {
+            const int c = SFS_THREADS - 1 - tid;
+            if (c < SFS_NCELL) baseO[c] = gbase;
+        }
+        __syncthreads(); // B5: baseO visible; cntN / cntO are not read any more
+        for (int k = tid; k < 2 * SFS_NCELL; k += SFS_THREADS) cntN[k] = 0;
+#pragma unroll
+        for (int j = 0; j < SFS_PPT; j++) {
+            const SPart &q = sp[j];
+            if (q.lo == -2) continue;
+            const size_t slot = (q.lo >= 0) ? (size_t)baseO[q.lo] + q.ro : (size_t)q.ro;
+            a.out.x[slot] = q.x; a.out.y[slot] = q.y; a.out.z[slot] = q.z;
+            a.out.u[slot] = q.u; a.out.v[slot] = q.v; a.out.w[slot] = q.w;
+            a.out.mpw[slot] = q.mpw;
+            a.out.tag[slot] = make_int2(q.tid, q.tborn);
+        }
+        if (tid == 0) {
+            sDesc[sb] = dnn;
+            idx_next = idx_nn;
+        }
+        __syncthreads(); // B6: tables, stage and descriptor slot are free
+    }
+
+    // ---- mover sums of this CTA ----
+    sN = warp_sum(sN); sPx = warp_sum(sPx); sPy = warp_sum(sPy); sPz = warp_sum(sPz); sE = warp_sum(sE);
+    if (lane == 0 && sN != 0) {
+        atomicAdd(&a.b.c->sums[0], sN); atomicAdd(&a.b.c->sums[1], sPx); atomicAdd(&a.b.c->sums[2], sPy);
+        atomicAdd(&a.b.c->sums[3], sPz); atomicAdd(&a.b.c->sums[4], sE);
+    }
+    if (tid == 0 && sNFall) atomicAdd(&a.b.c->n_fallback, (unsigned long long)sNFall);
+}
+
+#define SFS_SMEM_BYTES ((2 * SFS_STAGE_DOUBLES + SFS_MAXP * SFS_SROW) * 8 + 4 * SFS_NCELL * 4 + (SFS_NCELL + 3 * SFS_NPIECE_MAX) * 2 + 64)
+
+// chunks of the streaming kernel: each tile's run [offs[tile*64], offs[(tile+1)*64]) cut into <= SFS_CHUNK particles
+__global__ void k_build_chunks(const unsigned *__restrict__ offs, int n_tiles, WorkItem *__restrict__ items, unsigned *__restrict__ n_items,
+                               unsigned max_items)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const unsigned b = offs[(size_t)t * SF_TILE * SF_TILE], e = offs[(size_t)(t + 1) * SF_TILE * SF_TILE];
+    if (e <= b) return;
+    const unsigned cnt = e - b, pieces = (cnt + SFS_CHUNK - 1) / SFS_CHUNK;
+    const unsigned per = (cnt + pieces - 1) / pieces;
+    const unsigned s = atomicAdd(n_items, pieces);
+    for (unsigned k = 0; k < pieces && s + k < max_items; k++) {
+        const unsigned pb = b + k * per, pe = min(e, pb + per);
+        WorkItem w;
+        w.begin = pb;
+        w.count = pe > pb ? (int)(pe - pb) : 0;
+        w.tile = t;
+        items[s + k] = w;
+    }
+}
+
+// per-key histogram of the live particles of a store (re-establishes the streaming invariant after in-place edits)
+__global__ void __launch_bounds__(256)
+k_stream_hist(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs fs, unsigned long long first, unsigned long long n, int ntj,
+              unsigned *__restrict__ hist)
+{
+    const MeshDev m = meshes[mesh_id];
+    const unsigned long long q0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q0 >= n) return;
+    const size_t q = first + q0;
+    const double mpw = fs.mpw[q];
+    if (mpw != mpw) return;
+    atomicAdd(&hist[sf_cell_key(m, (fs.x[q] - m.x0) / m.dhx, (fs.y[q] - m.y0) / m.dhy, ntj)], 1u);
+}
+
+// debug: every cell's cursor must have reached the start of the next segment
+__global__ void k_stream_check(const unsigned *__restrict__ offs, const unsigned *__restrict__ cursor, unsigned nkeys, unsigned long long *bad)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nkeys && cursor[k] != offs[k + 1]) atomicAdd(bad, 1ULL);
+}

@@ -110,3 +110,55 @@ class UniformMesh:
             jj[-1] -= 0.25
             r = (self.x0[1] + jj * self.dh[1])[None, :]
         return 2 * np.pi * area * r
+
+
+def set_mesh_neighbors(meshes):
+    """``Mesh.setMeshNeighbors`` (Mesh.java:405-468) for a list of uniform meshes: a boundary node whose position lies
+    inside another mesh (``containsPos``, FLT_EPS tolerance) becomes a MESH boundary with up to two neighbours
+    (``addMeshToBoundary``, Mesh.java:476-489).  Interior face nodes first, then the corners, which only join a face that
+    is already a MESH face next to them -- the rule that keeps a mesh stacked on top of another from getting a MESH
+    boundary on its side face.  Mesh setup stays in Java; this mirror only builds inputs for the tests and examples."""
+    def add(mesh, face, index, other):
+        row = mesh.nbr[int(face)][index]
+        mesh.bc[int(face)][index] = int(DomainBoundaryType.MESH)
+        if row[0] < 0:
+            row[0] = other
+        else:
+            row[1] = other
+
+    for me in meshes:
+        ni, nj = me.ni, me.nj
+        pos = lambda i, j: np.array([me.x0[0] + i * me.dh[0], me.x0[1] + j * me.dh[1]])
+        for k, other in enumerate(meshes):
+            if other is me:
+                continue
+            for j in range(1, nj - 1):
+                if other.containsPos(pos(0, j)):
+                    add(me, Face.LEFT, j, k)
+                if other.containsPos(pos(ni - 1, j)):
+                    add(me, Face.RIGHT, j, k)
+            for i in range(1, ni - 1):
+                if other.containsPos(pos(i, 0)):
+                    add(me, Face.BOTTOM, i, k)
+                if other.containsPos(pos(i, nj - 1)):
+                    add(me, Face.TOP, i, k)
+        is_mesh = lambda face, idx: me.bc[int(face)][idx] == int(DomainBoundaryType.MESH)
+        for k, other in enumerate(meshes):
+            if other is me:
+                continue
+            if is_mesh(Face.LEFT, 1) and other.containsPos(pos(0, 0)):
+                add(me, Face.LEFT, 0, k)
+            if is_mesh(Face.LEFT, nj - 2) and other.containsPos(pos(0, nj - 1)):
+                add(me, Face.LEFT, nj - 1, k)
+            if is_mesh(Face.RIGHT, 1) and other.containsPos(pos(ni - 1, 0)):
+                add(me, Face.RIGHT, 0, k)
+            if is_mesh(Face.RIGHT, nj - 2) and other.containsPos(pos(ni - 1, nj - 1)):
+                add(me, Face.RIGHT, nj - 1, k)
+            if is_mesh(Face.TOP, 1) and other.containsPos(pos(0, nj - 1)):
+                add(me, Face.TOP, 0, k)
+            if is_mesh(Face.TOP, ni - 2) and other.containsPos(pos(ni - 1, nj - 1)):
+                add(me, Face.TOP, ni - 1, k)
+            if is_mesh(Face.BOTTOM, 1) and other.containsPos(pos(0, 0)):
+                add(me, Face.BOTTOM, 0, k)
+            if is_mesh(Face.BOTTOM, ni - 2) and other.containsPos(pos(ni - 1, 0)):
+                add(me, Face.BOTTOM, ni - 1, k)

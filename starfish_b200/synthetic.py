@@ -121,3 +121,19 @@ def config_e(ni=2048, nj=2048, seed=20260119):
     """Synthetic E: XY 2048x2048, particles loaded as in B, partitioned by index over the ranks."""
     mesh = make_mesh(ni, nj, DomainType.XY, 1e-3, "periodic")
     return Workload("xy%dx%d_periodic" % (ni, nj), mesh, 1e-7, QE, 16 * AMU, seed, vth_cells=0.2)
+
+
+def config_multi_domain():
+    """BASELINE config 4: the mesh layout of dat/examples/multi-domain/domain.xml (RZ, four uniform meshes with different
+    spacings, LEFT symmetry), Ar+ with spwt 1e3, dt 5e-8 (materials.xml, starfish.xml); no field solver in that example.
+    Returns (meshes, charge, mass, dt)."""
+    from .domain import set_mesh_neighbors
+    spec = [((0.0, 0.0), (5e-4, 1e-3), (12, 50)), ((0.0055, 0.0), (1e-3, 1e-3), (12, 14)),
+            ((0.0055, 0.031), (5e-4, 1e-3), (10, 9)), ((0.0, 0.049), (1e-3, 1e-3), (14, 14))]
+    meshes = []
+    for k, (x0, dh, (ni, nj)) in enumerate(spec):
+        m = UniformMesh(ni, nj, x0, dh, DomainType.RZ, name="mesh%d" % (k + 1))
+        m.setMeshBCType(Face.LEFT, DomainBoundaryType.SYMMETRY)
+        meshes.append(m)
+    set_mesh_neighbors(meshes)
+    return meshes, QE, 39.9 * AMU, 5e-8

@@ -14,7 +14,7 @@ from starfish_b200.domain import DomainBoundaryType as BC, DomainType, Face, Uni
 
 pytestmark = pytest.mark.gpu
 
-PATHS = [pytest.param(_lib.STEP_GENERIC, id="generic"), pytest.param(0, id="tiled")]
+PATHS = [pytest.param(_lib.STEP_GENERIC, id="generic"), pytest.param(_lib.STEP_INPLACE, id="tiled"), pytest.param(0, id="stream")]
 
 
 def to_particles(arr):
