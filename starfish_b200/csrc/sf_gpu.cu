@@ -1072,9 +1072,16 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             { ctx->last_launches++; ctx->launch_total++; }
             if (f.n > 0) {
                 CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
+                CU(cudaMemsetAsync(f.items, 0, (size_t)f.max_items * sizeof(WorkItem), ctx->stream)); // count 0 ends a CTA's round-robin walk
                 if (f.n_sorted > 0) {
                     const int n_tiles = f.nti * f.ntj;
                     k_build_chunks<<<(n_tiles + 127) / 128, 128, 0, ctx->stream>>>(f.offs, n_tiles, f.items, f.d_nitems, f.max_items);
+                    CU(cudaGetLastError());
+                    { ctx->last_launches++; ctx->launch_total++; }
+                }
+                if (f.n > f.n_sorted) {
+                    const int64_t n_tail = (f.n - f.n_sorted + SFS_CHUNK - 1) / SFS_CHUNK;
+                    k_build_tail<<<(unsigned)((n_tail + 127) / 128), 128, 0, ctx->stream>>>((unsigned long long)f.n_sorted, (unsigned long long)(f.n - f.n_sorted), f.items, f.d_nitems, f.max_items);
                     CU(cudaGetLastError());
                     { ctx->last_launches++; ctx->launch_total++; }
                 }
@@ -1083,9 +1090,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                 sa.out = f.alt;
                 sa.cursor = f.cursor;
                 sa.hist_next = f.hist_next;
-                sa.tail_first = (unsigned long long)f.n_sorted;
-                sa.tail_n = (unsigned long long)(f.n - f.n_sorted);
-                sa.n_tail_items = (unsigned)((f.n - f.n_sorted + SFS_CHUNK - 1) / SFS_CHUNK);
+                sa.max_items = f.max_items;
                 CU(cudaMemcpyAsync(ctx->d_args + m, &sa.b, sizeof sa.b, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
                 k_stream_step<<<ctx->stream_grid, SFS_THREADS, SFS_SMEM_BYTES, ctx->stream>>>(sa, ctx->d_args + m);
                 CU(cudaGetLastError());

@@ -37,17 +37,17 @@
 #ifndef SFS_PIECE
 #define SFS_PIECE 64                    // longest run a warp reduces in one go
 #endif
-#ifndef SFS_MAXP
-#define SFS_MAXP 64                     // run totals held per round
-#endif
 #define SFS_NPIECE_MAX (SFS_NCELL + SFS_CHUNK / SFS_PIECE + 2)
 #define SFS_ROW (SFS_CHUNK + 2)         // stage row (doubles): an aligned superset of the chunk
 #define SFS_DROW (SFS_CHUNK + 4)        // deposit operand row (doubles); +4 spreads the rows over the banks
 #define SFS_SROW 33                     // run-total row (doubles), padded
 #define SFS_STAGE_DOUBLES (8 * SFS_ROW)
 
-static_assert(6 * SFS_DROW <= SFS_STAGE_DOUBLES, "deposit operands overlay the consumed input stage");
+static_assert(sizeof(WorkItem) == 16, "descriptors are fetched with one 16-byte cp.async");
+static_assert(7 * SFS_DROW <= SFS_STAGE_DOUBLES, "deposit operands overlay the consumed input stage");
+static_assert(SFS_CHUNK < 0x8000 && SFS_NPIECE_MAX < 0x8000, "particles and pieces are scanned as two 16-bit halves");
 static_assert(SFS_NCELL <= SFS_THREADS - 32, "one thread per region cell besides warp 0");
+static_assert(SFS_NN <= 16, "phase 4 gives half a warp to a node row");
 static_assert(SFS_NCELL <= 5 * 32, "warp-0 scan handles 5 cells per lane");
 
 struct StreamArgs {
@@ -55,8 +55,7 @@ struct StreamArgs {
     FastPtrs out;          // output store (second slab)
     unsigned *cursor;      // [nkeys] next free output slot of every cell key (starts at the segment offset)
     unsigned *hist_next;   // [nkeys] live particles per cell key after this step
-    unsigned long long tail_first, tail_n; // unsorted input tail (injection, records that became normal)
-    unsigned n_tail_items;
+    unsigned max_items;    // length of b.items (entries behind the last chunk have count 0)
 };
 
 struct SDesc {
@@ -154,7 +153,17 @@ __device__ __noinline__ int stream_general(const FastStepArgs *__restrict__ ga, 
 }
 
 // deposit of a particle the shared-memory path cannot take: global FP64 REDs (F2D:290-293, KM:1593)
-__device__ __noinline__ void stream_fallback(const MeshDev *mp, const PState *pp, double *dep) { deposit_global(*mp, *pp, dep); }
+// and its mover sums (KM:406-413) into the CTA's shared slots (CAS atomics: rare)
+__device__ __noinline__ void stream_fallback(const MeshDev *mp, const PState *pp, double *dep, double *sums)
+{
+    const PState &p = *pp;
+    deposit_global(*mp, p, dep);
+    atomicAdd(sums + 0, p.mpw);
+    atomicAdd(sums + 1, p.mpw * p.u);
+    atomicAdd(sums + 2, p.mpw * p.v);
+    atomicAdd(sums + 3, p.mpw * p.w);
+    atomicAdd(sums + 4, p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w));
+}
 
 // the corrected in-cell offsets of F2D:262-288: the four weights are (1-di)(1-dj), di(1-dj), di*dj, (1-di)dj
 __device__ __forceinline__ void sfs_offsets(const MeshDev &m, double fi, double fj, int i, int j, double &di, double &dj)
@@ -170,18 +179,14 @@ __device__ __forceinline__ void sfs_offsets(const MeshDev &m, double fi, double 
     }
 }
 
-__device__ __forceinline__ SDesc sfs_get_desc(const StreamArgs &a, unsigned idx, unsigned n_items)
+// chunk descriptors come from the item list (tile chunks, then tail chunks; zero-filled behind the last one)
+__device__ __forceinline__ SDesc sfs_get_desc(const StreamArgs &a, unsigned idx)
 {
     SDesc d;
     d.begin = 0; d.count = 0; d.tile = -1;
-    if (idx < n_items) {
+    if (idx < a.max_items) {
         const WorkItem w = a.b.items[idx];
         d.begin = w.begin; d.count = w.count; d.tile = w.tile;
-    } else if (idx - n_items < a.n_tail_items) {
-        const unsigned long long o = (unsigned long long)(idx - n_items) * SFS_CHUNK;
-        d.begin = a.tail_first + o;
-        const unsigned long long left = a.tail_n - o;
-        d.count = left < SFS_CHUNK ? (int)left : SFS_CHUNK;
     }
     return d;
 }
@@ -200,7 +205,7 @@ __device__ __forceinline__ void sfs_issue(const FastPtrs &fs, const SDesc &d, do
 }
 
 struct SPart { // what phase 1 hands to the later phases, in registers
-    double x, y, z, u, v, w, mpw, di, dj;
+    double x, y, z, u, v, w, mpw, di, dj, en; // en = mpw*|vel| (KM:412)
     int tid, tborn;
     int ln;      // region cell after the push (deposit + next histogram through shared memory), or -1
     unsigned rn; // rank inside that cell
@@ -213,57 +218,56 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
 {
     extern __shared__ __align__(128) unsigned char sfs_raw[];
     double *stage = reinterpret_cast<double *>(sfs_raw);                 // [2][8][SFS_ROW]
-    double *S = stage + 2 * SFS_STAGE_DOUBLES;                            // [SFS_MAXP][SFS_SROW]
-    unsigned *cntN = reinterpret_cast<unsigned *>(S + SFS_MAXP * SFS_SROW); // [NCELL] particles per new cell
-    unsigned *cntO = cntN + SFS_NCELL;                                    // [NCELL] particles per old cell
-    unsigned *offN = cntO + SFS_NCELL;                                    // [NCELL] first sorted position of a new cell
+    double *S = stage + 2 * SFS_STAGE_DOUBLES;                            // [NCELL][SFS_SROW] totals per new cell: [node][field half][group]
+    unsigned *cnt = reinterpret_cast<unsigned *>(S + SFS_NCELL * SFS_SROW); // [2 sets][cntN | cntO][NCELL], sets alternate between chunks
+    unsigned *offN = cnt + 4 * SFS_NCELL;                                 // [NCELL] first sorted position of a new cell
     unsigned *baseO = offN + SFS_NCELL;                                   // [NCELL] first output slot of this chunk's share
-    unsigned short *pcBase = reinterpret_cast<unsigned short *>(baseO + SFS_NCELL); // [NCELL] first piece of a cell
-    unsigned short *pcCell = pcBase + SFS_NCELL;                          // [NPIECE_MAX]
+    unsigned short *pcCell = reinterpret_cast<unsigned short *>(baseO + SFS_NCELL); // [NPIECE_MAX] pieces: cell, first sorted position, length
     unsigned short *pcStart = pcCell + SFS_NPIECE_MAX;
     unsigned short *pcLen = pcStart + SFS_NPIECE_MAX;
     __shared__ __align__(8) unsigned long long sBar[2];
-    __shared__ SDesc sDesc[2];
-    __shared__ int sNPieces, sNFall;
+    __shared__ __align__(16) SDesc sDesc[3];
+    __shared__ double sSums[5];
+    __shared__ int sNPieces, sNFall, sBox[4];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const MeshDev &m = a.b.m;
     const size_t plane = (size_t)m.ni * m.nj;
     const bool simple_ok = !m.has_b && !m.any_seg && a.b.dt > 0;
     const int ntj = a.b.ntj;
-    double sN = 0, sPx = 0, sPy = 0, sPz = 0, sE = 0; // mover sums, KM:406-413
+    double msum0 = 0, msum1 = 0; // mover sums, KM:406-413: lane (h, g) of every warp collects N, Px, Py, Pz (h = 0, g = 0..3) and E (h = 1, g = 0)
 
-    // ---- chunk queue, three deep: index of chunk k+3 requested, descriptor of k+2 loading, data of k+1 in flight ----
-    unsigned n_items = 0, idx_next = 0;
+    // ---- chunks are dealt round robin; descriptor of chunk k+2 and data of chunk k+1 are in flight while k is processed ----
     if (tid == 0) {
-        n_items = *a.b.n_items;
         sfs_mbar_init(&sBar[0], 1);
         sfs_mbar_init(&sBar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sNFall = 0;
-        const unsigned i0 = atomicAdd(&a.b.c->queue[a.b.mesh_id], 2u);
-        const SDesc d0 = sfs_get_desc(a, i0, n_items), d1 = sfs_get_desc(a, i0 + 1, n_items);
+        const SDesc d0 = sfs_get_desc(a, blockIdx.x), d1 = sfs_get_desc(a, blockIdx.x + gridDim.x);
         sDesc[0] = d0;
         sDesc[1] = d1;
         if (d0.count) sfs_issue(a.b.fs, d0, stage, &sBar[0]);
-        idx_next = atomicAdd(&a.b.c->queue[a.b.mesh_id], 1u);
     }
-    for (int k = tid; k < 2 * SFS_NCELL; k += SFS_THREADS) cntN[k] = 0; // cntN and cntO
+    if (tid < 5) sSums[tid] = 0.0;
+    for (int k = tid; k < 4 * SFS_NCELL; k += SFS_THREADS) cnt[k] = 0;
     __syncthreads();
 
     for (unsigned it = 0;; it++) {
         const int sb = it & 1;
-        const SDesc cur = sDesc[sb];
+        const SDesc cur = sDesc[it % 3];
         if (cur.count == 0) break;
-        SDesc dnn;
-        unsigned idx_nn = 0;
-        dnn.begin = 0; dnn.count = 0; dnn.tile = -1;
         if (tid == 0) {
-            const SDesc nx = sDesc[sb ^ 1];
+            const SDesc nx = sDesc[(it + 1) % 3];
             if (nx.count) sfs_issue(a.b.fs, nx, stage + (sb ^ 1) * SFS_STAGE_DOUBLES, &sBar[sb ^ 1]);
-            dnn = sfs_get_desc(a, idx_next, n_items);                  // consumed at the end of this iteration
-            idx_nn = atomicAdd(&a.b.c->queue[a.b.mesh_id], 1u);        // consumed in the next iteration
+            const unsigned long long idx = (unsigned long long)blockIdx.x + (unsigned long long)(it + 2) * gridDim.x;
+            SDesc *dst = &sDesc[(it + 2) % 3];
+            if (idx < a.max_items) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sfs_smem(dst)), "l"(a.b.items + idx) : "memory");
+            } else {
+                dst->begin = 0; dst->count = 0; dst->tile = -1;
+            }
         }
+        unsigned *cntN = cnt + sb * 2 * SFS_NCELL, *cntO = cntN + SFS_NCELL; // particles per new / old cell of this chunk
         const double *in = stage + sb * SFS_STAGE_DOUBLES;
         double *D = stage + sb * SFS_STAGE_DOUBLES; // deposit operands overlay the input once phase 1 has consumed it
         const int lead = (int)(cur.begin & 1ULL);
@@ -304,12 +308,14 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 }
             }
             int fl = 3;
-            if (!(simple_ok && sf_move_simple(m, a.b.qm, a.b.dt, p))) fl = stream_general(ga, &p, q.tid, q.tborn);
+            if (!(simple_ok && sf_move_simple(m, a.b.qm, a.b.dt, p))) {
+                PState t = p; // only the copy has its address taken: p stays in registers
+                fl = stream_general(ga, &t, q.tid, q.tborn);
+                p = t;
+            }
             q.x = p.x; q.y = p.y; q.z = p.z; q.u = p.u; q.v = p.v; q.w = p.w;
             q.mpw = (fl & 2) ? p.mpw : sf_vacant();
             if (fl & 1) {
-                sN += p.mpw; sPx += p.mpw * p.u; sPy += p.mpw * p.v; sPz += p.mpw * p.w;
-                sE += p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w);
                 const int i = sf_j2i(p.li), jj = sf_j2i(p.lj);
                 const bool inside = i >= 0 && jj >= 0 && i < m.ni - 1 && jj < m.nj - 1; // F2D:253: scatter() returns early otherwise
                 const int ri = i - ci0, rj = jj - cj0;
@@ -317,9 +323,10 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                     q.ln = ri * SFS_RC + rj;
                     q.rn = atomicAdd(&cntN[q.ln], 1u);
                     sfs_offsets(m, p.li, p.lj, i, jj, q.di, q.dj);
-                    q.mpw = p.mpw;
+                    q.en = p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w);
                 } else {
-                    stream_fallback(&ga->m, &p, a.b.dep);
+                    const PState t = p;
+                    stream_fallback(&ga->m, &t, a.b.dep, sSums);
                     atomicAdd(&sNFall, 1);
                     if (fl & 2) {
                         const int ci = min(max(i, 0), m.ni - 2), cj = min(max(jj, 0), m.nj - 2);
@@ -333,33 +340,34 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
         // ================= phase 2a: offsets, pieces, global bookkeeping =================
         unsigned gbase = 0;
         if (wid == 0) {
-            unsigned cn[5], np[5], sc = 0, spc = 0;
+            unsigned cn[5], np[5], sc = 0;
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 const int c = lane * 5 + k;
                 cn[k] = c < SFS_NCELL ? cntN[c] : 0u;
                 np[k] = (cn[k] + SFS_PIECE - 1) / SFS_PIECE;
-                sc += cn[k];
-                spc += np[k];
+                sc += cn[k] | (np[k] << 16); // particles and pieces scanned together
             }
-            unsigned ic = sc, ip = spc; // inclusive warp scans
+            unsigned ic = sc; // inclusive warp scan
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const unsigned yc = __shfl_up_sync(0xffffffffu, ic, d), yp = __shfl_up_sync(0xffffffffu, ip, d);
-                if (lane >= d) { ic += yc; ip += yp; }
+                const unsigned y = __shfl_up_sync(0xffffffffu, ic, d);
+                if (lane >= d) ic += y;
             }
-            unsigned oc = ic - sc, op = ip - spc;
+            unsigned oc = (ic - sc) & 0xffffu, op = (ic - sc) >> 16;
+            int bi0 = SFS_RC, bi1 = -1, bj0 = SFS_RC, bj1 = -1; // bounding box of the non-empty new cells
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 const int c = lane * 5 + k;
                 if (c < SFS_NCELL) {
                     offN[c] = oc;
-                    pcBase[c] = (unsigned short)op;
-                    if (np[k]) {
+                    if (cn[k]) {
+                        bi0 = min(bi0, c / SFS_RC); bi1 = max(bi1, c / SFS_RC);
+                        bj0 = min(bj0, c % SFS_RC); bj1 = max(bj1, c % SFS_RC);
                         const unsigned per = (cn[k] + np[k] - 1) / np[k];
                         for (unsigned q = 0; q < np[k]; q++) {
                             const unsigned st = q * per, ln = min(per, cn[k] - st);
-                            pcCell[op + q] = (unsigned short)c;
+                            pcCell[op + q] = (unsigned short)(c | (np[k] > 1 ? 0x8000 : 0)); // bit 15: the cell's total is shared by several pieces
                             pcStart[op + q] = (unsigned short)(oc + st);
                             pcLen[op + q] = (unsigned short)ln;
                         }
@@ -368,18 +376,24 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                     op += np[k];
                 }
             }
-            if (lane == 31) sNPieces = (int)ip;
+            bi0 = __reduce_min_sync(0xffffffffu, bi0); bi1 = __reduce_max_sync(0xffffffffu, bi1);
+            bj0 = __reduce_min_sync(0xffffffffu, bj0); bj1 = __reduce_max_sync(0xffffffffu, bj1);
+            if (lane == 31) {
+                sNPieces = (int)(ic >> 16);
+                sBox[0] = bi0; sBox[1] = bi1; sBox[2] = bj0; sBox[3] = bj1;
+            }
         } else if (tiled) {
-            const int c = SFS_THREADS - 1 - tid;
-            if (c < SFS_NCELL) {
+            for (int c = SFS_THREADS - 1 - tid; c < SFS_NCELL; c += SFS_THREADS - 32) {
                 const unsigned no = cntO[c], nn = cntN[c];
                 if (no | nn) {
                     const int ci = ci0 + c / SFS_RC, cj = cj0 + c % SFS_RC;
                     const unsigned key = sfs_gkey(ci, cj, ntj);
-                    if (no) gbase = atomicAdd(&a.cursor[key], no); // the result is needed in phase 4 only
+                    if (no) gbase = atomicAdd(&a.cursor[key], no); // the result is needed for the output only
                     if (nn) {
                         atomicAdd(&a.hist_next[key], nn);
                         atomicAdd(a.b.dep + SFGPU_F_MPC * plane + (size_t)ci * m.nj + cj, (double)nn); // KM:1593
+                        if (nn > SFS_PIECE) // several pieces add into this cell's totals
+                            for (int k = 0; k < 32; k++) S[c * SFS_SROW + k] = 0.0;
                     }
                 }
             }
@@ -394,81 +408,67 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 const unsigned pos = offN[q.ln] + q.rn;
                 D[0 * SFS_DROW + pos] = q.di; D[1 * SFS_DROW + pos] = q.dj; D[2 * SFS_DROW + pos] = q.mpw;
                 D[3 * SFS_DROW + pos] = q.u; D[4 * SFS_DROW + pos] = q.v; D[5 * SFS_DROW + pos] = q.w;
+                D[6 * SFS_DROW + pos] = q.en;
             }
+        }
+        { // the other counter set is free (its chunk finished phase 4 before B1): clear it for the next chunk
+            unsigned *nextc = cnt + ((it + 1) & 1) * 2 * SFS_NCELL;
+            for (int k = tid; k < 2 * SFS_NCELL; k += SFS_THREADS) nextc[k] = 0;
         }
         __syncthreads(); // B3
 
-        const int npieces = sNPieces;
-        for (int p0 = 0; p0 < npieces; p0 += SFS_MAXP) {
-            const int p1 = min(npieces, p0 + SFS_MAXP);
-            // ================= phase 3: run totals =================
-            {
-                const int s = lane >> 2, g = lane & 3;
-                const double *Dv = D + (g == 0 ? 2 : 2 + g) * SFS_DROW; // velocity component of this lane's two fields
-                for (int pid = p0 + wid; pid < p1; pid += SFS_WARPS) {
-                    const int start = pcStart[pid], end = start + pcLen[pid];
-                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0; // [node 00,10,11,01][field lo, hi]
-                    for (int k = start + s; k < end; k += 8) {
-                        const double di = D[k], dj = D[SFS_DROW + k], mp = D[2 * SFS_DROW + k], vc = Dv[k];
-                        const double t = mp * vc;
-                        const double v1 = g == 0 ? mp : t, v2 = t * vc; // (Den | U,V,W) and (unused | UU,VV,WW), KM:1584-1590
-                        const double ai = 1 - di, bj = 1 - dj;
-                        const double b1 = bj * v1, d1 = dj * v1, b2 = bj * v2, d2 = dj * v2;
-                        a0 = __fma_rn(ai, b1, a0); a1 = __fma_rn(ai, b2, a1); // (1-di)(1-dj)
-                        a2 = __fma_rn(di, b1, a2); a3 = __fma_rn(di, b2, a3); // di(1-dj)
-                        a4 = __fma_rn(di, d1, a4); a5 = __fma_rn(di, d2, a5); // di*dj
-                        a6 = __fma_rn(ai, d1, a6); a7 = __fma_rn(ai, d2, a7); // (1-di)dj
+        // ================= phase 3: cell totals.  Half a warp per piece: lane (slot s of 4, group g of 4) =================
+        {
+            const int half = lane >> 4, s = (lane >> 2) & 3, g = lane & 3;
+            const double *Dv = D + (g == 0 ? 6 : 2 + g) * SFS_DROW; // velocity component of this lane's two fields (g = 0: the energy term)
+            const int npieces = sNPieces;
+            const bool h0 = (lane & 4) != 0, h1 = (lane & 8) != 0;
+            for (int pp = 2 * wid; pp < npieces; pp += 2 * SFS_WARPS) {
+                const int pid = pp + half;
+                const bool have = pid < npieces;
+                const int start = have ? pcStart[pid] : 0, end = have ? start + pcLen[pid] : 0;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0; // [node 00,10,11,01][field lo, hi]
+                for (int k = start + s; k < end; k += 4) {
+                    const double di = D[k], dj = D[SFS_DROW + k], mp = D[2 * SFS_DROW + k], vc = Dv[k];
+                    const double t = mp * vc;
+                    const double v1 = g == 0 ? mp : t, v2 = g == 0 ? vc : t * vc; // (Den | U,V,W) and (mpw*|vel| | UU,VV,WW), KM:1584-1590
+                    const double ai = 1 - di, bj = 1 - dj;
+                    const double b1 = bj * v1, d1 = dj * v1, b2 = bj * v2, d2 = dj * v2;
+                    a0 = __fma_rn(ai, b1, a0); a1 = __fma_rn(ai, b2, a1); // (1-di)(1-dj)
+                    a2 = __fma_rn(di, b1, a2); a3 = __fma_rn(di, b2, a3); // di(1-dj)
+                    a4 = __fma_rn(di, d1, a4); a5 = __fma_rn(di, d2, a5); // di*dj
+                    a6 = __fma_rn(ai, d1, a6); a7 = __fma_rn(ai, d2, a7); // (1-di)dj
+                }
+                // transposed reduction over the 4 slots: every stage halves the values a lane keeps
+                double k0 = h0 ? a4 : a0, k1 = h0 ? a5 : a1, k2 = h0 ? a6 : a2, k3 = h0 ? a7 : a3;
+                k0 += __shfl_xor_sync(0xffffffffu, h0 ? a0 : a4, 4);
+                k1 += __shfl_xor_sync(0xffffffffu, h0 ? a1 : a5, 4);
+                k2 += __shfl_xor_sync(0xffffffffu, h0 ? a2 : a6, 4);
+                k3 += __shfl_xor_sync(0xffffffffu, h0 ? a3 : a7, 4);
+                double m0 = h1 ? k2 : k0, m1 = h1 ? k3 : k1;
+                m0 += __shfl_xor_sync(0xffffffffu, h1 ? k0 : k2, 8);
+                m1 += __shfl_xor_sync(0xffffffffu, h1 ? k1 : k3, 8);
+                // this lane now holds node n = 2*h0 + h1 of group g: m0 = low field, m1 = high field
+                if (have) {
+                    const unsigned pc = pcCell[pid];
+                    double *row = S + (pc & 0x7fffu) * SFS_SROW + ((h0 ? 4 : 0) + (h1 ? 2 : 0)) * 4 + g;
+                    if (pc & 0x8000u) {
+                        atomicAdd(row, m0);
+                        atomicAdd(row + 4, m1);
+                    } else {
+                        row[0] = m0;
+                        row[4] = m1;
                     }
-                    // transposed reduction over the 8 slots: every stage halves the values a lane keeps
-                    const bool h0 = (lane & 4) != 0, h1 = (lane & 8) != 0, h2 = (lane & 16) != 0;
-                    double k0 = h0 ? a4 : a0, k1 = h0 ? a5 : a1, k2 = h0 ? a6 : a2, k3 = h0 ? a7 : a3;
-                    k0 += __shfl_xor_sync(0xffffffffu, h0 ? a0 : a4, 4);
-                    k1 += __shfl_xor_sync(0xffffffffu, h0 ? a1 : a5, 4);
-                    k2 += __shfl_xor_sync(0xffffffffu, h0 ? a2 : a6, 4);
-                    k3 += __shfl_xor_sync(0xffffffffu, h0 ? a3 : a7, 4);
-                    double m0 = h1 ? k2 : k0, m1 = h1 ? k3 : k1;
-                    m0 += __shfl_xor_sync(0xffffffffu, h1 ? k0 : k2, 8);
-                    m1 += __shfl_xor_sync(0xffffffffu, h1 ? k1 : k3, 8);
-                    double r = h2 ? m1 : m0;
-                    r += __shfl_xor_sync(0xffffffffu, h2 ? m0 : m1, 16);
-                    // this lane now holds accumulator e = 4*h0 + 2*h1 + h2 (node e>>1, field half e&1) of group g
-                    const int e = (h0 ? 4 : 0) + (h1 ? 2 : 0) + (h2 ? 1 : 0);
-                    S[(pid - p0) * SFS_SROW + e * 4 + g] = r;
+                    msum0 += m0; // the node parts of a field add up to its particle total (the weights sum to 1)
+                    msum1 += m1;
                 }
             }
-            __syncthreads(); // B4
-            // ================= phase 4: node totals -> global deposit =================
-            for (int idx = tid; idx < 7 * SFS_NN * SFS_NN; idx += SFS_THREADS) {
-                const int f = idx / (SFS_NN * SFS_NN), r2 = idx % (SFS_NN * SFS_NN);
-                const int na = r2 / SFS_NN, nb = r2 % SFS_NN;
-                const int g = f == 0 ? 0 : (f <= 3 ? f : f - 3), h = f >= 4 ? 1 : 0;
-                double sum = 0;
-                bool any = false;
-#pragma unroll
-                for (int n = 0; n < 4; n++) { // node n of cell (na - dn_i, nb - dn_j): 00, 10, 11, 01
-                    const int ca = na - ((n == 1 || n == 2) ? 1 : 0), cb = nb - ((n >= 2) ? 1 : 0);
-                    if (ca < 0 || cb < 0 || ca >= SFS_RC || cb >= SFS_RC) continue;
-                    const int c = ca * SFS_RC + cb;
-                    const unsigned cn = cntN[c];
-                    if (!cn) continue;
-                    const int q0 = pcBase[c], q1 = q0 + (int)((cn + SFS_PIECE - 1) / SFS_PIECE);
-                    for (int q = max(q0, p0); q < min(q1, p1); q++) {
-                        sum += S[(q - p0) * SFS_SROW + (n * 2 + h) * 4 + g];
-                        any = true;
-                    }
-                }
-                if (any) atomicAdd(a.b.dep + f * plane + (size_t)(ci0 + na) * m.nj + (cj0 + nb), sum);
-            }
-            if (p1 < npieces) __syncthreads(); // S is reused by the next round
         }
+        if (wid != 0 && tiled)
+            for (int c = SFS_THREADS - 1 - tid; c < SFS_NCELL; c += SFS_THREADS - 32) baseO[c] = gbase;
+        __syncthreads(); // B4: cell totals and output bases visible; D is dead
 
         // ================= output: every live input particle takes one slot of its old cell's segment =================
-        if (wid != 0 && tiled) {
-            const int c = SFS_THREADS - 1 - tid;
-            if (c < SFS_NCELL) baseO[c] = gbase;
-        }
-        __syncthreads(); // B5: baseO visible; cntN / cntO are not read any more
-        for (int k = tid; k < 2 * SFS_NCELL; k += SFS_THREADS) cntN[k] = 0;
 #pragma unroll
         for (int j = 0; j < SFS_PPT; j++) {
             const SPart &q = sp[j];
@@ -479,23 +479,47 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
             a.out.mpw[slot] = q.mpw;
             a.out.tag[slot] = make_int2(q.tid, q.tborn);
         }
-        if (tid == 0) {
-            sDesc[sb] = dnn;
-            idx_next = idx_nn;
+        // ================= phase 4: node totals -> global deposit =================
+        // half a warp per (field, node row) of the bounding box; a lane sums the totals of the four cells around its node
+        if (sNPieces) {
+            const int bi0 = sBox[0], bj0 = sBox[2];
+            const int nh = sBox[1] - bi0 + 2, nw = sBox[3] - bj0 + 2; // node rows / columns touched
+            const int half = lane >> 4, hl = lane & 15;
+            for (int r = 2 * wid + half; r < 7 * nh; r += 2 * SFS_WARPS) {
+                const int f = r / nh, na = bi0 + r % nh, nb = bj0 + hl;
+                if (hl >= nw) continue;
+                const int col = ((f >= 4 ? 1 : 0)) * 4 + (f == 0 ? 0 : (f <= 3 ? f : f - 3)); // + node * 8
+                double sum = 0;
+                bool any = false;
+#pragma unroll
+                for (int n = 0; n < 4; n++) { // this node is node n (00, 10, 11, 01) of cell (na - dn_i, nb - dn_j)
+                    const int ca = na - ((n == 1 || n == 2) ? 1 : 0), cb = nb - ((n >= 2) ? 1 : 0);
+                    if (ca < 0 || cb < 0 || ca >= SFS_RC || cb >= SFS_RC) continue;
+                    const int c = ca * SFS_RC + cb;
+                    if (cntN[c]) {
+                        sum += S[c * SFS_SROW + n * 8 + col];
+                        any = true;
+                    }
+                }
+                if (any) atomicAdd(a.b.dep + f * plane + (size_t)(ci0 + na) * m.nj + (cj0 + nb), sum);
+            }
         }
-        __syncthreads(); // B6: tables, stage and descriptor slot are free
+        if (tid == 0) asm volatile("cp.async.wait_all;" ::: "memory"); // descriptor of chunk it+2 (published by the next barriers)
     }
 
-    // ---- mover sums of this CTA ----
-    sN = warp_sum(sN); sPx = warp_sum(sPx); sPy = warp_sum(sPy); sPz = warp_sum(sPz); sE = warp_sum(sE);
-    if (lane == 0 && sN != 0) {
-        atomicAdd(&a.b.c->sums[0], sN); atomicAdd(&a.b.c->sums[1], sPx); atomicAdd(&a.b.c->sums[2], sPy);
-        atomicAdd(&a.b.c->sums[3], sPz); atomicAdd(&a.b.c->sums[4], sE);
+    // ---- mover sums of this CTA: lanes (half, node n, group g) -> sum over the four nodes and the two halves ----
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1) {
+        msum0 += __shfl_xor_sync(0xffffffffu, msum0, o);
+        msum1 += __shfl_xor_sync(0xffffffffu, msum1, o);
     }
+    if (lane < 4 && msum0 != 0) atomicAdd(&a.b.c->sums[lane], msum0); // N, Px, Py, Pz
+    if (lane == 0 && msum1 != 0) atomicAdd(&a.b.c->sums[4], msum1);   // E
+    if (tid < 5 && sSums[tid] != 0) atomicAdd(&a.b.c->sums[tid], sSums[tid]);
     if (tid == 0 && sNFall) atomicAdd(&a.b.c->n_fallback, (unsigned long long)sNFall);
 }
 
-#define SFS_SMEM_BYTES ((2 * SFS_STAGE_DOUBLES + SFS_MAXP * SFS_SROW) * 8 + 4 * SFS_NCELL * 4 + (SFS_NCELL + 3 * SFS_NPIECE_MAX) * 2 + 64)
+#define SFS_SMEM_BYTES ((2 * SFS_STAGE_DOUBLES + SFS_NCELL * SFS_SROW) * 8 + 6 * SFS_NCELL * 4 + 3 * SFS_NPIECE_MAX * 2 + 64)
 
 // chunks of the streaming kernel: each tile's run [offs[tile*64], offs[(tile+1)*64]) cut into <= SFS_CHUNK particles
 __global__ void k_build_chunks(const unsigned *__restrict__ offs, int n_tiles, WorkItem *__restrict__ items, unsigned *__restrict__ n_items,
@@ -516,6 +540,20 @@ __global__ void k_build_chunks(const unsigned *__restrict__ offs, int n_tiles, W
         w.tile = t;
         items[s + k] = w;
     }
+}
+
+// chunks of the unsorted tail (tile = -1: no region, everything through global atomics)
+__global__ void k_build_tail(unsigned long long first, unsigned long long n, WorkItem *__restrict__ items, unsigned *__restrict__ n_items, unsigned max_items)
+{
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k * SFS_CHUNK >= n) return;
+    const unsigned s = atomicAdd(n_items, 1u);
+    if (s >= max_items) return;
+    WorkItem w;
+    w.begin = first + k * SFS_CHUNK;
+    w.count = (int)((n - k * SFS_CHUNK) < SFS_CHUNK ? (n - k * SFS_CHUNK) : SFS_CHUNK);
+    w.tile = -1;
+    items[s] = w;
 }
 
 // per-key histogram of the live particles of a store (re-establishes the streaming invariant after in-place edits)
