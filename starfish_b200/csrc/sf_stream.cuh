@@ -39,13 +39,16 @@
 #endif
 #define SFS_NPIECE_MAX (SFS_NCELL + SFS_CHUNK / SFS_PIECE + 2)
 #define SFS_ROW (SFS_CHUNK + 2)         // stage row (doubles): an aligned superset of the chunk
-#define SFS_DROW (SFS_CHUNK + 4)        // deposit operand row (doubles); +4 spreads the rows over the banks
+#define SFS_NSTAGE 2
+#ifndef SFS_MAXP
+#define SFS_MAXP 80                     // cell totals held per round (a chunk rarely fills more new cells)
+#endif
 #define SFS_SROW 33                     // run-total row (doubles), padded
 #define SFS_STAGE_DOUBLES (8 * SFS_ROW)
 
 static_assert(sizeof(WorkItem) == 16, "descriptors are fetched with one 16-byte cp.async");
-static_assert(7 * SFS_DROW <= SFS_STAGE_DOUBLES, "deposit operands overlay the consumed input stage");
-static_assert(SFS_CHUNK < 0x8000 && SFS_NPIECE_MAX < 0x8000, "particles and pieces are scanned as two 16-bit halves");
+static_assert(SFS_CHUNK < 0x1000 && SFS_NPIECE_MAX < 0x400 && SFS_NCELL < 0x400, "particles, pieces and cells are scanned as 12 + 10 + 10 bits");
+static_assert(SFS_NCELL / SFS_MAXP + 2 <= 8, "round starts");
 static_assert(SFS_NCELL <= SFS_THREADS - 32, "one thread per region cell besides warp 0");
 static_assert(SFS_NN <= 16, "phase 4 gives half a warp to a node row");
 static_assert(SFS_NCELL <= 5 * 32, "warp-0 scan handles 5 cells per lane");
@@ -204,38 +207,55 @@ __device__ __forceinline__ void sfs_issue(const FastPtrs &fs, const SDesc &d, do
     for (int r = 0; r < 8; r++) sfs_tma_load(stage + r * SFS_ROW, src[r], bytes, bar);
 }
 
-struct SPart { // what phase 1 hands to the later phases, in registers
-    double x, y, z, u, v, w, mpw, di, dj, en; // en = mpw*|vel| (KM:412)
-    int tid, tborn;
-    int ln;      // region cell after the push (deposit + next histogram through shared memory), or -1
-    unsigned rn; // rank inside that cell
-    int lo;      // region cell before the push (output segment through shared memory), -1: `ro` is the slot, -2: nothing to write
-    unsigned ro; // rank inside that cell's share of the segment, or the absolute output slot
-};
+// rows of S that several pieces add into (cells holding more than SFS_PIECE particles of the chunk) start from zero
+__device__ __forceinline__ void sfs_zero_shared_rows(double *S, const unsigned short *pcOrd, int pbeg, int pend, int tid)
+{
+    for (int pid = pbeg + tid; pid < pend; pid += SFS_THREADS) {
+        const unsigned pc = pcOrd[pid];
+        if ((pc & 0x8000u) && (pid == pbeg || pcOrd[pid - 1] != pc))
+            for (int k = 0; k < 32; k++) S[(pc & 0x7fffu) * SFS_SROW + k] = 0.0;
+    }
+}
+
+static_assert(SFS_WARPS == 8, "phase 4 deals 7 fields x 2 row halves to 16 half warps");
+// shared memory of one CTA (dynamic), in doubles unless noted
+#define SFS_OFF_AUX (SFS_NSTAGE * SFS_STAGE_DOUBLES)            // [3][SFS_ROW]: corrected di, dj, mpw*|vel| of the pushed particle
+#define SFS_OFF_S (SFS_OFF_AUX + 3 * SFS_ROW)                   // [SFS_MAXP][SFS_SROW]: totals per non-empty new cell
+#define SFS_OFF_END (SFS_OFF_S + SFS_MAXP * SFS_SROW)
+#define SFS_U32_WORDS (2 * SFS_CHUNK + 4 * SFS_NCELL + 2 * SFS_NCELL) // pkN, pkO, cnt[2][2][NCELL], offN, baseO
+#define SFS_U16_WORDS (2 * SFS_CHUNK + 3 * SFS_NPIECE_MAX + SFS_NCELL + 8) // flO, perm, pieces, ordN, round starts
+#define SFS_SMEM_BYTES (SFS_OFF_END * 8 + SFS_U32_WORDS * 4 + SFS_U16_WORDS * 2 + 64)
 
 __global__ void __launch_bounds__(SFS_THREADS, SFS_MIN_CTAS)
 k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restrict__ ga)
 {
     extern __shared__ __align__(128) unsigned char sfs_raw[];
-    double *stage = reinterpret_cast<double *>(sfs_raw);                 // [2][8][SFS_ROW]
-    double *S = stage + 2 * SFS_STAGE_DOUBLES;                            // [NCELL][SFS_SROW] totals per new cell: [node][field half][group]
-    unsigned *cnt = reinterpret_cast<unsigned *>(S + SFS_NCELL * SFS_SROW); // [2 sets][cntN | cntO][NCELL], sets alternate between chunks
-    unsigned *offN = cnt + 4 * SFS_NCELL;                                 // [NCELL] first sorted position of a new cell
-    unsigned *baseO = offN + SFS_NCELL;                                   // [NCELL] first output slot of this chunk's share
-    unsigned short *pcCell = reinterpret_cast<unsigned short *>(baseO + SFS_NCELL); // [NPIECE_MAX] pieces: cell, first sorted position, length
-    unsigned short *pcStart = pcCell + SFS_NPIECE_MAX;
+    double *stage = reinterpret_cast<double *>(sfs_raw);       // [NSTAGE][8][SFS_ROW]: x,y,z,u,v,w,mpw,tag; phase 1 parks the pushed state in place
+    double *aux = stage + SFS_OFF_AUX;
+    double *S = stage + SFS_OFF_S;
+    unsigned *pkN = reinterpret_cast<unsigned *>(stage + SFS_OFF_END); // [CHUNK] new region cell << 16 | rank in it, ~0: not in the shared-memory deposit
+    unsigned *pkO = pkN + SFS_CHUNK;                           // [CHUNK] rank in the old region cell, or the absolute output slot
+    unsigned *cnt = pkO + SFS_CHUNK;                           // [2 sets][cntN | cntO][NCELL], sets alternate between chunks
+    unsigned *offN = cnt + 4 * SFS_NCELL;                      // [NCELL] first sorted position of a new cell
+    unsigned *baseO = offN + SFS_NCELL;                        // [NCELL] first output slot of this chunk's share of an old cell's segment
+    short *flO = reinterpret_cast<short *>(baseO + SFS_NCELL); // [CHUNK] old region cell, -1: pkO is the slot, -2: nothing to write
+    unsigned short *perm = reinterpret_cast<unsigned short *>(flO + SFS_CHUNK); // [CHUNK] stage index of the k-th particle in new-cell order
+    unsigned short *pcOrd = perm + SFS_CHUNK;                  // [NPIECE_MAX] pieces: row of S (bit 15: shared by several pieces), start, length
+    unsigned short *pcStart = pcOrd + SFS_NPIECE_MAX;
     unsigned short *pcLen = pcStart + SFS_NPIECE_MAX;
+    unsigned short *ordN = pcLen + SFS_NPIECE_MAX;             // [NCELL] 1 + ordinal of a non-empty new cell, 0: empty
+    unsigned short *rndStart = ordN + SFS_NCELL;               // [<= 8] first piece of every round of SFS_MAXP cells
     __shared__ __align__(8) unsigned long long sBar[2];
     __shared__ __align__(16) SDesc sDesc[3];
     __shared__ double sSums[5];
-    __shared__ int sNPieces, sNFall, sBox[4];
+    __shared__ int sNPieces, sNRows, sNFall, sBox[4];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const MeshDev &m = a.b.m;
     const size_t plane = (size_t)m.ni * m.nj;
     const bool simple_ok = !m.has_b && !m.any_seg && a.b.dt > 0;
     const int ntj = a.b.ntj;
-    double msum0 = 0, msum1 = 0; // mover sums, KM:406-413: lane (h, g) of every warp collects N, Px, Py, Pz (h = 0, g = 0..3) and E (h = 1, g = 0)
+    double msum0 = 0, msum1 = 0; // mover sums, KM:406-413: lane group g collects N, Px, Py, Pz (msum0) and E (msum1 of g = 0)
 
     // ---- chunks are dealt round robin; descriptor of chunk k+2 and data of chunk k+1 are in flight while k is processed ----
     if (tid == 0) {
@@ -268,62 +288,61 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
             }
         }
         unsigned *cntN = cnt + sb * 2 * SFS_NCELL, *cntO = cntN + SFS_NCELL; // particles per new / old cell of this chunk
-        const double *in = stage + sb * SFS_STAGE_DOUBLES;
-        double *D = stage + sb * SFS_STAGE_DOUBLES; // deposit operands overlay the input once phase 1 has consumed it
+        double *st = stage + sb * SFS_STAGE_DOUBLES;
         const int lead = (int)(cur.begin & 1ULL);
         const bool tiled = cur.tile >= 0;
         const int ci0 = tiled ? (cur.tile / ntj) * SF_TILE - SF_HALO : 0; // first cell row / column of the region
         const int cj0 = tiled ? (cur.tile % ntj) * SF_TILE - SF_HALO : 0;
         sfs_mbar_wait(&sBar[sb], (it >> 1) & 1u);
 
-        // ================= phase 1: push =================
-        SPart sp[SFS_PPT];
-#pragma unroll
-        for (int j = 0; j < SFS_PPT; j++) {
-            SPart &q = sp[j];
-            q.ln = -1; q.lo = -2; q.rn = 0; q.ro = 0;
-            const int o = j * SFS_THREADS + tid;
-            if (o >= cur.count) continue;
+        // ================= phase 1: push; the new state is parked in the particle's own stage slot =================
+#pragma unroll 1
+        for (int o = tid; o < SFS_CHUNK; o += SFS_THREADS) {
+            if (o >= cur.count) { flO[o] = -2; pkN[o] = 0xffffffffu; continue; }
             const int s = lead + o;
             PState p;
-            p.mpw = in[6 * SFS_ROW + s];
-            if (p.mpw != p.mpw) continue; // vacant slot (a particle that left during the previous step)
-            p.x = in[0 * SFS_ROW + s]; p.y = in[1 * SFS_ROW + s]; p.z = in[2 * SFS_ROW + s];
-            p.u = in[3 * SFS_ROW + s]; p.v = in[4 * SFS_ROW + s]; p.w = in[5 * SFS_ROW + s];
-            const int2 tag = reinterpret_cast<const int2 *>(in + 7 * SFS_ROW)[s];
-            q.tid = tag.x; q.tborn = tag.y;
+            p.mpw = st[6 * SFS_ROW + s];
+            if (p.mpw != p.mpw) { flO[o] = -2; pkN[o] = 0xffffffffu; continue; } // vacant slot (a particle that left during the previous step)
+            p.x = st[0 * SFS_ROW + s]; p.y = st[1 * SFS_ROW + s]; p.z = st[2 * SFS_ROW + s];
+            p.u = st[3 * SFS_ROW + s]; p.v = st[4 * SFS_ROW + s]; p.w = st[5 * SFS_ROW + s];
             p.li = sf_div_exact(p.x - m.x0, m.dhx, m.rdhx, m.fastdiv); // the stored lc of a normal particle is exactly XtoL(pos)
             p.lj = sf_div_exact(p.y - m.y0, m.dhy, m.rdhy, m.fastdiv);
             p.dt = 0;
-            // output segment: the cell the particle is in now
-            {
+            { // output segment: the cell the particle is in now
                 const int ci = min(max(sf_j2i(p.li), 0), m.ni - 2), cj = min(max(sf_j2i(p.lj), 0), m.nj - 2);
                 const int ri = ci - ci0, rj = cj - cj0;
                 if (tiled && ri >= 0 && rj >= 0 && ri < SFS_RC && rj < SFS_RC) {
-                    q.lo = ri * SFS_RC + rj;
-                    q.ro = atomicAdd(&cntO[q.lo], 1u);
+                    const int lo = ri * SFS_RC + rj;
+                    flO[o] = (short)lo;
+                    pkO[o] = atomicAdd(&cntO[lo], 1u);
                 } else {
-                    q.lo = -1;
-                    q.ro = atomicAdd(&a.cursor[sfs_gkey(ci, cj, ntj)], 1u);
+                    flO[o] = -1;
+                    pkO[o] = atomicAdd(&a.cursor[sfs_gkey(ci, cj, ntj)], 1u);
                 }
             }
             int fl = 3;
             if (!(simple_ok && sf_move_simple(m, a.b.qm, a.b.dt, p))) {
                 PState t = p; // only the copy has its address taken: p stays in registers
-                fl = stream_general(ga, &t, q.tid, q.tborn);
+                const int2 tag = reinterpret_cast<const int2 *>(st + 7 * SFS_ROW)[s];
+                fl = stream_general(ga, &t, tag.x, tag.y);
                 p = t;
             }
-            q.x = p.x; q.y = p.y; q.z = p.z; q.u = p.u; q.v = p.v; q.w = p.w;
-            q.mpw = (fl & 2) ? p.mpw : sf_vacant();
+            st[0 * SFS_ROW + s] = p.x; st[1 * SFS_ROW + s] = p.y; st[2 * SFS_ROW + s] = p.z;
+            st[3 * SFS_ROW + s] = p.u; st[4 * SFS_ROW + s] = p.v; st[5 * SFS_ROW + s] = p.w;
+            if (!(fl & 2)) st[6 * SFS_ROW + s] = sf_vacant(); // it left the fast store: the output slot becomes a vacant marker
+            unsigned pn = 0xffffffffu;
             if (fl & 1) {
                 const int i = sf_j2i(p.li), jj = sf_j2i(p.lj);
                 const bool inside = i >= 0 && jj >= 0 && i < m.ni - 1 && jj < m.nj - 1; // F2D:253: scatter() returns early otherwise
                 const int ri = i - ci0, rj = jj - cj0;
                 if (fl == 3 && tiled && inside && ri >= 0 && rj >= 0 && ri < SFS_RC && rj < SFS_RC) {
-                    q.ln = ri * SFS_RC + rj;
-                    q.rn = atomicAdd(&cntN[q.ln], 1u);
-                    sfs_offsets(m, p.li, p.lj, i, jj, q.di, q.dj);
-                    q.en = p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w);
+                    const int ln = ri * SFS_RC + rj;
+                    pn = ((unsigned)ln << 16) | atomicAdd(&cntN[ln], 1u);
+                    double di, dj;
+                    sfs_offsets(m, p.li, p.lj, i, jj, di, dj);
+                    aux[0 * SFS_ROW + s] = di;
+                    aux[1 * SFS_ROW + s] = dj;
+                    aux[2 * SFS_ROW + s] = p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w); // KM:412
                 } else {
                     const PState t = p;
                     stream_fallback(&ga->m, &t, a.b.dep, sSums);
@@ -334,6 +353,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                     }
                 }
             }
+            pkN[o] = pn;
         }
         __syncthreads(); // B1
 
@@ -346,7 +366,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 const int c = lane * 5 + k;
                 cn[k] = c < SFS_NCELL ? cntN[c] : 0u;
                 np[k] = (cn[k] + SFS_PIECE - 1) / SFS_PIECE;
-                sc += cn[k] | (np[k] << 16); // particles and pieces scanned together
+                sc += cn[k] | (np[k] << 12) | ((cn[k] ? 1u : 0u) << 22); // particles, pieces and non-empty cells scanned together
             }
             unsigned ic = sc; // inclusive warp scan
 #pragma unroll
@@ -354,23 +374,26 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 const unsigned y = __shfl_up_sync(0xffffffffu, ic, d);
                 if (lane >= d) ic += y;
             }
-            unsigned oc = (ic - sc) & 0xffffu, op = (ic - sc) >> 16;
+            unsigned oc = (ic - sc) & 0xfffu, op = ((ic - sc) >> 12) & 0x3ffu, orow = (ic - sc) >> 22;
             int bi0 = SFS_RC, bi1 = -1, bj0 = SFS_RC, bj1 = -1; // bounding box of the non-empty new cells
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 const int c = lane * 5 + k;
                 if (c < SFS_NCELL) {
                     offN[c] = oc;
+                    ordN[c] = (unsigned short)(cn[k] ? orow + 1 : 0);
                     if (cn[k]) {
                         bi0 = min(bi0, c / SFS_RC); bi1 = max(bi1, c / SFS_RC);
                         bj0 = min(bj0, c % SFS_RC); bj1 = max(bj1, c % SFS_RC);
+                        if (orow % SFS_MAXP == 0) rndStart[orow / SFS_MAXP] = (unsigned short)op;
                         const unsigned per = (cn[k] + np[k] - 1) / np[k];
                         for (unsigned q = 0; q < np[k]; q++) {
-                            const unsigned st = q * per, ln = min(per, cn[k] - st);
-                            pcCell[op + q] = (unsigned short)(c | (np[k] > 1 ? 0x8000 : 0)); // bit 15: the cell's total is shared by several pieces
-                            pcStart[op + q] = (unsigned short)(oc + st);
+                            const unsigned b = q * per, ln = min(per, cn[k] - b);
+                            pcOrd[op + q] = (unsigned short)((orow % SFS_MAXP) | (np[k] > 1 ? 0x8000u : 0u));
+                            pcStart[op + q] = (unsigned short)(oc + b);
                             pcLen[op + q] = (unsigned short)ln;
                         }
+                        orow++;
                     }
                     oc += cn[k];
                     op += np[k];
@@ -379,11 +402,16 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
             bi0 = __reduce_min_sync(0xffffffffu, bi0); bi1 = __reduce_max_sync(0xffffffffu, bi1);
             bj0 = __reduce_min_sync(0xffffffffu, bj0); bj1 = __reduce_max_sync(0xffffffffu, bj1);
             if (lane == 31) {
-                sNPieces = (int)(ic >> 16);
+                sNPieces = (int)((ic >> 12) & 0x3ffu);
+                sNRows = (int)(ic >> 22);
+                const unsigned rows = ic >> 22;
+                rndStart[rows ? (rows + SFS_MAXP - 1) / SFS_MAXP : 1] = (unsigned short)((ic >> 12) & 0x3ffu); // end of the last round
+                if (!rows) rndStart[0] = 0;
                 sBox[0] = bi0; sBox[1] = bi1; sBox[2] = bj0; sBox[3] = bj1;
             }
         } else if (tiled) {
-            for (int c = SFS_THREADS - 1 - tid; c < SFS_NCELL; c += SFS_THREADS - 32) {
+            const int c = SFS_THREADS - 1 - tid;
+            if (c < SFS_NCELL) {
                 const unsigned no = cntO[c], nn = cntN[c];
                 if (no | nn) {
                     const int ci = ci0 + c / SFS_RC, cj = cj0 + c % SFS_RC;
@@ -392,118 +420,134 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                     if (nn) {
                         atomicAdd(&a.hist_next[key], nn);
                         atomicAdd(a.b.dep + SFGPU_F_MPC * plane + (size_t)ci * m.nj + cj, (double)nn); // KM:1593
-                        if (nn > SFS_PIECE) // several pieces add into this cell's totals
-                            for (int k = 0; k < 32; k++) S[c * SFS_SROW + k] = 0.0;
                     }
                 }
             }
         }
         __syncthreads(); // B2
 
-        // ================= phase 2b: deposit operands to their sorted position =================
+        // ================= phase 2b: permutation into new-cell order; output bases =================
 #pragma unroll
         for (int j = 0; j < SFS_PPT; j++) {
-            const SPart &q = sp[j];
-            if (q.ln >= 0) {
-                const unsigned pos = offN[q.ln] + q.rn;
-                D[0 * SFS_DROW + pos] = q.di; D[1 * SFS_DROW + pos] = q.dj; D[2 * SFS_DROW + pos] = q.mpw;
-                D[3 * SFS_DROW + pos] = q.u; D[4 * SFS_DROW + pos] = q.v; D[5 * SFS_DROW + pos] = q.w;
-                D[6 * SFS_DROW + pos] = q.en;
-            }
+            const int o = j * SFS_THREADS + tid;
+            const unsigned pn = pkN[o];
+            if (pn != 0xffffffffu) perm[offN[pn >> 16] + (pn & 0xffffu)] = (unsigned short)(lead + o);
         }
         { // the other counter set is free (its chunk finished phase 4 before B1): clear it for the next chunk
             unsigned *nextc = cnt + ((it + 1) & 1) * 2 * SFS_NCELL;
             for (int k = tid; k < 2 * SFS_NCELL; k += SFS_THREADS) nextc[k] = 0;
         }
-        __syncthreads(); // B3
-
-        // ================= phase 3: cell totals.  Half a warp per piece: lane (slot s of 4, group g of 4) =================
-        {
-            const int half = lane >> 4, s = (lane >> 2) & 3, g = lane & 3;
-            const double *Dv = D + (g == 0 ? 6 : 2 + g) * SFS_DROW; // velocity component of this lane's two fields (g = 0: the energy term)
-            const int npieces = sNPieces;
-            const bool h0 = (lane & 4) != 0, h1 = (lane & 8) != 0;
-            for (int pp = 2 * wid; pp < npieces; pp += 2 * SFS_WARPS) {
-                const int pid = pp + half;
-                const bool have = pid < npieces;
-                const int start = have ? pcStart[pid] : 0, end = have ? start + pcLen[pid] : 0;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0; // [node 00,10,11,01][field lo, hi]
-                for (int k = start + s; k < end; k += 4) {
-                    const double di = D[k], dj = D[SFS_DROW + k], mp = D[2 * SFS_DROW + k], vc = Dv[k];
-                    const double t = mp * vc;
-                    const double v1 = g == 0 ? mp : t, v2 = g == 0 ? vc : t * vc; // (Den | U,V,W) and (mpw*|vel| | UU,VV,WW), KM:1584-1590
-                    const double ai = 1 - di, bj = 1 - dj;
-                    const double b1 = bj * v1, d1 = dj * v1, b2 = bj * v2, d2 = dj * v2;
-                    a0 = __fma_rn(ai, b1, a0); a1 = __fma_rn(ai, b2, a1); // (1-di)(1-dj)
-                    a2 = __fma_rn(di, b1, a2); a3 = __fma_rn(di, b2, a3); // di(1-dj)
-                    a4 = __fma_rn(di, d1, a4); a5 = __fma_rn(di, d2, a5); // di*dj
-                    a6 = __fma_rn(ai, d1, a6); a7 = __fma_rn(ai, d2, a7); // (1-di)dj
-                }
-                // transposed reduction over the 4 slots: every stage halves the values a lane keeps
-                double k0 = h0 ? a4 : a0, k1 = h0 ? a5 : a1, k2 = h0 ? a6 : a2, k3 = h0 ? a7 : a3;
-                k0 += __shfl_xor_sync(0xffffffffu, h0 ? a0 : a4, 4);
-                k1 += __shfl_xor_sync(0xffffffffu, h0 ? a1 : a5, 4);
-                k2 += __shfl_xor_sync(0xffffffffu, h0 ? a2 : a6, 4);
-                k3 += __shfl_xor_sync(0xffffffffu, h0 ? a3 : a7, 4);
-                double m0 = h1 ? k2 : k0, m1 = h1 ? k3 : k1;
-                m0 += __shfl_xor_sync(0xffffffffu, h1 ? k0 : k2, 8);
-                m1 += __shfl_xor_sync(0xffffffffu, h1 ? k1 : k3, 8);
-                // this lane now holds node n = 2*h0 + h1 of group g: m0 = low field, m1 = high field
-                if (have) {
-                    const unsigned pc = pcCell[pid];
-                    double *row = S + (pc & 0x7fffu) * SFS_SROW + ((h0 ? 4 : 0) + (h1 ? 2 : 0)) * 4 + g;
-                    if (pc & 0x8000u) {
-                        atomicAdd(row, m0);
-                        atomicAdd(row + 4, m1);
-                    } else {
-                        row[0] = m0;
-                        row[4] = m1;
-                    }
-                    msum0 += m0; // the node parts of a field add up to its particle total (the weights sum to 1)
-                    msum1 += m1;
-                }
-            }
+        sfs_zero_shared_rows(S, pcOrd, rndStart[0], rndStart[1], tid);
+        if (wid != 0 && tiled) {
+            const int c = SFS_THREADS - 1 - tid;
+            if (c < SFS_NCELL) baseO[c] = gbase;
         }
-        if (wid != 0 && tiled)
-            for (int c = SFS_THREADS - 1 - tid; c < SFS_NCELL; c += SFS_THREADS - 32) baseO[c] = gbase;
-        __syncthreads(); // B4: cell totals and output bases visible; D is dead
+        __syncthreads(); // B3
 
         // ================= output: every live input particle takes one slot of its old cell's segment =================
 #pragma unroll
         for (int j = 0; j < SFS_PPT; j++) {
-            const SPart &q = sp[j];
-            if (q.lo == -2) continue;
-            const size_t slot = (q.lo >= 0) ? (size_t)baseO[q.lo] + q.ro : (size_t)q.ro;
-            a.out.x[slot] = q.x; a.out.y[slot] = q.y; a.out.z[slot] = q.z;
-            a.out.u[slot] = q.u; a.out.v[slot] = q.v; a.out.w[slot] = q.w;
-            a.out.mpw[slot] = q.mpw;
-            a.out.tag[slot] = make_int2(q.tid, q.tborn);
+            const int o = j * SFS_THREADS + tid;
+            const int lo = flO[o];
+            if (lo == -2) continue;
+            const int s = lead + o;
+            const size_t slot = (lo >= 0) ? (size_t)baseO[lo] + pkO[o] : (size_t)pkO[o];
+            a.out.x[slot] = st[0 * SFS_ROW + s]; a.out.y[slot] = st[1 * SFS_ROW + s]; a.out.z[slot] = st[2 * SFS_ROW + s];
+            a.out.u[slot] = st[3 * SFS_ROW + s]; a.out.v[slot] = st[4 * SFS_ROW + s]; a.out.w[slot] = st[5 * SFS_ROW + s];
+            a.out.mpw[slot] = st[6 * SFS_ROW + s];
+            a.out.tag[slot] = reinterpret_cast<const int2 *>(st + 7 * SFS_ROW)[s];
         }
-        // ================= phase 4: node totals -> global deposit =================
-        // half a warp per (field, node row) of the bounding box; a lane sums the totals of the four cells around its node
-        if (sNPieces) {
-            const int bi0 = sBox[0], bj0 = sBox[2];
-            const int nh = sBox[1] - bi0 + 2, nw = sBox[3] - bj0 + 2; // node rows / columns touched
-            const int half = lane >> 4, hl = lane & 15;
-            for (int r = 2 * wid + half; r < 7 * nh; r += 2 * SFS_WARPS) {
-                const int f = r / nh, na = bi0 + r % nh, nb = bj0 + hl;
-                if (hl >= nw) continue;
-                const int col = ((f >= 4 ? 1 : 0)) * 4 + (f == 0 ? 0 : (f <= 3 ? f : f - 3)); // + node * 8
-                double sum = 0;
-                bool any = false;
-#pragma unroll
-                for (int n = 0; n < 4; n++) { // this node is node n (00, 10, 11, 01) of cell (na - dn_i, nb - dn_j)
-                    const int ca = na - ((n == 1 || n == 2) ? 1 : 0), cb = nb - ((n >= 2) ? 1 : 0);
-                    if (ca < 0 || cb < 0 || ca >= SFS_RC || cb >= SFS_RC) continue;
-                    const int c = ca * SFS_RC + cb;
-                    if (cntN[c]) {
-                        sum += S[c * SFS_SROW + n * 8 + col];
-                        any = true;
+
+        const int nrows = sNRows;
+        for (int r0 = 0, rnd = 0; r0 < nrows; r0 += SFS_MAXP, rnd++) {
+            const int pbeg = rndStart[rnd], pend = rndStart[rnd + 1];
+            if (rnd > 0) { // (round 0 was prepared before B3)
+                __syncthreads(); // S is reused
+                sfs_zero_shared_rows(S, pcOrd, pbeg, pend, tid);
+                __syncthreads();
+            }
+            // ================= phase 3: cell totals.  Half a warp per piece: lane (slot s of 4, group g of 4) =================
+            {
+                const int half = lane >> 4, s4 = (lane >> 2) & 3, g = lane & 3;
+                const double *Dv = (g == 0) ? (aux + 2 * SFS_ROW) : (st + (2 + g) * SFS_ROW); // g = 0: mpw*|vel|; g = 1..3: u, v, w
+                const bool h0 = (lane & 4) != 0, h1 = (lane & 8) != 0;
+                for (int pp = pbeg + 2 * wid; pp < pend; pp += 2 * SFS_WARPS) {
+                    const int pid = pp + half;
+                    const bool have = pid < pend;
+                    const int start = have ? pcStart[pid] : 0, end = have ? start + pcLen[pid] : 0;
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0; // [node 00,10,11,01][field lo, hi]
+                    for (int k = start + s4; k < end; k += 4) {
+                        const int q = perm[k];
+                        const double di = aux[q], dj = aux[SFS_ROW + q], mp = st[6 * SFS_ROW + q], vc = Dv[q];
+                        const double t = mp * vc;
+                        const double v1 = g == 0 ? mp : t, v2 = g == 0 ? vc : t * vc; // (Den | U,V,W) and (mpw*|vel| | UU,VV,WW), KM:1584-1590
+                        const double ai = 1 - di, bj = 1 - dj;
+                        const double b1 = bj * v1, d1 = dj * v1, b2 = bj * v2, d2 = dj * v2;
+                        a0 = __fma_rn(ai, b1, a0); a1 = __fma_rn(ai, b2, a1); // (1-di)(1-dj)
+                        a2 = __fma_rn(di, b1, a2); a3 = __fma_rn(di, b2, a3); // di(1-dj)
+                        a4 = __fma_rn(di, d1, a4); a5 = __fma_rn(di, d2, a5); // di*dj
+                        a6 = __fma_rn(ai, d1, a6); a7 = __fma_rn(ai, d2, a7); // (1-di)dj
+                    }
+                    // transposed reduction over the 4 slots: every stage halves the values a lane keeps
+                    double k0 = h0 ? a4 : a0, k1 = h0 ? a5 : a1, k2 = h0 ? a6 : a2, k3 = h0 ? a7 : a3;
+                    k0 += __shfl_xor_sync(0xffffffffu, h0 ? a0 : a4, 4);
+                    k1 += __shfl_xor_sync(0xffffffffu, h0 ? a1 : a5, 4);
+                    k2 += __shfl_xor_sync(0xffffffffu, h0 ? a2 : a6, 4);
+                    k3 += __shfl_xor_sync(0xffffffffu, h0 ? a3 : a7, 4);
+                    double m0 = h1 ? k2 : k0, m1 = h1 ? k3 : k1;
+                    m0 += __shfl_xor_sync(0xffffffffu, h1 ? k0 : k2, 8);
+                    m1 += __shfl_xor_sync(0xffffffffu, h1 ? k1 : k3, 8);
+                    // this lane now holds node n = 2*h0 + h1 of group g: m0 = low field, m1 = high field
+                    if (have) {
+                        const unsigned pc = pcOrd[pid];
+                        double *row = S + (pc & 0x7fffu) * SFS_SROW + ((h0 ? 4 : 0) + (h1 ? 2 : 0)) * 4 + g;
+                        if (pc & 0x8000u) {
+                            atomicAdd(row, m0);
+                            atomicAdd(row + 4, m1);
+                        } else {
+                            row[0] = m0;
+                            row[4] = m1;
+                        }
+                        msum0 += m0; // the node parts of a field add up to its particle total (the weights sum to 1)
+                        msum1 += m1;
                     }
                 }
-                if (any) atomicAdd(a.b.dep + f * plane + (size_t)(ci0 + na) * m.nj + (cj0 + nb), sum);
+            }
+            __syncthreads(); // B4: cell totals visible
+            // ================= phase 4: node totals -> global deposit =================
+            // half a warp per field and half of the cell rows of the bounding box: a lane owns a node column, walks the cell rows
+            // and hands the lower node row of each cell row to the next one in a register
+            {
+                const int bi0 = sBox[0], bi1 = sBox[1], bj0 = sBox[2], bj1 = sBox[3];
+                const int unit = 2 * wid + (lane >> 4), hl = lane & 15;
+                const int f = unit & 7, part = unit >> 3;
+                const int nrow = bi1 - bi0 + 1, mid = bi0 + (nrow + 1) / 2;
+                const int ra = part == 0 ? bi0 : mid, rb = part == 0 ? mid : bi1 + 1; // cell rows [ra, rb)
+                const int nb = bj0 + hl; // node column; also the column of the cell whose node 00 / 10 it is
+                const bool cell_ok = nb <= bj1, node_ok = nb <= bj1 + 1;
+                const int col = (f >= 4 ? 4 : 0) + (f == 0 ? 0 : (f <= 3 ? f : f - 3));
+                const bool fok = f < 7; // (the 16th unit idles; every lane still takes part in the shuffles)
+                {
+                    double carry = 0;
+                    for (int ca = ra; ca < rb; ca++) {
+                        double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+                        if (cell_ok && fok) {
+                            const int ord = (int)ordN[ca * SFS_RC + nb] - 1;
+                            if (ord >= r0 && ord < r0 + SFS_MAXP) {
+                                const double *row = S + (ord - r0) * SFS_SROW + col;
+                                t0 = row[0]; t1 = row[8]; t2 = row[16]; t3 = row[24];
+                            }
+                        }
+                        const double u2 = __shfl_up_sync(0xffffffffu, t2, 1, 16), u3 = __shfl_up_sync(0xffffffffu, t3, 1, 16);
+                        const double top = carry + (t0 + (hl ? u3 : 0.0));
+                        carry = t1 + (hl ? u2 : 0.0);
+                        if (fok && node_ok && top != 0.0) atomicAdd(a.b.dep + f * plane + (size_t)(ci0 + ca) * m.nj + (cj0 + nb), top);
+                    }
+                    if (fok && rb > ra && node_ok && carry != 0.0) atomicAdd(a.b.dep + f * plane + (size_t)(ci0 + rb) * m.nj + (cj0 + nb), carry);
+                }
             }
         }
+        if (nrows == 0) __syncthreads(); // (keeps the barrier count per chunk uniform: the stage must be dead before the next chunk's TMA)
         if (tid == 0) asm volatile("cp.async.wait_all;" ::: "memory"); // descriptor of chunk it+2 (published by the next barriers)
     }
 
@@ -519,7 +563,6 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
     if (tid == 0 && sNFall) atomicAdd(&a.b.c->n_fallback, (unsigned long long)sNFall);
 }
 
-#define SFS_SMEM_BYTES ((2 * SFS_STAGE_DOUBLES + SFS_NCELL * SFS_SROW) * 8 + 6 * SFS_NCELL * 4 + 3 * SFS_NPIECE_MAX * 2 + 64)
 
 // chunks of the streaming kernel: each tile's run [offs[tile*64], offs[(tile+1)*64]) cut into <= SFS_CHUNK particles
 __global__ void k_build_chunks(const unsigned *__restrict__ offs, int n_tiles, WorkItem *__restrict__ items, unsigned *__restrict__ n_items,
