@@ -40,6 +40,9 @@
 #define SFS_NPIECE_MAX (SFS_NCELL + SFS_CHUNK / SFS_PIECE + 2)
 #define SFS_ROW (SFS_CHUNK + 2)         // stage row (doubles): an aligned superset of the chunk
 #define SFS_NSTAGE 2
+#ifndef SFS_DYNAMIC
+#define SFS_DYNAMIC 0   // 1: warps draw pieces from a shared counter instead of a fixed round robin (no gain measured)
+#endif
 #ifndef SFS_MAXP
 #define SFS_MAXP 80                     // cell totals held per round (a chunk rarely fills more new cells)
 #endif
@@ -51,7 +54,8 @@ static_assert(SFS_CHUNK < 0x1000 && SFS_NPIECE_MAX < 0x400 && SFS_NCELL < 0x400,
 static_assert(SFS_NCELL / SFS_MAXP + 2 <= 8, "round starts");
 static_assert(SFS_NCELL <= SFS_THREADS - 32, "one thread per region cell besides warp 0");
 static_assert(SFS_NN <= 16, "phase 4 gives half a warp to a node row");
-static_assert(SFS_NCELL <= 5 * 32, "warp-0 scan handles 5 cells per lane");
+#define SFS_SCAN_WARPS ((SFS_NCELL + 31) / 32)
+static_assert(SFS_SCAN_WARPS <= SFS_WARPS, "one new cell per lane of the scanning warps");
 
 struct StreamArgs {
     FastStepArgs b;        // b.fs = input store, b.items / b.n_items = chunks of the sorted prefix
@@ -85,12 +89,14 @@ __device__ __forceinline__ void sfs_tma_load(void *dst, const void *src, unsigne
 __device__ __forceinline__ void sfs_mbar_wait(unsigned long long *bar, unsigned parity)
 {
     unsigned ok;
+    if ((threadIdx.x & 31) == 0) // one lane polls; __syncwarp() orders the others behind the observed completion
     do {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok)
                      : "r"(sfs_smem(bar)), "r"(parity)
                      : "memory");
     } while (!ok);
+    __syncwarp();
 }
 
 // tile-major cell key of a (clamped) cell: the key of sf_cell_key()
@@ -139,33 +145,57 @@ __device__ __forceinline__ void fast_leave(const FastStepArgs &a, int st, const 
     }
 }
 
-// everything that is not the common case, out of line.  Returns bit 0: the particle deposits in this step,
-// bit 1: it stays a normal particle of the fast store.
-__device__ __noinline__ int stream_general(const FastStepArgs *__restrict__ ga, PState *pp, int tag_id, int tag_born)
+// deposit of a particle the shared-memory path cannot take (outside the tile + halo, F2D:253 early return, exceptional):
+// global FP64 REDs (F2D:290-293, KM:1593) and its mover sums (KM:406-413) into the CTA's shared slots (CAS atomics: rare)
+__device__ __forceinline__ void sfs_deposit_global(const MeshDev &m, const PState &p, double *dep, double *sums)
 {
-    const FastStepArgs &a = *ga;
-    MoveAux aux;
-    bool exact = true;
-    const GlobalFieldGather fg;
-    PState p = *pp;
-    const int st = sf_move(a.m, a.meshes, a.qm, a.charge, a.dt, false, p, aux, exact, fg);
-    *pp = p;
-    if (st == SF_ALIVE && exact && p.dt == 0) return 3;
-    fast_leave(a, st, p, aux, make_int2(tag_id, tag_born));
-    return st == SF_ALIVE ? 1 : 0;
-}
-
-// deposit of a particle the shared-memory path cannot take: global FP64 REDs (F2D:290-293, KM:1593)
-// and its mover sums (KM:406-413) into the CTA's shared slots (CAS atomics: rare)
-__device__ __noinline__ void stream_fallback(const MeshDev *mp, const PState *pp, double *dep, double *sums)
-{
-    const PState &p = *pp;
-    deposit_global(*mp, p, dep);
+    deposit_global(m, p, dep);
     atomicAdd(sums + 0, p.mpw);
     atomicAdd(sums + 1, p.mpw * p.u);
     atomicAdd(sums + 2, p.mpw * p.v);
     atomicAdd(sums + 3, p.mpw * p.w);
     atomicAdd(sums + 4, p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w));
+}
+
+// Everything that is not the common case, out of line.  The particle travels through its stage slot (shared memory), not
+// through registers or a local struct: a call that keeps ten doubles alive costs the hot loop ~55 registers.
+// Returns 3 when the particle stays a normal particle of the fast store (new state parked in the slot), else 0 (it left for a
+// record list / died; if it still deposits in this step, that has been done here through the global path).
+__device__ __noinline__ int stream_general(const FastStepArgs *__restrict__ ga, double *st, int s, double *sums)
+{
+    const FastStepArgs &a = *ga;
+    MoveAux aux;
+    bool exact = true;
+    const GlobalFieldGather fg;
+    PState p;
+    p.x = st[0 * SFS_ROW + s]; p.y = st[1 * SFS_ROW + s]; p.z = st[2 * SFS_ROW + s];
+    p.u = st[3 * SFS_ROW + s]; p.v = st[4 * SFS_ROW + s]; p.w = st[5 * SFS_ROW + s];
+    p.mpw = st[6 * SFS_ROW + s];
+    p.li = (p.x - a.m.x0) / a.m.dhx; // the stored lc of a normal particle is exactly XtoL(pos)
+    p.lj = (p.y - a.m.y0) / a.m.dhy;
+    p.dt = 0;
+    const int st_ = sf_move(a.m, a.meshes, a.qm, a.charge, a.dt, false, p, aux, exact, fg);
+    st[0 * SFS_ROW + s] = p.x; st[1 * SFS_ROW + s] = p.y; st[2 * SFS_ROW + s] = p.z;
+    st[3 * SFS_ROW + s] = p.u; st[4 * SFS_ROW + s] = p.v; st[5 * SFS_ROW + s] = p.w;
+    if (st_ == SF_ALIVE && exact && p.dt == 0) return 3;
+    fast_leave(a, st_, p, aux, reinterpret_cast<const int2 *>(st + 7 * SFS_ROW)[s]);
+    if (st_ == SF_ALIVE) sfs_deposit_global(a.m, p, a.dep, sums); // stale lc / residual dt: it deposits where its lc says
+    return 0;
+}
+
+// global-path deposit of a normal particle whose new cell the shared-memory path does not cover; counts it for the next launch
+__device__ __noinline__ void stream_fallback(const FastStepArgs *__restrict__ ga, const double *st, int s, double *sums, unsigned *hist_next)
+{
+    const MeshDev &m = ga->m;
+    PState p;
+    p.x = st[0 * SFS_ROW + s]; p.y = st[1 * SFS_ROW + s]; p.z = st[2 * SFS_ROW + s];
+    p.u = st[3 * SFS_ROW + s]; p.v = st[4 * SFS_ROW + s]; p.w = st[5 * SFS_ROW + s];
+    p.mpw = st[6 * SFS_ROW + s];
+    p.li = (p.x - m.x0) / m.dhx;
+    p.lj = (p.y - m.y0) / m.dhy;
+    p.dt = 0;
+    sfs_deposit_global(m, p, ga->dep, sums);
+    atomicAdd(&hist_next[sf_cell_key(m, p.li, p.lj, ga->ntj)], 1u);
 }
 
 // the corrected in-cell offsets of F2D:262-288: the four weights are (1-di)(1-dj), di(1-dj), di*dj, (1-di)dj
@@ -248,7 +278,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
     __shared__ __align__(8) unsigned long long sBar[2];
     __shared__ __align__(16) SDesc sDesc[3];
     __shared__ double sSums[5];
-    __shared__ int sNPieces, sNRows, sNFall, sBox[4];
+    __shared__ int sNPieces, sNRows, sNFall, sBox[8], sNextPiece; // sBox: [2 sets][i min, i max, j min, j max]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const MeshDev &m = a.b.m;
@@ -269,6 +299,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
         if (d0.count) sfs_issue(a.b.fs, d0, stage, &sBar[0]);
     }
     if (tid < 5) sSums[tid] = 0.0;
+    if (tid < 8) sBox[tid] = (tid & 1) ? -1 : SFS_RC;
     for (int k = tid; k < 4 * SFS_NCELL; k += SFS_THREADS) cnt[k] = 0;
     __syncthreads();
 
@@ -321,21 +352,26 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 }
             }
             int fl = 3;
-            if (!(simple_ok && sf_move_simple(m, a.b.qm, a.b.dt, p))) {
-                PState t = p; // only the copy has its address taken: p stays in registers
-                const int2 tag = reinterpret_cast<const int2 *>(st + 7 * SFS_ROW)[s];
-                fl = stream_general(ga, &t, tag.x, tag.y);
-                p = t;
+            if (simple_ok && sf_move_simple(m, a.b.qm, a.b.dt, p)) {
+                st[0 * SFS_ROW + s] = p.x; st[1 * SFS_ROW + s] = p.y; st[2 * SFS_ROW + s] = p.z;
+                st[3 * SFS_ROW + s] = p.u; st[4 * SFS_ROW + s] = p.v; st[5 * SFS_ROW + s] = p.w;
+            } else {
+                fl = stream_general(ga, st, s, sSums);
+                if (fl == 3) { // back to the common path: a normal particle again, lc = XtoL(pos)
+                    p.x = st[0 * SFS_ROW + s]; p.y = st[1 * SFS_ROW + s];
+                    p.u = st[3 * SFS_ROW + s]; p.v = st[4 * SFS_ROW + s]; p.w = st[5 * SFS_ROW + s];
+                    p.li = sf_div_ieee(p.x - m.x0, m.dhx);
+                    p.lj = sf_div_ieee(p.y - m.y0, m.dhy);
+                } else {
+                    st[6 * SFS_ROW + s] = sf_vacant(); // it left the fast store: the output slot becomes a vacant marker
+                }
             }
-            st[0 * SFS_ROW + s] = p.x; st[1 * SFS_ROW + s] = p.y; st[2 * SFS_ROW + s] = p.z;
-            st[3 * SFS_ROW + s] = p.u; st[4 * SFS_ROW + s] = p.v; st[5 * SFS_ROW + s] = p.w;
-            if (!(fl & 2)) st[6 * SFS_ROW + s] = sf_vacant(); // it left the fast store: the output slot becomes a vacant marker
             unsigned pn = 0xffffffffu;
-            if (fl & 1) {
+            if (fl == 3) {
                 const int i = sf_j2i(p.li), jj = sf_j2i(p.lj);
                 const bool inside = i >= 0 && jj >= 0 && i < m.ni - 1 && jj < m.nj - 1; // F2D:253: scatter() returns early otherwise
                 const int ri = i - ci0, rj = jj - cj0;
-                if (fl == 3 && tiled && inside && ri >= 0 && rj >= 0 && ri < SFS_RC && rj < SFS_RC) {
+                if (tiled && inside && ri >= 0 && rj >= 0 && ri < SFS_RC && rj < SFS_RC) {
                     const int ln = ri * SFS_RC + rj;
                     pn = ((unsigned)ln << 16) | atomicAdd(&cntN[ln], 1u);
                     double di, dj;
@@ -344,13 +380,8 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                     aux[1 * SFS_ROW + s] = dj;
                     aux[2 * SFS_ROW + s] = p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w); // KM:412
                 } else {
-                    const PState t = p;
-                    stream_fallback(&ga->m, &t, a.b.dep, sSums);
+                    stream_fallback(ga, st, s, sSums, a.hist_next);
                     atomicAdd(&sNFall, 1);
-                    if (fl & 2) {
-                        const int ci = min(max(i, 0), m.ni - 2), cj = min(max(jj, 0), m.nj - 2);
-                        atomicAdd(&a.hist_next[sfs_gkey(ci, cj, ntj)], 1u);
-                    }
                 }
             }
             pkN[o] = pn;
@@ -359,57 +390,60 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
 
         // ================= phase 2a: offsets, pieces, global bookkeeping =================
         unsigned gbase = 0;
-        if (wid == 0) {
-            unsigned cn[5], np[5], sc = 0;
+        if (wid < SFS_SCAN_WARPS) { // one new cell per lane: particles, pieces and non-empty cells are scanned together (12 + 10 + 10 bits)
+            unsigned mine = 0, base = 0;
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const int c = lane * 5 + k;
-                cn[k] = c < SFS_NCELL ? cntN[c] : 0u;
-                np[k] = (cn[k] + SFS_PIECE - 1) / SFS_PIECE;
-                sc += cn[k] | (np[k] << 12) | ((cn[k] ? 1u : 0u) << 22); // particles, pieces and non-empty cells scanned together
+            for (int g = 0; g < SFS_SCAN_WARPS; g++) { // every scanning warp sums all groups: no cross-warp hand-over, no extra barrier
+                const int c = g * 32 + lane;
+                const unsigned cn = c < SFS_NCELL ? cntN[c] : 0u;
+                const unsigned v = cn | (((cn + SFS_PIECE - 1) / SFS_PIECE) << 12) | ((cn ? 1u : 0u) << 22);
+                const unsigned t = __reduce_add_sync(0xffffffffu, v);
+                if (g < wid) base += t;
+                if (g == wid) mine = v;
             }
-            unsigned ic = sc; // inclusive warp scan
+            unsigned ic = mine; // inclusive warp scan
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const unsigned y = __shfl_up_sync(0xffffffffu, ic, d);
                 if (lane >= d) ic += y;
             }
-            unsigned oc = (ic - sc) & 0xfffu, op = ((ic - sc) >> 12) & 0x3ffu, orow = (ic - sc) >> 22;
+            ic += base;
+            const unsigned ex = ic - mine, cn = mine & 0xfffu, np = (mine >> 12) & 0x3ffu;
+            const unsigned oc = ex & 0xfffu, op = (ex >> 12) & 0x3ffu, orow = ex >> 22;
+            const int c = wid * 32 + lane;
             int bi0 = SFS_RC, bi1 = -1, bj0 = SFS_RC, bj1 = -1; // bounding box of the non-empty new cells
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const int c = lane * 5 + k;
-                if (c < SFS_NCELL) {
-                    offN[c] = oc;
-                    ordN[c] = (unsigned short)(cn[k] ? orow + 1 : 0);
-                    if (cn[k]) {
-                        bi0 = min(bi0, c / SFS_RC); bi1 = max(bi1, c / SFS_RC);
-                        bj0 = min(bj0, c % SFS_RC); bj1 = max(bj1, c % SFS_RC);
-                        if (orow % SFS_MAXP == 0) rndStart[orow / SFS_MAXP] = (unsigned short)op;
-                        const unsigned per = (cn[k] + np[k] - 1) / np[k];
-                        for (unsigned q = 0; q < np[k]; q++) {
-                            const unsigned b = q * per, ln = min(per, cn[k] - b);
-                            pcOrd[op + q] = (unsigned short)((orow % SFS_MAXP) | (np[k] > 1 ? 0x8000u : 0u));
-                            pcStart[op + q] = (unsigned short)(oc + b);
-                            pcLen[op + q] = (unsigned short)ln;
-                        }
-                        orow++;
+            if (c < SFS_NCELL) {
+                offN[c] = oc;
+                ordN[c] = (unsigned short)(cn ? orow + 1 : 0);
+                if (cn) {
+                    bi0 = bi1 = c / SFS_RC;
+                    bj0 = bj1 = c % SFS_RC;
+                    if (orow % SFS_MAXP == 0) rndStart[orow / SFS_MAXP] = (unsigned short)op;
+                    const unsigned per = (cn + np - 1) / np;
+                    for (unsigned q = 0; q < np; q++) {
+                        const unsigned b = q * per, ln = min(per, cn - b);
+                        pcOrd[op + q] = (unsigned short)((orow % SFS_MAXP) | (np > 1 ? 0x8000u : 0u));
+                        pcStart[op + q] = (unsigned short)(oc + b);
+                        pcLen[op + q] = (unsigned short)ln;
                     }
-                    oc += cn[k];
-                    op += np[k];
+                }
+                if (c == SFS_NCELL - 1) { // inclusive totals
+                    const unsigned rows = ic >> 22, pieces = (ic >> 12) & 0x3ffu;
+                    sNextPiece = 0;
+                    sNPieces = (int)pieces;
+                    sNRows = (int)rows;
+                    rndStart[rows ? (rows + SFS_MAXP - 1) / SFS_MAXP : 1] = (unsigned short)pieces; // end of the last round
+                    if (!rows) rndStart[0] = 0;
                 }
             }
             bi0 = __reduce_min_sync(0xffffffffu, bi0); bi1 = __reduce_max_sync(0xffffffffu, bi1);
             bj0 = __reduce_min_sync(0xffffffffu, bj0); bj1 = __reduce_max_sync(0xffffffffu, bj1);
-            if (lane == 31) {
-                sNPieces = (int)((ic >> 12) & 0x3ffu);
-                sNRows = (int)(ic >> 22);
-                const unsigned rows = ic >> 22;
-                rndStart[rows ? (rows + SFS_MAXP - 1) / SFS_MAXP : 1] = (unsigned short)((ic >> 12) & 0x3ffu); // end of the last round
-                if (!rows) rndStart[0] = 0;
-                sBox[0] = bi0; sBox[1] = bi1; sBox[2] = bj0; sBox[3] = bj1;
+            if (lane == 0 && bi1 >= 0) {
+                atomicMin(&sBox[sb * 4 + 0], bi0); atomicMax(&sBox[sb * 4 + 1], bi1);
+                atomicMin(&sBox[sb * 4 + 2], bj0); atomicMax(&sBox[sb * 4 + 3], bj1);
             }
-        } else if (tiled) {
+        }
+        if (tiled) {
             const int c = SFS_THREADS - 1 - tid;
             if (c < SFS_NCELL) {
                 const unsigned no = cntO[c], nn = cntN[c];
@@ -433,6 +467,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
             const unsigned pn = pkN[o];
             if (pn != 0xffffffffu) perm[offN[pn >> 16] + (pn & 0xffffu)] = (unsigned short)(lead + o);
         }
+        if (tid < 4) sBox[(sb ^ 1) * 4 + tid] = (tid & 1) ? -1 : SFS_RC; // the next chunk's bounding box starts empty
         { // the other counter set is free (its chunk finished phase 4 before B1): clear it for the next chunk
             unsigned *nextc = cnt + ((it + 1) & 1) * 2 * SFS_NCELL;
             for (int k = tid; k < 2 * SFS_NCELL; k += SFS_THREADS) nextc[k] = 0;
@@ -463,6 +498,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
             const int pbeg = rndStart[rnd], pend = rndStart[rnd + 1];
             if (rnd > 0) { // (round 0 was prepared before B3)
                 __syncthreads(); // S is reused
+                if (tid == 0) sNextPiece = 0;
                 sfs_zero_shared_rows(S, pcOrd, pbeg, pend, tid);
                 __syncthreads();
             }
@@ -471,7 +507,15 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 const int half = lane >> 4, s4 = (lane >> 2) & 3, g = lane & 3;
                 const double *Dv = (g == 0) ? (aux + 2 * SFS_ROW) : (st + (2 + g) * SFS_ROW); // g = 0: mpw*|vel|; g = 1..3: u, v, w
                 const bool h0 = (lane & 4) != 0, h1 = (lane & 8) != 0;
+#if SFS_DYNAMIC
+                for (;;) { // warps draw pairs of pieces from a shared counter (runs differ in length)
+                    int pp = 0;
+                    if (lane == 0) pp = atomicAdd(&sNextPiece, 2);
+                    pp = pbeg + __shfl_sync(0xffffffffu, pp, 0);
+                    if (pp >= pend) break;
+#else
                 for (int pp = pbeg + 2 * wid; pp < pend; pp += 2 * SFS_WARPS) {
+#endif
                     const int pid = pp + half;
                     const bool have = pid < pend;
                     const int start = have ? pcStart[pid] : 0, end = have ? start + pcLen[pid] : 0;
@@ -518,7 +562,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
             // half a warp per field and half of the cell rows of the bounding box: a lane owns a node column, walks the cell rows
             // and hands the lower node row of each cell row to the next one in a register
             {
-                const int bi0 = sBox[0], bi1 = sBox[1], bj0 = sBox[2], bj1 = sBox[3];
+                const int bi0 = sBox[sb * 4 + 0], bi1 = sBox[sb * 4 + 1], bj0 = sBox[sb * 4 + 2], bj1 = sBox[sb * 4 + 3];
                 const int unit = 2 * wid + (lane >> 4), hl = lane & 15;
                 const int f = unit & 7, part = unit >> 3;
                 const int nrow = bi1 - bi0 + 1, mid = bi0 + (nrow + 1) / 2;
