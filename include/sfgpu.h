@@ -73,8 +73,9 @@ extern "C" {
                                   and deposits straight from / to global memory (FP64 REDs)         */
 #define SFGPU_STEP_DEFER_FINISH 2u /* do not close the step: the host still has slow-path survivors to
                                       re-inject (SFGPU_INJECT_DEPOSIT_NOW); it calls sfgpu_finish_step */
-#define SFGPU_STEP_INPLACE 4u  /* A/B comparison: the in-place tiled step kernel with a periodic cell sort
-                                  instead of the default streaming step that re-sorts as it writes        */
+#define SFGPU_STEP_INPLACE 4u  /* force the in-place tiled step kernel + periodic cell sort (sf_fast.cuh)            */
+#define SFGPU_STEP_STREAM 8u   /* force the streaming step kernel that re-sorts the store as it writes (sf_stream.cuh).
+                                  Without either flag the context default applies (env SFGPU_PATH=tiled|stream).    */
 
 /* index of each raw per-step deposit field inside the packed device buffer / sfgpu_get_deposit */
 #define SFGPU_F_DEN 0 /* += mpw            KM:184, KM:1590 */

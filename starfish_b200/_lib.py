@@ -16,7 +16,7 @@ NFIELDS = 8
 FIELD_NAMES = ("den", "u", "v", "w", "uu", "vv", "ww", "mpc")
 
 INJECT_REWIND, INJECT_DEPOSIT_NOW, INJECT_TRANSFER = 1, 2, 4
-STEP_GENERIC, STEP_DEFER_FINISH, STEP_INPLACE = 1, 2, 4
+STEP_GENERIC, STEP_DEFER_FINISH, STEP_INPLACE, STEP_STREAM = 1, 2, 4, 8
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

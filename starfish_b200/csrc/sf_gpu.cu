@@ -185,7 +185,7 @@ struct sfgpu_ctx {
     bool timing_valid = false;
     int sort_every = 4;      // steps between cell sorts of the fast store
     int fast_grid = 0;       // CTAs of the tiled kernel (persistent)
-    int path = 1;            // 1: streaming step (sf_stream.cuh), 0: tiled in-place step + periodic sort (sf_fast.cuh)
+    int path = 0;            // default step kernel: 0 = tiled in-place step + periodic sort (sf_fast.cuh), 1 = streaming step (sf_stream.cuh)
     int stream_grid = 0;     // CTAs of the streaming kernel (persistent)
     bool stream_check = false; // debug: verify the output cursors after every streaming launch
     unsigned long long *d_bad = nullptr;
@@ -495,7 +495,7 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         if (per_sm_s < 1) return fail(ctx, SFGPU_ECUDA, "k_stream_step does not fit on this device");
         ctx->stream_grid = nsm * per_sm_s;
         if (const char *e = getenv("SFGPU_STREAM_GRID")) ctx->stream_grid = atoi(e) > 0 ? atoi(e) : ctx->stream_grid;
-        if (const char *e = getenv("SFGPU_PATH")) ctx->path = strcmp(e, "tiled") == 0 ? 0 : 1;
+        if (const char *e = getenv("SFGPU_PATH")) ctx->path = strcmp(e, "stream") == 0 ? 1 : 0;
         ctx->stream_check = getenv("SFGPU_STREAM_CHECK") != nullptr;
         CU(cudaMalloc(&ctx->d_bad, sizeof(unsigned long long)));
         if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_stream_step %d CTAs/SM x %d threads, %d B dynamic smem per CTA, grid %d, path %s\n", per_sm_s, SFS_THREADS, (int)SFS_SMEM_BYTES, ctx->stream_grid, ctx->path ? "stream" : "tiled");
@@ -991,7 +991,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         rc = push_xfer_table(ctx, s);
         if (rc) return rc;
     }
-    const bool stream = ctx->path == 1 && !untiled && !(flags & SFGPU_STEP_INPLACE);
+    const bool stream = !untiled && !(flags & SFGPU_STEP_INPLACE) && (ctx->path == 1 || (flags & SFGPU_STEP_STREAM));
     // K3: cell sort + compaction of the fast store.  Streaming path: the step kernel itself re-sorts, a separate sort only
     // (re-)establishes the invariant (first step, after in-place edits).  Tiled path: periodic sort.
     for (int m = 0; m < nmesh; m++) {

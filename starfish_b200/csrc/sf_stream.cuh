@@ -21,7 +21,7 @@
 #include "sf_fast.cuh"
 
 #ifndef SFS_CHUNK
-#define SFS_CHUNK 512   // particles per chunk
+#define SFS_CHUNK 1024  // particles per chunk (measured: 512 x 2 CTAs/SM is 6 % slower -- more runs and per-chunk overhead per particle)
 #endif
 #ifndef SFS_PPT
 #define SFS_PPT 2       // particles per thread in phase 1
@@ -29,7 +29,7 @@
 #define SFS_THREADS (SFS_CHUNK / SFS_PPT)
 #define SFS_WARPS (SFS_THREADS / 32)
 #ifndef SFS_MIN_CTAS
-#define SFS_MIN_CTAS 2
+#define SFS_MIN_CTAS 1
 #endif
 #define SFS_RC (SF_TILE + 2 * SF_HALO)  // region cells per edge
 #define SFS_NCELL (SFS_RC * SFS_RC)
@@ -40,6 +40,10 @@
 #define SFS_NPIECE_MAX (SFS_NCELL + SFS_CHUNK / SFS_PIECE + 2)
 #define SFS_ROW (SFS_CHUNK + 2)         // stage row (doubles): an aligned superset of the chunk
 #define SFS_NSTAGE 2
+#ifndef SFS_P1_UNROLL
+#define SFS_P1_UNROLL 1 // particles of a thread are pushed one after the other (interleaving them doubles the live registers)
+#endif
+constexpr int sfs_p1_unroll = SFS_P1_UNROLL;
 #ifndef SFS_DYNAMIC
 #define SFS_DYNAMIC 0   // 1: warps draw pieces from a shared counter instead of a fixed round robin (no gain measured)
 #endif
@@ -247,7 +251,8 @@ __device__ __forceinline__ void sfs_zero_shared_rows(double *S, const unsigned s
     }
 }
 
-static_assert(SFS_WARPS == 8, "phase 4 deals 7 fields x 2 row halves to 16 half warps");
+#define SFS_P4_PARTS (SFS_WARPS / 4) // phase 4 deals 7 fields x SFS_P4_PARTS row ranges to the half warps
+static_assert(SFS_WARPS % 4 == 0, "phase 4 deals 7 fields x row ranges to the half warps");
 // shared memory of one CTA (dynamic), in doubles unless noted
 #define SFS_OFF_AUX (SFS_NSTAGE * SFS_STAGE_DOUBLES)            // [3][SFS_ROW]: corrected di, dj, mpw*|vel| of the pushed particle
 #define SFS_OFF_S (SFS_OFF_AUX + 3 * SFS_ROW)                   // [SFS_MAXP][SFS_SROW]: totals per non-empty new cell
@@ -327,7 +332,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
         sfs_mbar_wait(&sBar[sb], (it >> 1) & 1u);
 
         // ================= phase 1: push; the new state is parked in the particle's own stage slot =================
-#pragma unroll 1
+#pragma unroll sfs_p1_unroll
         for (int o = tid; o < SFS_CHUNK; o += SFS_THREADS) {
             if (o >= cur.count) { flO[o] = -2; pkN[o] = 0xffffffffu; continue; }
             const int s = lead + o;
@@ -565,8 +570,8 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 const int bi0 = sBox[sb * 4 + 0], bi1 = sBox[sb * 4 + 1], bj0 = sBox[sb * 4 + 2], bj1 = sBox[sb * 4 + 3];
                 const int unit = 2 * wid + (lane >> 4), hl = lane & 15;
                 const int f = unit & 7, part = unit >> 3;
-                const int nrow = bi1 - bi0 + 1, mid = bi0 + (nrow + 1) / 2;
-                const int ra = part == 0 ? bi0 : mid, rb = part == 0 ? mid : bi1 + 1; // cell rows [ra, rb)
+                const int nrow = bi1 - bi0 + 1;
+                const int ra = bi0 + (nrow * part) / SFS_P4_PARTS, rb = bi0 + (nrow * (part + 1)) / SFS_P4_PARTS; // cell rows [ra, rb)
                 const int nb = bj0 + hl; // node column; also the column of the cell whose node 00 / 10 it is
                 const bool cell_ok = nb <= bj1, node_ok = nb <= bj1 + 1;
                 const int col = (f >= 4 ? 4 : 0) + (f == 0 ? 0 : (f <= 3 ? f : f - 3));

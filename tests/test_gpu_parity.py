@@ -14,7 +14,7 @@ from starfish_b200.domain import DomainBoundaryType as BC, DomainType, Face, Uni
 
 pytestmark = pytest.mark.gpu
 
-PATHS = [pytest.param(_lib.STEP_GENERIC, id="generic"), pytest.param(_lib.STEP_INPLACE, id="tiled"), pytest.param(0, id="stream")]
+PATHS = [pytest.param(_lib.STEP_GENERIC, id="generic"), pytest.param(_lib.STEP_INPLACE, id="tiled"), pytest.param(_lib.STEP_STREAM, id="stream")]
 
 
 def to_particles(arr):
@@ -146,6 +146,26 @@ def test_mesh_handoff(flags):
 
 
 @pytest.mark.parametrize("flags", PATHS)
+def test_multi_domain_example_layout(flags):
+    """BASELINE config 4: the four-mesh RZ layout of dat/examples/multi-domain (different spacings, MESH faces found by
+    Mesh.setMeshNeighbors, LEFT symmetry, Ar+): particles loaded in every mesh wander across the hand-off faces and out."""
+    meshes, charge, mass, dt = S.config_multi_domain()
+    assert sum(int((np.asarray(mm.bc[int(f)]) == int(BC.MESH)).any()) for mm in meshes for f in Face) >= 5  # the layout is connected
+    arrays, oks = [], None
+    for k, mm in enumerate(meshes):
+        wl = S.Workload("t%d" % k, mm, dt, charge, mass, 100 + k, vth_cells=0.35, drift_cells=(0.1, 0.25), kick_frac=0.0)
+        arrays.append(wl.particles(0, 3000))
+    km, ok = make_pair(meshes, wl, arrays, flags)
+    with km:
+        for _ in range(40):
+            km.updateFields()
+            ok.updateFields(dt)
+        compare_state(km, ok)
+        compare_fields(km, ok)
+        assert ok.n_exited > 0 and all(ok.getNp(k) > 0 for k in range(len(meshes)))
+
+
+@pytest.mark.parametrize("flags", PATHS)
 def test_slow_path_classification(flags):
     """Particles whose substep bounding box touches a segment node are handed to the host untouched (KM:504-518)."""
     m = S.make_mesh(40, 40, DomainType.XY, 1e-3, "open")
@@ -271,12 +291,16 @@ def test_explicit_lc_injection_goes_through_records(flags):
             compare_fields(km, ok)
 
 
+BOTH = [pytest.param(0, id="default"), pytest.param(_lib.STEP_STREAM, id="stream")]
+
+
+@pytest.mark.parametrize("flags", BOTH)
 @pytest.mark.parametrize("every", [1, 3, 100])
-def test_sort_interval_does_not_change_results(every):
+def test_sort_interval_does_not_change_results(every, flags):
     m = S.make_mesh(70, 50, DomainType.XY, 1e-3, "periodic")
     wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 4, vth_cells=0.9, kick_frac=0.1)
     arr = wl.particles(0, 30000)
-    km, ok = make_pair([m], wl, [arr], 0)
+    km, ok = make_pair([m], wl, [arr], flags)
     with km:
         km.setSortInterval(every)
         for _ in range(7):
@@ -286,14 +310,15 @@ def test_sort_interval_does_not_change_results(every):
         compare_fields(km, ok)
 
 
-def test_restart_records_round_trip():
+@pytest.mark.parametrize("flags", BOTH)
+def test_restart_records_round_trip(flags):
     """restart.bin particle section (KM:904-1000): the saved bytes are the DataOutputStream layout (checked with Python's
     big-endian struct), and loading them goes through addParticle like the reference (rewind re-applied, ids renumbered)."""
     import struct
     m = S.make_mesh(6, 5, DomainType.XY, 1e-3, "symmetry")
     wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 55, vth_cells=25.0, kick_frac=0.05)  # >10 bounces: records with residual dt
     arr = wl.particles(0, 5000)
-    km, ok = make_pair([m], wl, [arr], 0)
+    km, ok = make_pair([m], wl, [arr], flags)
     with km:
         for _ in range(3):
             km.updateFields()
@@ -308,7 +333,7 @@ def test_restart_records_round_trip():
         assert np.all(rec["d"][:, 10] == wl.mass) and np.array_equal(rec["id"], p.id) and np.array_equal(rec["born"], p.born_it)
         assert (p.dt > 0).any() or (p.li != (p.x - m.x0[0]) / m.dh[0]).any(), "case should include exceptional records"
         # load into a fresh material and into a fresh oracle through addParticle(md, part)
-        km2, ok2 = make_pair([m], wl, [None], 0)
+        km2, ok2 = make_pair([m], wl, [None], flags)
         with km2:
             used, added = km2.loadRestartParticles(m, data + b"FIELDS...", wl.dt)
             assert used == len(data)
@@ -321,25 +346,33 @@ def test_restart_records_round_trip():
             compare_fields(km2, ok2)
 
 
-def test_download_upload_round_trip():
+@pytest.mark.parametrize("flags", BOTH)
+def test_download_upload_round_trip(flags):
+    """The particle-store view of MCC / DSMC / output: download, mutate on the host, upload, keep stepping."""
     m = S.make_mesh(16, 16, DomainType.XY, 1e-3, "periodic")
     wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 1)
     arr = wl.particles(0, 1000)
-    km, ok = make_pair([m], wl, [arr], 0)
+    km, ok = make_pair([m], wl, [arr], flags)
     with km:
+        km.updateFields()
+        ok.updateFields(wl.dt)
         p = km.getParticles(m)
         p.u[:] *= 2.0
         km.setParticles(m, p)
         q = km.getParticles(m)
         assert np.array_equal(p.u, q.u) and np.array_equal(p.id, q.id)
+        km.updateFields()  # the in-place edit invalidated the cell histogram: the streaming step must re-establish it
+        assert km.getNp() == 1000
+        assert km.last_deposit[0][7].sum() == 1000
 
 
+@pytest.mark.parametrize("flags", BOTH)
 @pytest.mark.parametrize("n", [1 << 24])
-def test_full_size_properties_config_b(n):
+def test_full_size_properties_config_b(n, flags):
     """BASELINE config B at full size (512x512, 16M): size-independent properties instead of the oracle."""
     wl = S.config_b()
     m = wl.mesh
-    km = KineticMaterial("O+", wl.charge, wl.mass, [m], DomainType.XY, capacity_hint=n)
+    km = KineticMaterial("O+", wl.charge, wl.mass, [m], DomainType.XY, capacity_hint=n, step_flags=flags)
     km.dt = wl.dt
     with km:
         chunk = 1 << 22
