@@ -165,36 +165,36 @@ __device__ __forceinline__ void sfs_deposit_global(const MeshDev &m, const PStat
 // through registers or a local struct: a call that keeps ten doubles alive costs the hot loop ~55 registers.
 // Returns 3 when the particle stays a normal particle of the fast store (new state parked in the slot), else 0 (it left for a
 // record list / died; if it still deposits in this step, that has been done here through the global path).
-__device__ __noinline__ int stream_general(const FastStepArgs *__restrict__ ga, double *st, int s, double *sums)
+__device__ __noinline__ int stream_general(const FastStepArgs *__restrict__ ga, double *st, int row, int s, double *sums)
 {
     const FastStepArgs &a = *ga;
     MoveAux aux;
     bool exact = true;
     const GlobalFieldGather fg;
     PState p;
-    p.x = st[0 * SFS_ROW + s]; p.y = st[1 * SFS_ROW + s]; p.z = st[2 * SFS_ROW + s];
-    p.u = st[3 * SFS_ROW + s]; p.v = st[4 * SFS_ROW + s]; p.w = st[5 * SFS_ROW + s];
-    p.mpw = st[6 * SFS_ROW + s];
+    p.x = st[0 * row + s]; p.y = st[1 * row + s]; p.z = st[2 * row + s];
+    p.u = st[3 * row + s]; p.v = st[4 * row + s]; p.w = st[5 * row + s];
+    p.mpw = st[6 * row + s];
     p.li = (p.x - a.m.x0) / a.m.dhx; // the stored lc of a normal particle is exactly XtoL(pos)
     p.lj = (p.y - a.m.y0) / a.m.dhy;
     p.dt = 0;
     const int st_ = sf_move(a.m, a.meshes, a.qm, a.charge, a.dt, false, p, aux, exact, fg);
-    st[0 * SFS_ROW + s] = p.x; st[1 * SFS_ROW + s] = p.y; st[2 * SFS_ROW + s] = p.z;
-    st[3 * SFS_ROW + s] = p.u; st[4 * SFS_ROW + s] = p.v; st[5 * SFS_ROW + s] = p.w;
+    st[0 * row + s] = p.x; st[1 * row + s] = p.y; st[2 * row + s] = p.z;
+    st[3 * row + s] = p.u; st[4 * row + s] = p.v; st[5 * row + s] = p.w;
     if (st_ == SF_ALIVE && exact && p.dt == 0) return 3;
-    fast_leave(a, st_, p, aux, reinterpret_cast<const int2 *>(st + 7 * SFS_ROW)[s]);
+    fast_leave(a, st_, p, aux, reinterpret_cast<const int2 *>(st + 7 * row)[s]);
     if (st_ == SF_ALIVE) sfs_deposit_global(a.m, p, a.dep, sums); // stale lc / residual dt: it deposits where its lc says
     return 0;
 }
 
 // global-path deposit of a normal particle whose new cell the shared-memory path does not cover; counts it for the next launch
-__device__ __noinline__ void stream_fallback(const FastStepArgs *__restrict__ ga, const double *st, int s, double *sums, unsigned *hist_next)
+__device__ __noinline__ void stream_fallback(const FastStepArgs *__restrict__ ga, const double *st, int row, int s, double *sums, unsigned *hist_next)
 {
     const MeshDev &m = ga->m;
     PState p;
-    p.x = st[0 * SFS_ROW + s]; p.y = st[1 * SFS_ROW + s]; p.z = st[2 * SFS_ROW + s];
-    p.u = st[3 * SFS_ROW + s]; p.v = st[4 * SFS_ROW + s]; p.w = st[5 * SFS_ROW + s];
-    p.mpw = st[6 * SFS_ROW + s];
+    p.x = st[0 * row + s]; p.y = st[1 * row + s]; p.z = st[2 * row + s];
+    p.u = st[3 * row + s]; p.v = st[4 * row + s]; p.w = st[5 * row + s];
+    p.mpw = st[6 * row + s];
     p.li = (p.x - m.x0) / m.dhx;
     p.lj = (p.y - m.y0) / m.dhy;
     p.dt = 0;
@@ -361,7 +361,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 st[0 * SFS_ROW + s] = p.x; st[1 * SFS_ROW + s] = p.y; st[2 * SFS_ROW + s] = p.z;
                 st[3 * SFS_ROW + s] = p.u; st[4 * SFS_ROW + s] = p.v; st[5 * SFS_ROW + s] = p.w;
             } else {
-                fl = stream_general(ga, st, s, sSums);
+                fl = stream_general(ga, st, SFS_ROW, s, sSums);
                 if (fl == 3) { // back to the common path: a normal particle again, lc = XtoL(pos)
                     p.x = st[0 * SFS_ROW + s]; p.y = st[1 * SFS_ROW + s];
                     p.u = st[3 * SFS_ROW + s]; p.v = st[4 * SFS_ROW + s]; p.w = st[5 * SFS_ROW + s];
@@ -385,7 +385,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                     aux[1 * SFS_ROW + s] = dj;
                     aux[2 * SFS_ROW + s] = p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w); // KM:412
                 } else {
-                    stream_fallback(ga, st, s, sSums, a.hist_next);
+                    stream_fallback(ga, st, SFS_ROW, s, sSums, a.hist_next);
                     atomicAdd(&sNFall, 1);
                 }
             }
@@ -615,13 +615,13 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
 
 // chunks of the streaming kernel: each tile's run [offs[tile*64], offs[(tile+1)*64]) cut into <= SFS_CHUNK particles
 __global__ void k_build_chunks(const unsigned *__restrict__ offs, int n_tiles, WorkItem *__restrict__ items, unsigned *__restrict__ n_items,
-                               unsigned max_items)
+                               unsigned max_items, unsigned chunk)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     const unsigned b = offs[(size_t)t * SF_TILE * SF_TILE], e = offs[(size_t)(t + 1) * SF_TILE * SF_TILE];
     if (e <= b) return;
-    const unsigned cnt = e - b, pieces = (cnt + SFS_CHUNK - 1) / SFS_CHUNK;
+    const unsigned cnt = e - b, pieces = (cnt + chunk - 1) / chunk;
     const unsigned per = (cnt + pieces - 1) / pieces;
     const unsigned s = atomicAdd(n_items, pieces);
     for (unsigned k = 0; k < pieces && s + k < max_items; k++) {
@@ -635,15 +635,16 @@ __global__ void k_build_chunks(const unsigned *__restrict__ offs, int n_tiles, W
 }
 
 // chunks of the unsorted tail (tile = -1: no region, everything through global atomics)
-__global__ void k_build_tail(unsigned long long first, unsigned long long n, WorkItem *__restrict__ items, unsigned *__restrict__ n_items, unsigned max_items)
+__global__ void k_build_tail(unsigned long long first, unsigned long long n, WorkItem *__restrict__ items, unsigned *__restrict__ n_items, unsigned max_items,
+                             unsigned chunk)
 {
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k * SFS_CHUNK >= n) return;
+    if (k * chunk >= n) return;
     const unsigned s = atomicAdd(n_items, 1u);
     if (s >= max_items) return;
     WorkItem w;
-    w.begin = first + k * SFS_CHUNK;
-    w.count = (int)((n - k * SFS_CHUNK) < SFS_CHUNK ? (n - k * SFS_CHUNK) : SFS_CHUNK);
+    w.begin = first + k * chunk;
+    w.count = (int)((n - k * chunk) < chunk ? (n - k * chunk) : chunk);
     w.tile = -1;
     items[s] = w;
 }
