@@ -210,6 +210,10 @@ int sfgpu_deposit_device_ptr(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, void *
  * whole step (memsets, kernels, collective), ms_kernel only the fused move+deposit kernel(s) of the main
  * pass; launches = kernels launched by the step.  Any pointer nullable. */
 int sfgpu_last_step_timing(sfgpu_ctx *ctx, float *ms_total, float *ms_kernel, int32_t *launches);
+/* which step kernel ran in the last sfgpu_step: 0 = tiled in-place kernel, 1 = streaming kernel (moves, deposits and re-sorts),
+ * 2 = generic.  The default path alternates: three tiled steps, then one streaming step where the reference's
+ * sortParticlesToCells-style re-ordering (KM:1150-1179) is due. */
+int sfgpu_last_step_kernel(sfgpu_ctx *ctx, int32_t *kind);
 /* diagnostics of the last step: particles whose deposit missed the warp tile of their sort position and went
  * through global atomics instead (grows between cell sorts; the step re-sorts early when it passes 1/64) */
 int sfgpu_last_step_counters(sfgpu_ctx *ctx, int64_t *n_fallback);

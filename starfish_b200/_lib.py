@@ -67,6 +67,7 @@ EXPORTS = {
     "sfgpu_deposit_device_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),
     "sfgpu_last_step_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), c_int32_p]),
     "sfgpu_last_step_counters": (C.c_int, [C.c_void_p, c_int64_p]),
+    "sfgpu_last_step_kernel": (C.c_int, [C.c_void_p, c_int32_p]),
     "sfgpu_sync": (C.c_int, [C.c_void_p]),
     "sfgpu_timer_start": (C.c_int, [C.c_void_p]),
     "sfgpu_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

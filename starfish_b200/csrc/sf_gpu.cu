@@ -189,6 +189,10 @@ struct sfgpu_ctx {
     int path = 0;            // default step kernel: 0 = tiled in-place step + periodic sort (sf_fast.cuh), 1 = streaming step (sf_stream.cuh)
     int stream_grid = 0;     // CTAs of the streaming kernel (persistent)
     int ws_grid = 0;         // CTAs of the warp-specialised streaming kernel (one per SM)
+    bool hybrid = false;     // tiled path: run the step in which a re-sort is due with the streaming kernel instead of sorting separately
+    unsigned *h_cnt2 = nullptr; // pinned: per-mesh work-item counts read back with the step counters
+    int last_kernel = 0;     // step kernel of the last sfgpu_step: 0 tiled, 1 streaming, 2 generic
+    bool stream_sort = true; // periodic re-sort of the tiled path: streaming pass (k_stream_sort) instead of the generic counting sort
     bool stream_ws = true;   // which streaming kernel runs: warp-specialised (sf_stream_ws.cuh) or uniform (sf_stream.cuh)
     bool stream_check = false; // debug: verify the output cursors after every streaming launch
     unsigned long long *d_bad = nullptr;
@@ -376,6 +380,84 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     return 0;
 }
 
+// live particles per cell key of a store whose slots were edited in place (tiled steps, uploads): the layout (offs, n_sorted)
+// stands, only the histogram the streaming step lays its output out by is rebuilt
+static int fast_rehist(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
+{
+    CU(cudaMemsetAsync(f.hist, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
+    if (f.n > 0) {
+        k_stream_hist<<<(unsigned)((f.n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, 0ULL, (unsigned long long)f.n, f.ntj, f.hist);
+        CU(cudaGetLastError());
+        ctx->launch_total++;
+        ctx->last_launches++;
+    }
+    f.stream_ok = true;
+    return 0;
+}
+
+static int fast_reserve_alt(sfgpu_ctx *ctx, FastStore &f);
+
+// K3 for a store that is still roughly in cell order: histogram of the current cells, exclusive scan, one streaming pass
+// (k_stream_sort) that writes every particle into its cell's segment of the second slab.  Falls back to the generic counting
+// sort for a store that was never sorted or whose unsorted tail is large.
+static int fast_resort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
+{
+    if (!ctx->stream_sort || f.n == 0 || f.n_sorted == 0 || (f.n - f.n_sorted) * 16 > f.n) return fast_sort(ctx, mesh_id, f);
+    if ((uint64_t)f.n >= 0xfffffff0ull) return fail(ctx, SFGPU_EINVAL, "more than 2^32 particles of one species on one GPU mesh are not supported");
+    int rc = fast_rehist(ctx, mesh_id, f);
+    if (rc) return rc;
+    rc = fast_reserve_alt(ctx, f);
+    if (rc) return rc;
+    const unsigned want_items = (unsigned)(f.n / SFR_CHUNK + (int64_t)f.nti * f.ntj + 16);
+    if (f.max_items < want_items) {
+        if (f.items) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(f.items)); }
+        f.items = nullptr; f.max_items = 0;
+        CU(cudaMalloc(&f.items, (size_t)want_items * sizeof(WorkItem)));
+        f.max_items = want_items;
+    }
+    const int n_tiles = f.nti * f.ntj;
+    CU(cub::DeviceScan::ExclusiveSum(f.cub_tmp, f.cub_bytes, f.hist, f.offs_out, (int)(f.nkeys + 1), ctx->stream));
+    CU(cudaMemcpyAsync(f.cursor, f.offs_out, (size_t)f.nkeys * sizeof(unsigned), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
+    CU(cudaMemsetAsync(f.items, 0, (size_t)f.max_items * sizeof(WorkItem), ctx->stream));
+    k_build_chunks<<<(n_tiles + 127) / 128, 128, 0, ctx->stream>>>(f.offs, n_tiles, f.items, f.d_nitems, f.max_items, SFR_CHUNK);
+    CU(cudaGetLastError());
+    if (f.n > f.n_sorted) {
+        const int64_t n_tail = (f.n - f.n_sorted + SFR_CHUNK - 1) / SFR_CHUNK;
+        k_build_tail<<<(unsigned)((n_tail + 127) / 128), 128, 0, ctx->stream>>>((unsigned long long)f.n_sorted, (unsigned long long)(f.n - f.n_sorted), f.items, f.d_nitems, f.max_items, SFR_CHUNK);
+        CU(cudaGetLastError());
+    }
+    k_stream_sort<<<want_items, SFR_THREADS, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, f.alt, f.items, f.max_items, f.cursor, f.ntj);
+    CU(cudaGetLastError());
+    if (ctx->stream_check) {
+        CU(cudaMemsetAsync(ctx->d_bad, 0, sizeof(unsigned long long), ctx->stream));
+        k_stream_check<<<(f.nkeys + 255) / 256, 256, 0, ctx->stream>>>(f.offs_out, f.cursor, f.nkeys, ctx->d_bad);
+        unsigned long long bad = 0;
+        CU(cudaMemcpyAsync(&bad, ctx->d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (bad) return fail(ctx, SFGPU_ESTATE, "internal: %llu cell segments of the streaming sort were not filled exactly", bad);
+    }
+    // work items of the tiled kernel for the new layout
+    CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
+    k_build_items<<<(n_tiles + 127) / 128, 128, 0, ctx->stream>>>(f.offs_out, n_tiles, f.items, f.d_nitems, f.max_items);
+    CU(cudaGetLastError());
+    ctx->launch_total += 6; // hist (counted there), scan, chunks, tail, sort, items
+    ctx->last_launches += 5;
+    unsigned n_items = 0;
+    CU(cudaMemcpyAsync(&n_items, f.d_nitems, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::swap(f.p, f.alt);
+    std::swap(f.slab, f.alt_slab);
+    std::swap(f.cap, f.alt_cap);
+    std::swap(f.offs, f.offs_out);
+    f.n = f.n_sorted = f.alive;
+    f.n_items = n_items < f.max_items ? n_items : f.max_items;
+    f.dirty = false;
+    f.steps_since_sort = 0;
+    f.stream_ok = true;
+    return 0;
+}
+
 // second slab of the fast store: sort target / output of the streaming step
 static int fast_reserve_alt(sfgpu_ctx *ctx, FastStore &f)
 {
@@ -482,6 +564,9 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaMalloc(&ctx->d_cnt, sizeof(StepCounters)));
         CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
         CU(cudaMallocHost(&ctx->h_cnt, sizeof(StepCounters)));
+        CU(cudaMallocHost(&ctx->h_cnt2, sizeof(unsigned) * SF_MAX_MESHES));
+        if (const char *e = getenv("SFGPU_HYBRID")) ctx->hybrid = atoi(e) != 0;
+        if (const char *e = getenv("SFGPU_STREAM_SORT")) ctx->stream_sort = atoi(e) != 0;
         CU(cudaMalloc(&ctx->d_xfer, sizeof(XferDev) * SF_MAX_MESHES));
         CU(cudaMalloc(&ctx->d_args, sizeof(FastStepArgs) * SF_MAX_MESHES));
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
@@ -564,6 +649,7 @@ extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
     if (ctx->d_xfer) cudaFree(ctx->d_xfer);
     if (ctx->d_args) cudaFree(ctx->d_args);
     if (ctx->d_bad) cudaFree(ctx->d_bad);
+    if (ctx->h_cnt2) cudaFreeHost(ctx->h_cnt2);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1000,15 +1086,27 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         rc = push_xfer_table(ctx, s);
         if (rc) return rc;
     }
-    const bool stream = !untiled && !(flags & SFGPU_STEP_INPLACE) && (ctx->path == 1 || (flags & SFGPU_STEP_STREAM));
-    // K3: cell sort + compaction of the fast store.  Streaming path: the step kernel itself re-sorts, a separate sort only
-    // (re-)establishes the invariant (first step, after in-place edits).  Tiled path: periodic sort.
+    bool stream = !untiled && !(flags & SFGPU_STEP_INPLACE) && (ctx->path == 1 || (flags & SFGPU_STEP_STREAM));
+    // K3: cell sort + compaction of the fast store.
+    //  * streaming step: the kernel re-sorts as it writes; a separate pass only (re-)establishes its invariant;
+    //  * tiled step: needs a re-sort every few steps.  When one is due, that step is run by the streaming kernel instead
+    //    (it moves, deposits AND leaves the store re-sorted), so the stand-alone sort only runs for a store that was never sorted.
+    if (!untiled && !stream && ctx->hybrid && !(flags & SFGPU_STEP_INPLACE)) {
+        bool due = false;
+        for (int m = 0; m < nmesh; m++) {
+            const FastStore &f = s.pops[m].fast;
+            if (f.n == 0 || f.n_sorted == 0 || (f.n - f.n_sorted) * 16 > f.n) continue; // (needs the real sort below)
+            if (f.steps_since_sort >= ctx->sort_every || ctx->force_sort) due = true;
+        }
+        stream = due;
+    }
     for (int m = 0; m < nmesh; m++) {
         FastStore &f = s.pops[m].fast;
         if (untiled) { f.stream_ok = false; continue; }
         if (stream) {
             if (!f.stream_ok) {
-                rc = fast_sort(ctx, m, f);
+                if (f.n > 0 && f.n_sorted > 0 && (f.n - f.n_sorted) * 16 <= f.n) rc = fast_rehist(ctx, m, f); // the layout stands, the cells moved
+                else rc = fast_sort(ctx, m, f);
                 if (rc) return rc;
             }
             continue;
@@ -1017,7 +1115,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         if (f.n == 0) continue;
         const int64_t tail = f.n - f.n_sorted;
         if (f.n_sorted == 0 || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n || ctx->force_sort) {
-            rc = fast_sort(ctx, m, f);
+            rc = fast_resort(ctx, m, f); // streaming re-sort when the store is still roughly ordered, counting sort otherwise
             if (rc) return rc;
             f.stream_ok = false;
         }
@@ -1106,6 +1204,14 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                 else k_stream_step<<<ctx->stream_grid, SFS_THREADS, SFS_SMEM_BYTES, ctx->stream>>>(sa, ctx->d_args + m);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
+                if (ctx->path == 0) { // the tiled kernel runs the next steps: its work items follow the new layout
+                    CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
+                    const int n_tiles = f.nti * f.ntj;
+                    k_build_items<<<(n_tiles + 127) / 128, 128, 0, ctx->stream>>>(f.offs_out, n_tiles, f.items, f.d_nitems, f.max_items);
+                    CU(cudaGetLastError());
+                    CU(cudaMemcpyAsync(&ctx->h_cnt2[m], f.d_nitems, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+                    { ctx->last_launches++; ctx->launch_total++; }
+                }
                 if (ctx->stream_check) {
                     CU(cudaMemsetAsync(ctx->d_bad, 0, sizeof(unsigned long long), ctx->stream));
                     k_stream_check<<<(f.nkeys + 255) / 256, 256, 0, ctx->stream>>>(f.offs_out, f.cursor, f.nkeys, ctx->d_bad);
@@ -1204,6 +1310,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             f.n = fn;
             f.n_sorted = n_sorted;
             f.stream_ok = true;
+            f.steps_since_sort = 1; // the output is ordered by the cell each particle had BEFORE this push
+            if (ctx->path == 0) f.n_items = ctx->h_cnt2[m] < f.max_items ? ctx->h_cnt2[m] : f.max_items;
         } else {
             if (fn > f.cap) fn = f.cap;
             if (fn < f.n) fn = f.n;
@@ -1219,6 +1327,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     ctx->last_fallback = ctx->h_cnt->n_fallback;
     // too many particles drifted out of their warp tiles: sort before the next step instead of waiting for the interval
     ctx->force_sort = !untiled && !stream && (int64_t)ctx->last_fallback * 64 > n_total;
+    ctx->last_kernel = untiled ? 2 : (stream ? 1 : 0);
     s.step_open = true;
     if (flags & SFGPU_STEP_DEFER_FINISH) return 0;
     return sfgpu_finish_step(ctx, sp);
@@ -1717,6 +1826,14 @@ extern "C" int sfgpu_last_step_timing(sfgpu_ctx *ctx, float *ms_total, float *ms
     if (ms_total) CU(cudaEventElapsedTime(ms_total, ctx->ev0, ctx->ev1));
     if (ms_kernel) CU(cudaEventElapsedTime(ms_kernel, ctx->evk0, ctx->evk1));
     if (launches) *launches = ctx->last_launches;
+    return 0;
+}
+
+extern "C" int sfgpu_last_step_kernel(sfgpu_ctx *ctx, int32_t *kind)
+{
+    CHECK_CTX();
+    if (!kind) return fail(ctx, SFGPU_EINVAL, "kind is null");
+    *kind = ctx->last_kernel;
     return 0;
 }
 

@@ -649,6 +649,74 @@ __global__ void k_build_tail(unsigned long long first, unsigned long long n, Wor
     items[s] = w;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K3 as a streaming pass: re-sort of a store that is still ROUGHLY in cell order (it was sorted a few steps ago).  One chunk
+// of one tile per CTA; a particle's destination = segment of its current cell (exclusive scan of the histogram) + this chunk's
+// share of the segment (one global atomic per touched cell and chunk) + its rank among the chunk's particles of that cell
+// (integer shared-memory atomic).  Reads are coalesced, writes leave in runs of same-cell particles: 128 B per particle at
+// close to copy speed, where the generic counting sort scatters single 8-byte elements.
+// ---------------------------------------------------------------------------------------------------------
+#define SFR_THREADS 256
+#define SFR_PPT 2
+#define SFR_CHUNK (SFR_THREADS * SFR_PPT)
+__global__ void __launch_bounds__(SFR_THREADS)
+k_stream_sort(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs in, FastPtrs out, const WorkItem *__restrict__ items, unsigned max_items,
+              unsigned *__restrict__ cursor, int ntj)
+{
+    __shared__ unsigned cntO[SFS_NCELL], baseO[SFS_NCELL];
+    if (blockIdx.x >= max_items) return;
+    const WorkItem it = items[blockIdx.x];
+    if (it.count == 0) return;
+    const MeshDev &m = meshes[mesh_id];
+    const int tid = threadIdx.x;
+    const bool tiled = it.tile >= 0;
+    const int ci0 = tiled ? (it.tile / ntj) * SF_TILE - SF_HALO : 0, cj0 = tiled ? (it.tile % ntj) * SF_TILE - SF_HALO : 0;
+    const double x0 = m.x0, y0 = m.y0, dhx = m.dhx, dhy = m.dhy;
+    const int ni = m.ni, nj = m.nj;
+    for (int k = tid; k < SFS_NCELL; k += SFR_THREADS) cntO[k] = 0;
+    __syncthreads();
+    double px[SFR_PPT], py[SFR_PPT], pz[SFR_PPT], pu[SFR_PPT], pv[SFR_PPT], pw[SFR_PPT], pm[SFR_PPT];
+    int2 ptag[SFR_PPT];
+    int lo[SFR_PPT];
+    unsigned ro[SFR_PPT];
+#pragma unroll
+    for (int j = 0; j < SFR_PPT; j++) {
+        const int o = j * SFR_THREADS + tid;
+        lo[j] = -2;
+        ro[j] = 0;
+        if (o >= it.count) continue;
+        const size_t q = (size_t)it.begin + o;
+        pm[j] = in.mpw[q];
+        if (pm[j] != pm[j]) continue; // vacant
+        px[j] = in.x[q]; py[j] = in.y[q]; pz[j] = in.z[q]; pu[j] = in.u[q]; pv[j] = in.v[q]; pw[j] = in.w[q];
+        ptag[j] = in.tag[q];
+        const int ci = min(max(sf_j2i((px[j] - x0) / dhx), 0), ni - 2), cj = min(max(sf_j2i((py[j] - y0) / dhy), 0), nj - 2);
+        const int ri = ci - ci0, rj = cj - cj0;
+        if (tiled && ri >= 0 && rj >= 0 && ri < SFS_RC && rj < SFS_RC) {
+            lo[j] = ri * SFS_RC + rj;
+            ro[j] = atomicAdd(&cntO[lo[j]], 1u);
+        } else {
+            lo[j] = -1;
+            ro[j] = atomicAdd(&cursor[sfs_gkey(ci, cj, ntj)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < SFS_NCELL; c += SFR_THREADS) {
+        const unsigned no = cntO[c];
+        if (no) baseO[c] = atomicAdd(&cursor[sfs_gkey(ci0 + c / SFS_RC, cj0 + c % SFS_RC, ntj)], no);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SFR_PPT; j++) {
+        if (lo[j] == -2) continue;
+        const size_t slot = lo[j] >= 0 ? (size_t)baseO[lo[j]] + ro[j] : (size_t)ro[j];
+        out.x[slot] = px[j]; out.y[slot] = py[j]; out.z[slot] = pz[j];
+        out.u[slot] = pu[j]; out.v[slot] = pv[j]; out.w[slot] = pw[j];
+        out.mpw[slot] = pm[j];
+        out.tag[slot] = ptag[j];
+    }
+}
+
 // per-key histogram of the live particles of a store (re-establishes the streaming invariant after in-place edits)
 __global__ void __launch_bounds__(256)
 k_stream_hist(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs fs, unsigned long long first, unsigned long long n, int ntj,

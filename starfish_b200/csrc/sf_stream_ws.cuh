@@ -20,6 +20,10 @@
 #define SFW_STAGE_DOUBLES (8 * SFW_ROW)
 #define SFW_NPIECE_MAX (SFS_NCELL + SFW_CHUNK / SFS_PIECE + 2)
 #define SFW_P4_PARTS (SFW_DWARPS / 4)
+#ifndef SFW_P1_UNROLL
+#define SFW_P1_UNROLL 1
+#endif
+constexpr int sfw_p1_unroll = SFW_P1_UNROLL;
 #ifndef SFW_PREGS
 #define SFW_PREGS 128
 #endif
@@ -130,7 +134,7 @@ k_stream_ws(const __grid_constant__ StreamArgs a, const FastStepArgs *__restrict
             const int ci0 = tiled ? (cur.tile / ntj) * SF_TILE - SF_HALO : 0;
             const int cj0 = tiled ? (cur.tile % ntj) * SF_TILE - SF_HALO : 0;
             sfs_mbar_wait(&sFull[j % 3], (j / 3) & 1u);
-#pragma unroll 1
+#pragma unroll sfw_p1_unroll
             for (int o = tid; o < SFW_CHUNK; o += SFW_PT) {
                 if (o >= cur.count) { flO[o] = -2; pkN[o] = 0xffffffffu; continue; }
                 const int s = lead + o;

@@ -381,6 +381,12 @@ class KineticMaterial:
         self._check(self.lib.sfgpu_last_step_timing(self._ctx, C.byref(tot), C.byref(ker), C.byref(n)))
         return tot.value, ker.value, n.value
 
+    def lastStepKernel(self):
+        """Which step kernel ran last: 0 tiled in-place, 1 streaming (moves, deposits and re-sorts), 2 generic."""
+        k = C.c_int32()
+        self._check(self.lib.sfgpu_last_step_kernel(self._ctx, C.byref(k)))
+        return k.value
+
     def sync(self):
         self._check(self.lib.sfgpu_sync(self._ctx))
 
