@@ -192,8 +192,8 @@ struct sfgpu_ctx {
     bool hybrid = false;     // tiled path: run the step in which a re-sort is due with the streaming kernel instead of sorting separately
     unsigned *h_cnt2 = nullptr; // pinned: per-mesh work-item counts read back with the step counters
     int last_kernel = 0;     // step kernel of the last sfgpu_step: 0 tiled, 1 streaming, 2 generic
-    bool stream_sort = true; // periodic re-sort of the tiled path: streaming pass (k_stream_sort) instead of the generic counting sort
-    bool stream_ws = true;   // which streaming kernel runs: warp-specialised (sf_stream_ws.cuh) or uniform (sf_stream.cuh)
+    bool stream_sort = false; // periodic re-sort of the tiled path: 1 = streaming pass (k_stream_sort), 0 = generic counting sort (equal speed measured)
+    bool stream_ws = false;  // which streaming kernel runs: warp-specialised (sf_stream_ws.cuh) or uniform (sf_stream.cuh)
     bool stream_check = false; // debug: verify the output cursors after every streaming launch
     unsigned long long *d_bad = nullptr;
     Records tmp;             // staging records for download / upload of the fast store

@@ -692,12 +692,21 @@ k_stream_sort(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs in, Fast
         ptag[j] = in.tag[q];
         const int ci = min(max(sf_j2i((px[j] - x0) / dhx), 0), ni - 2), cj = min(max(sf_j2i((py[j] - y0) / dhy), 0), nj - 2);
         const int ri = ci - ci0, rj = cj - cj0;
-        if (tiled && ri >= 0 && rj >= 0 && ri < SFS_RC && rj < SFS_RC) {
-            lo[j] = ri * SFS_RC + rj;
-            ro[j] = atomicAdd(&cntO[lo[j]], 1u);
-        } else {
+        if (tiled && ri >= 0 && rj >= 0 && ri < SFS_RC && rj < SFS_RC) lo[j] = ri * SFS_RC + rj;
+        else {
             lo[j] = -1;
             ro[j] = atomicAdd(&cursor[sfs_gkey(ci, cj, ntj)], 1u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SFR_PPT; j++) { // ranks inside the region cells: one shared-memory atomic per distinct cell of the warp
+        const unsigned act = __ballot_sync(0xffffffffu, lo[j] >= 0);
+        if (lo[j] >= 0) {
+            const unsigned grp = __match_any_sync(act, lo[j]);
+            const int leader = __ffs(grp) - 1, lane = tid & 31;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(&cntO[lo[j]], (unsigned)__popc(grp));
+            ro[j] = __shfl_sync(grp, base, leader) + __popc(grp & ((1u << lane) - 1u));
         }
     }
     __syncthreads();
@@ -724,11 +733,18 @@ k_stream_hist(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs fs, unsi
 {
     const MeshDev m = meshes[mesh_id];
     const unsigned long long q0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q0 >= n) return;
-    const size_t q = first + q0;
-    const double mpw = fs.mpw[q];
-    if (mpw != mpw) return;
-    atomicAdd(&hist[sf_cell_key(m, (fs.x[q] - m.x0) / m.dhx, (fs.y[q] - m.y0) / m.dhy, ntj)], 1u);
+    unsigned key = 0xffffffffu;
+    if (q0 < n) {
+        const size_t q = first + q0;
+        const double mpw = fs.mpw[q];
+        if (mpw == mpw) key = sf_cell_key(m, (fs.x[q] - m.x0) / m.dhx, (fs.y[q] - m.y0) / m.dhy, ntj);
+    }
+    // neighbours in a roughly sorted store share their cell: one atomic per distinct key of the warp
+    const unsigned act = __ballot_sync(0xffffffffu, key != 0xffffffffu);
+    if (key != 0xffffffffu) {
+        const unsigned grp = __match_any_sync(act, key);
+        if ((threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&hist[key], (unsigned)__popc(grp));
+    }
 }
 
 // debug: every cell's cursor must have reached the start of the next segment

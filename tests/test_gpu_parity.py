@@ -90,6 +90,42 @@ def test_move_and_deposit_match_oracle(dom, bc, flags):
         assert km.num_samples == 0 and not km.fields[0]["count-sum"].any() and not km.fields[0]["mpc-sum"].any()
 
 
+@pytest.mark.parametrize("knob", ["SFGPU_STREAM_SORT", "SFGPU_HYBRID"])
+def test_streaming_resort_and_hybrid_schedule(knob, monkeypatch):
+    """Default (tiled) path with its periodic re-sort done by the streaming pass k_stream_sort, and with the step in which a
+    re-sort is due run by the streaming step kernel instead: order-only changes, same bars."""
+    monkeypatch.setenv(knob, "1")
+    monkeypatch.setenv("SFGPU_STREAM_CHECK", "1")
+    m = S.make_mesh(70, 50, DomainType.XY, 1e-3, "open")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 5, vth_cells=0.6, kick_frac=0.1)
+    arr = wl.particles(0, 30000)
+    km, ok = make_pair([m], wl, [arr], 0)
+    with km:
+        km.setSortInterval(2)
+        for _ in range(7):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+        compare_state(km, ok)
+        compare_fields(km, ok)
+
+
+@pytest.mark.parametrize("dom,bc", [(DomainType.XY, "periodic"), (DomainType.RZ, "beam"), (DomainType.XY, "open")])
+def test_warp_specialised_streaming_kernel(dom, bc, monkeypatch):
+    """The push-group / deposit-group form of the streaming step (sf_stream_ws.cuh, SFGPU_STREAM_WS=1): same bars."""
+    monkeypatch.setenv("SFGPU_STREAM_WS", "1")
+    monkeypatch.setenv("SFGPU_STREAM_CHECK", "1")
+    m = S.make_mesh(67, 45, dom, 1e-3, bc)
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 43, vth_cells=0.7, kick_frac=0.1)
+    arr = wl.particles(0, 20000)
+    km, ok = make_pair([m], wl, [arr], _lib.STEP_STREAM)
+    with km:
+        for _ in range(6):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+        compare_state(km, ok)
+        compare_fields(km, ok)
+
+
 @pytest.mark.parametrize("flags", PATHS)
 def test_fast_particles_many_bounces_and_residual_dt(flags):
     """CFL >> 1 on a tiny symmetric box: >10 bounces leaves dt > 0 that is added to the next step (KM:333, :360)."""
