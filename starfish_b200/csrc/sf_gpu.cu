@@ -184,7 +184,7 @@ struct sfgpu_ctx {
     int nranks = 1, rank = 0;
     int last_launches = 0;
     bool timing_valid = false;
-    int sort_every = 4;      // steps between cell sorts of the fast store
+    int sort_every = 3;      // steps between cell sorts of the fast store (2..5 give the same step time on config B; 3 keeps the kernel on a fresher order)
     int fast_grid = 0;       // CTAs of the tiled kernel (persistent)
     int path = 0;            // default step kernel: 0 = tiled in-place step + periodic sort (sf_fast.cuh), 1 = streaming step (sf_stream.cuh)
     int stream_grid = 0;     // CTAs of the streaming kernel (persistent)
