@@ -17,7 +17,6 @@
 
 #include "sf_fast.cuh"
 #include "sf_stream.cuh"
-#include "sf_stream_ws.cuh"
 #include "sf_generic.cuh"
 #include "sf_store.cuh"
 
@@ -188,12 +187,10 @@ struct sfgpu_ctx {
     int fast_grid = 0;       // CTAs of the tiled kernel (persistent)
     int path = 0;            // default step kernel: 0 = tiled in-place step + periodic sort (sf_fast.cuh), 1 = streaming step (sf_stream.cuh)
     int stream_grid = 0;     // CTAs of the streaming kernel (persistent)
-    int ws_grid = 0;         // CTAs of the warp-specialised streaming kernel (one per SM)
     bool hybrid = false;     // tiled path: run the step in which a re-sort is due with the streaming kernel instead of sorting separately
     unsigned *h_cnt2 = nullptr; // pinned: per-mesh work-item counts read back with the step counters
     int last_kernel = 0;     // step kernel of the last sfgpu_step: 0 tiled, 1 streaming, 2 generic
     bool stream_sort = false; // periodic re-sort of the tiled path: 1 = streaming pass (k_stream_sort), 0 = generic counting sort (equal speed measured)
-    bool stream_ws = false;  // which streaming kernel runs: warp-specialised (sf_stream_ws.cuh) or uniform (sf_stream.cuh)
     bool stream_check = false; // debug: verify the output cursors after every streaming launch
     unsigned long long *d_bad = nullptr;
     Records tmp;             // staging records for download / upload of the fast store
@@ -582,12 +579,6 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_stream_step, SFS_THREADS, SFS_SMEM_BYTES));
         if (per_sm_s < 1) return fail(ctx, SFGPU_ECUDA, "k_stream_step does not fit on this device");
         ctx->stream_grid = nsm * per_sm_s;
-        CU(cudaFuncSetAttribute(k_stream_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, SFW_SMEM_BYTES));
-        int per_sm_w = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, k_stream_ws, SFW_THREADS, SFW_SMEM_BYTES));
-        if (per_sm_w < 1) return fail(ctx, SFGPU_ECUDA, "k_stream_ws does not fit on this device");
-        ctx->ws_grid = nsm;
-        if (const char *e = getenv("SFGPU_STREAM_WS")) ctx->stream_ws = atoi(e) != 0;
         if (const char *e = getenv("SFGPU_STREAM_GRID")) ctx->stream_grid = atoi(e) > 0 ? atoi(e) : ctx->stream_grid;
         if (const char *e = getenv("SFGPU_PATH")) ctx->path = strcmp(e, "stream") == 0 ? 1 : 0;
         ctx->stream_check = getenv("SFGPU_STREAM_CHECK") != nullptr;
@@ -1137,7 +1128,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                 rc = fast_reserve_alt(ctx, f);
                 if (rc) return rc;
             }
-            const unsigned want_items = (unsigned)(f.n / SFW_CHUNK + (int64_t)f.nti * f.ntj + 16);
+            const unsigned want_items = (unsigned)(f.n / SFR_CHUNK + (int64_t)f.nti * f.ntj + 16); // (sized for the smaller chunks of k_stream_sort too)
             if (f.max_items < want_items) {
                 if (f.items) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(f.items)); }
                 f.items = nullptr; f.max_items = 0;
@@ -1178,7 +1169,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             CU(cudaMemsetAsync(f.hist_next, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
             { ctx->last_launches++; ctx->launch_total++; }
             if (f.n > 0) {
-                const unsigned chunk = ctx->stream_ws ? SFW_CHUNK : SFS_CHUNK;
+                const unsigned chunk = SFS_CHUNK;
                 CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
                 CU(cudaMemsetAsync(f.items, 0, (size_t)f.max_items * sizeof(WorkItem), ctx->stream)); // count 0 ends a CTA's round-robin walk
                 if (f.n_sorted > 0) {
@@ -1200,8 +1191,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                 sa.hist_next = f.hist_next;
                 sa.max_items = f.max_items;
                 CU(cudaMemcpyAsync(ctx->d_args + m, &sa.b, sizeof sa.b, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
-                if (ctx->stream_ws) k_stream_ws<<<ctx->ws_grid, SFW_THREADS, SFW_SMEM_BYTES, ctx->stream>>>(sa, ctx->d_args + m);
-                else k_stream_step<<<ctx->stream_grid, SFS_THREADS, SFS_SMEM_BYTES, ctx->stream>>>(sa, ctx->d_args + m);
+                k_stream_step<<<ctx->stream_grid, SFS_THREADS, SFS_SMEM_BYTES, ctx->stream>>>(sa, ctx->d_args + m);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
                 if (ctx->path == 0) { // the tiled kernel runs the next steps: its work items follow the new layout

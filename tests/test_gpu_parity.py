@@ -109,23 +109,6 @@ def test_streaming_resort_and_hybrid_schedule(knob, monkeypatch):
         compare_fields(km, ok)
 
 
-@pytest.mark.parametrize("dom,bc", [(DomainType.XY, "periodic"), (DomainType.RZ, "beam"), (DomainType.XY, "open")])
-def test_warp_specialised_streaming_kernel(dom, bc, monkeypatch):
-    """The push-group / deposit-group form of the streaming step (sf_stream_ws.cuh, SFGPU_STREAM_WS=1): same bars."""
-    monkeypatch.setenv("SFGPU_STREAM_WS", "1")
-    monkeypatch.setenv("SFGPU_STREAM_CHECK", "1")
-    m = S.make_mesh(67, 45, dom, 1e-3, bc)
-    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 43, vth_cells=0.7, kick_frac=0.1)
-    arr = wl.particles(0, 20000)
-    km, ok = make_pair([m], wl, [arr], _lib.STEP_STREAM)
-    with km:
-        for _ in range(6):
-            km.updateFields()
-            ok.updateFields(wl.dt)
-        compare_state(km, ok)
-        compare_fields(km, ok)
-
-
 @pytest.mark.parametrize("flags", PATHS)
 def test_fast_particles_many_bounces_and_residual_dt(flags):
     """CFL >> 1 on a tiny symmetric box: >10 bounces leaves dt > 0 that is added to the next step (KM:333, :360)."""
