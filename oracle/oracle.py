@@ -37,6 +37,10 @@ class _Parts(C.Structure):
     _fields_ = [("n", C.c_int64)] + [(k, _dp) for k in _PK]
 
 
+class _Spline(C.Structure):
+    _fields_ = [("n_seg", C.c_int32)] + [(k, _dp) for k in ("x1", "y1", "x2", "y2", "nx", "ny", "area", "cum_area")] + [("spline_area", C.c_double)]
+
+
 class _MoveOut(C.Structure):
     _fields_ = [("status", C.POINTER(C.c_int8)), ("xfer_mask", _ip), ("xfer_mesh", _ip), ("xfer_li", _dp), ("xfer_lj", _dp),
                 ("old_x", _dp), ("old_y", _dp), ("old_li", _dp), ("old_lj", _dp), ("bounces", _ip)]
@@ -87,8 +91,22 @@ def load():
     lib.sfo_sample.argtypes = [C.POINTER(_Mesh), C.POINTER(_Parts)] + [_dp] * 8
     lib.sfo_add_particles.restype = None
     lib.sfo_add_particles.argtypes = [C.POINTER(_Mesh), C.c_double, C.c_double, C.c_int, C.POINTER(_Parts), C.c_int64, C.c_int64]
+    lib.sfo_java_seed.restype = C.c_uint64
+    lib.sfo_java_seed.argtypes = [C.c_int64]
+    lib.sfo_java_next_int.restype = C.c_int32
+    lib.sfo_java_next_int.argtypes = [C.POINTER(C.c_uint64)]
+    lib.sfo_java_next_double.restype = C.c_double
+    lib.sfo_java_next_double.argtypes = [C.POINTER(C.c_uint64)]
+    lib.sfo_uniform_source.restype = None
+    lib.sfo_uniform_source.argtypes = [C.POINTER(_Spline), C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(_Mesh), C.c_int,
+                                       _dp, _dp, _dp, _dp, _dp, _dp, _ip]
     _lib = lib
     return lib
+
+
+def java_seed(seed):
+    """java.util.Random scrambled internal state for ``new Random(seed)``."""
+    return int(load().sfo_java_seed(int(seed)))
 
 
 def _d(a):
@@ -207,6 +225,29 @@ class OracleKM:
         self.ms.refresh()
 
     # KM:759-802 + MeshData.addParticle KM:1356-1361
+    def sampleUniformSource(self, spline, v_drift, num_mp, dt, rng_state, mpw, born_it=0):
+        """Source.sampleKinetic over UniformSource.sampleParticle: returns (particles added, new RNG state).
+        Particles keep the order they were sampled in; ids count up over the accepted ones (KM:797)."""
+        n = int(num_mp)
+        x, y, z, u, v, w = (np.zeros(n) for _ in range(6))
+        mesh_of = np.zeros(n, np.int32)
+        sp = _Spline(spline.n_seg, *[_d(getattr(spline, k)) for k in ("x1", "y1", "x2", "y2", "nx", "ny", "area", "cum_area")], spline.spline_area)
+        st = C.c_uint64(int(rng_state))
+        self.lib.sfo_uniform_source(C.byref(sp), float(v_drift), float(dt), n, C.byref(st), self.ms.arr, len(self.meshes),
+                                    _d(x), _d(y), _d(z), _d(u), _d(v), _d(w), mesh_of.ctypes.data_as(_ip))
+        acc = mesh_of >= 0
+        ids = (self.id_counter + np.cumsum(acc) - 1).astype(np.int32)
+        added = 0
+        for k in range(len(self.meshes)):
+            sel = mesh_of == k
+            if not sel.any():
+                continue
+            arr = dict(x=x[sel], y=y[sel], z=z[sel], u=u[sel], v=v[sel], w=w[sel], mpw=np.full(int(sel.sum()), float(mpw)))
+            self.addParticles(k, arr, dt, ids=ids[sel], born_it=np.full(int(sel.sum()), int(born_it), np.int32))
+            added += int(sel.sum())
+        self.id_counter += int(acc.sum())
+        return added, int(st.value)
+
     def addParticles(self, mesh_id, arrays, dt, rewind=True, ids=None, born_it=None, transfer=False):
         n = len(arrays["x"])
         p = empty_parts(n)

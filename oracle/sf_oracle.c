@@ -421,3 +421,79 @@ void sfo_add_particles(const sfo_mesh *m, double qm, double dt, int compute_lc, 
         p->dt[q] = 0;
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * particle injection by UniformSource on a Boundary of linear segments (XY domains)
+ * ------------------------------------------------------------------------------------------- */
+
+/* java.util.Random: 48-bit LCG, next(bits) (the JDK's documented algorithm; Starfish.rnd() = random.nextDouble(),
+ * Starfish.java:244-246).  `state` is the scrambled internal seed ((seed ^ 0x5DEECE66D) & (2^48 - 1) after setSeed). */
+static int32_t java_next(uint64_t *state, int bits)
+{
+    *state = (*state * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int32_t)((int64_t)*state >> (48 - bits)); /* (int)(seed >>> (48 - bits)) */
+}
+uint64_t sfo_java_seed(int64_t seed) { return ((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1); }
+int32_t sfo_java_next_int(uint64_t *state) { return java_next(state, 32); }
+double sfo_java_next_double(uint64_t *state)
+{
+    const int64_t hi = (int64_t)java_next(state, 26), lo = (int64_t)java_next(state, 27);
+    return (double)((hi << 27) + lo) * 0x1.0p-53; /* DOUBLE_UNIT */
+}
+
+/* Vec.binarySearch, Vec.java:529-546 */
+static int vec_binary_search(const double *vec, int n, double val)
+{
+    if (val < vec[0]) return -1;
+    if (val > vec[n - 1]) return n;
+    int i1 = 0, i2 = n;
+    for (;;) {
+        const int i_mid = (int)(0.5 * (i1 + i2));
+        if (val < vec[i_mid]) i2 = i_mid;
+        else if (val > vec[i_mid]) i1 = i_mid;
+        else return i_mid;
+        if ((i2 - i1) <= 1) return i1;
+    }
+}
+
+/* Source.sampleKinetic (Source.java:167-198) over UniformSource.sampleParticle (sources/UniformSource.java:56-72) with
+ * Spline.randomT for XY (Spline.java:582-641), Spline.pos / normal (:700-707, :947-954), LinearSegment.pos / normal
+ * (LinearSegment.java:94-101, :20-45), the 1e-6*dt nudge off the surface (Source.java:186-188) and
+ * DomainModule.getMesh (DomainModule.java:106-117: first mesh that strictly contains the point, else the first that
+ * contains it within FLT_EPS).  Outputs the sampled particles in order and the mesh each one lands in (-1: dropped). */
+void sfo_uniform_source(const sfo_spline *s, double v_drift, double dt, int64_t num_mp, uint64_t *rng_state,
+                        const sfo_mesh *meshes, int n_meshes, double *x, double *y, double *z, double *u, double *v,
+                        double *w, int32_t *mesh_of)
+{
+    for (int64_t q = 0; q < num_mp; q++) {
+        const double A1 = sfo_java_next_double(rng_state) * s->spline_area;
+        const int i = vec_binary_search(s->cum_area, s->n_seg + 1, A1);
+        const double frac = (A1 - s->cum_area[i]) / s->area[i];
+        const double t = i + frac;
+        int si = (int)t; /* Spline.pos */
+        double seg_t = t - si;
+        if (si > s->n_seg - 1) { si = s->n_seg - 1; seg_t = 1.0; }
+        double pos[3] = {s->x1[si] + seg_t * (s->x2[si] - s->x1[si]), s->y1[si] + seg_t * (s->y2[si] - s->y1[si]), 0.0};
+        int sn = (int)t; /* Spline.normal */
+        if (sn > s->n_seg - 1) sn = s->n_seg - 1;
+        const double n[3] = {s->nx[sn], s->ny[sn], 0.0};
+        double vel[3];
+        for (int k = 0; k < 3; k++) vel[k] = n[k] * v_drift;
+        for (int k = 0; k < 3; k++) pos[k] += vel[k] * 1e-6 * dt;
+        int found = -1;
+        for (int m = 0; m < n_meshes && found < 0; m++) { /* containsPosStrict, UM:164-171 */
+            const sfo_mesh *mm = &meshes[m];
+            const double xd0 = mm->x0[0] + (mm->ni - 1) * mm->dh[0], xd1 = mm->x0[1] + (mm->nj - 1) * mm->dh[1];
+            if (pos[0] >= mm->x0[0] && pos[0] < xd0 && pos[1] >= mm->x0[1] && pos[1] < xd1) found = m;
+        }
+        for (int m = 0; m < n_meshes && found < 0; m++) { /* containsPos, MESH:1476-1483 */
+            const sfo_mesh *mm = &meshes[m];
+            double li, lj;
+            sfo_xtol(mm, pos[0], pos[1], &li, &lj);
+            if (!(li < -FLT_EPS || lj < -FLT_EPS || li > (mm->ni - 1 + FLT_EPS) || lj > (mm->nj - 1 + FLT_EPS))) found = m;
+        }
+        x[q] = pos[0]; y[q] = pos[1]; z[q] = pos[2];
+        u[q] = vel[0]; v[q] = vel[1]; w[q] = vel[2];
+        mesh_of[q] = found;
+    }
+}

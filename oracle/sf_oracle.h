@@ -76,6 +76,24 @@ typedef struct {
     int32_t *bounces;          /* substeps consumed                                       */
 } sfo_move_out;
 
+/* a Boundary made of linear segments, as the Java Spline holds it (Spline.java: segments, cum_area, spline_area;
+ * LinearSegment.java:20-45: normal = (-dy, dx, 0) / length) */
+typedef struct {
+    int32_t n_seg;
+    const double *x1, *y1, *x2, *y2; /* LinearSegment end points                  */
+    const double *nx, *ny;           /* LinearSegment.normal[0..1]                */
+    const double *area;              /* Segment.area (XY: the segment length)     */
+    const double *cum_area;          /* n_seg + 1 entries, cum_area[0] = 0        */
+    double spline_area;
+} sfo_spline;
+
+uint64_t sfo_java_seed(int64_t seed);              /* java.util.Random.setSeed scrambling      */
+int32_t sfo_java_next_int(uint64_t *state);        /* java.util.Random.nextInt()               */
+double sfo_java_next_double(uint64_t *state);      /* java.util.Random.nextDouble()            */
+void sfo_uniform_source(const sfo_spline *s, double v_drift, double dt, int64_t num_mp, uint64_t *rng_state,
+                        const sfo_mesh *meshes, int n_meshes, double *x, double *y, double *z, double *u, double *v,
+                        double *w, int32_t *mesh_of);
+
 double sfo_gather(const double *d, int ni, int nj, double fi, double fj);      /* F2D:300-350 */
 double sfo_gather_safe(const double *d, int ni, int nj, double fi, double fj); /* F2D:371-390 */
 void sfo_scatter(double *d, const sfo_mesh *m, double fi, double fj, double val); /* F2D:244-295 */

@@ -162,3 +162,26 @@ def set_mesh_neighbors(meshes):
                 add(me, Face.BOTTOM, 0, k)
             if is_mesh(Face.BOTTOM, ni - 2) and other.containsPos(pos(ni - 1, 0)):
                 add(me, Face.BOTTOM, ni - 1, k)
+
+
+class LinearSpline:
+    """A Boundary made of linear segments as the reference's ``Spline`` holds it for an XY domain: per segment the end
+    points, ``LinearSegment.normal`` = (-dy, dx, 0)/length (LinearSegment.java:20-45) and ``area`` = length
+    (LinearSegment.area, XY), plus ``cum_area`` and ``spline_area`` (Spline.java).  Geometry set-up stays in Java; this
+    mirror only builds the INPUT of the source sampling for the tests and examples."""
+
+    def __init__(self, points):
+        pts = np.asarray(points, np.float64)
+        assert pts.ndim == 2 and pts.shape[1] == 2 and len(pts) >= 2
+        self.x1, self.y1 = np.ascontiguousarray(pts[:-1, 0]), np.ascontiguousarray(pts[:-1, 1])
+        self.x2, self.y2 = np.ascontiguousarray(pts[1:, 0]), np.ascontiguousarray(pts[1:, 1])
+        dx, dy = self.x2 - self.x1, self.y2 - self.y1
+        length = np.sqrt(dx * dx + dy * dy)
+        dx, dy = dx / length, dy / length
+        self.nx, self.ny = np.ascontiguousarray(-dy), np.ascontiguousarray(dx)
+        self.area = np.ascontiguousarray(length)  # XY: t*length at t = 1
+        self.cum_area = np.zeros(len(length) + 1)
+        for k in range(len(length)):  # sequential sum, like the Java loop
+            self.cum_area[k + 1] = self.cum_area[k] + self.area[k]
+        self.spline_area = float(self.cum_area[-1])
+        self.n_seg = len(length)

@@ -418,3 +418,113 @@ class KM:
                 if 0 <= ci < mesh.ni and 0 <= cj < mesh.nj:
                     F[7].data[ci][cj] += 1
             self.raw.append([f.data for f in F])
+
+
+# ---------------------------------------------------------------------------------------------
+# UniformSource on a Boundary of linear segments (XY), written from the Java, independently of the C oracle
+# ---------------------------------------------------------------------------------------------
+class JavaRandom:
+    """java.util.Random (the JDK's documented 48-bit LCG).  Starfish.rnd() = random.nextDouble(), Starfish.java:244."""
+
+    MASK = (1 << 48) - 1
+
+    def __init__(self, seed=None, state=None):
+        self.state = ((seed ^ 0x5DEECE66D) & self.MASK) if state is None else int(state)
+
+    def next(self, bits):
+        self.state = (self.state * 0x5DEECE66D + 0xB) & self.MASK
+        v = self.state >> (48 - bits)
+        return v - (1 << 32) if v >= (1 << 31) else v  # (int)
+
+    def nextInt(self):
+        return self.next(32)
+
+    def nextDouble(self):
+        return ((self.next(26) << 27) + self.next(27)) * (1.0 / (1 << 53))
+
+
+class LinearSegment:  # boundaries/LinearSegment.java:20-101
+    def __init__(self, x1, x2):
+        self.x1, self.x2 = [float(x1[0]), float(x1[1])], [float(x2[0]), float(x2[1])]
+        dx, dy = self.x2[0] - self.x1[0], self.x2[1] - self.x1[1]
+        self.length = math.sqrt(dx * dx + dy * dy)
+        dx /= self.length
+        dy /= self.length
+        self.normal = [-dy, dx, 0.0]
+        self.area = 1.0 * self.length  # area(1) in XY
+
+    def pos(self, t):
+        return [self.x1[0] + t * (self.x2[0] - self.x1[0]), self.x1[1] + t * (self.x2[1] - self.x1[1]), 0.0]
+
+
+class Spline:  # boundaries/Spline.java (linear segments, XY)
+    def __init__(self, points):
+        self.segments = [LinearSegment(points[k], points[k + 1]) for k in range(len(points) - 1)]
+        self.cum_area = [0.0]
+        for s in self.segments:
+            self.cum_area.append(self.cum_area[-1] + s.area)
+        self.spline_area = self.cum_area[-1]
+
+    @staticmethod
+    def binarySearch(vec, val):  # Vec.java:529-546
+        if val < vec[0]:
+            return -1
+        if val > vec[-1]:
+            return len(vec)
+        i1, i2 = 0, len(vec)
+        while True:
+            i_mid = int(0.5 * (i1 + i2))
+            if val < vec[i_mid]:
+                i2 = i_mid
+            elif val > vec[i_mid]:
+                i1 = i_mid
+            else:
+                return i_mid
+            if i2 - i1 <= 1:
+                return i1
+
+    def randomT(self, rnd):  # Spline.java:582-641, XY branch
+        A1 = rnd.nextDouble() * self.spline_area
+        i = self.binarySearch(self.cum_area, A1)
+        frac = (A1 - self.cum_area[i]) / self.segments[i].area
+        return i + frac
+
+    def pos(self, t):  # Spline.java:700-707
+        si = int(t)
+        seg_t = t - si
+        if si > len(self.segments) - 1:
+            si, seg_t = len(self.segments) - 1, 1.0
+        return self.segments[si].pos(seg_t)
+
+    def normal(self, t):  # Spline.java:947-954
+        si = min(int(t), len(self.segments) - 1)
+        return list(self.segments[si].normal)
+
+
+def uniform_source_sample(km, spline, v_drift, num_mp, dt, rnd, spwt0, born_it=0):
+    """Source.sampleKinetic (Source.java:167-198) with UniformSource.sampleParticle (sources/UniformSource.java:56-72) and
+    KineticMaterial.addParticle(Particle) (KM:810-818) + DomainModule.getMesh (DomainModule.java:106-117)."""
+    count = 0
+    while num_mp > 0:
+        t = spline.randomT(rnd)
+        x, n = spline.pos(t), spline.normal(t)
+        part = Particle([x[0], x[1], 0.0], [n[k] * v_drift for k in range(3)], spwt0)
+        part.born_it = born_it
+        num_mp -= 1
+        for k in range(3):
+            part.pos[k] += part.vel[k] * 1e-6 * dt
+        mesh = None
+        for m, mm in enumerate(km.meshes):  # containsPosStrict, UM:164-171
+            if part.pos[0] >= mm.x0[0] and part.pos[0] < mm.xd[0] and part.pos[1] >= mm.x0[1] and part.pos[1] < mm.xd[1]:
+                mesh = m
+                break
+        if mesh is None:
+            for m, mm in enumerate(km.meshes):
+                if mm.containsPos(part.pos):
+                    mesh = m
+                    break
+        if mesh is None:
+            continue
+        km.addParticle(mesh, part, dt)
+        count += 1
+    return count

@@ -332,3 +332,54 @@ def test_oracle_matches_python_restatement_mesh_handoff():
     arr["x"] = np.abs(arr["x"]) * 0.8 + 1e-5
     km, pk = _run_pair([a, b], wl.charge, wl.mass, wl.dt, [arr, None], 12, check_sums=False)
     assert km.getNp(1) > 0, "particles must have crossed into the second mesh"
+
+
+# ---------------------------------------------------------------- sources (java.util.Random + UniformSource)
+def test_kat_java_util_random_known_answers():
+    """The JDK's documented LCG, pinned by values every Java programmer can reproduce:
+    new Random(0).nextInt() -> -1155484576, -723955400, 1033096058; new Random(42).nextInt() -> -1170105035;
+    new Random(0).nextDouble() -> 0.730967787376657, 0.24053641567148587, 0.6374174253501083."""
+    lib = O.load()
+    for seed, want in ((0, [-1155484576, -723955400, 1033096058]), (42, [-1170105035, 234785527, -1360544799])):
+        st = C.c_uint64(O.java_seed(seed))
+        assert [lib.sfo_java_next_int(C.byref(st)) for _ in range(3)] == want
+        r = pyref.JavaRandom(seed)
+        assert [r.nextInt() for _ in range(3)] == want
+    st = C.c_uint64(O.java_seed(0))
+    want = [0.730967787376657, 0.24053641567148587, 0.6374174253501083, 0.5504370051176339, 0.5975452777972018]
+    assert [lib.sfo_java_next_double(C.byref(st)) for _ in range(5)] == want
+    r = pyref.JavaRandom(0)
+    assert [r.nextDouble() for _ in range(5)] == want and r.state == st.value
+
+
+def test_kat_spline_random_t_and_binary_search():
+    """Vec.binarySearch returns i with vec[i] <= x <= vec[i+1] (Vec.java:529-546); randomT = segment + area fraction."""
+    cum = [0.0, 1.0, 3.0, 3.5]
+    assert [pyref.Spline.binarySearch(cum, v) for v in (-0.1, 0.0, 0.5, 1.0, 2.9, 3.2, 3.5, 3.6)] == [-1, 0, 0, 1, 1, 2, 3, 4]
+    sp = pyref.Spline([(0.0, 0.0), (1.0, 0.0), (1.0, 2.0), (1.5, 2.0)])
+    assert sp.cum_area == cum
+    r = pyref.JavaRandom(0)  # 0.7309... * 3.5 = 2.558 -> segment 1, frac (2.558 - 1) / 2
+    t = sp.randomT(r)
+    assert int(t) == 1 and abs(t - (1 + (0.730967787376657 * 3.5 - 1.0) / 2.0)) < 1e-15
+    assert sp.normal(t) == [-1.0, 0.0, 0.0] and sp.pos(t)[0] == 1.0
+
+
+def test_oracle_uniform_source_matches_python_restatement():
+    """Source.sampleKinetic over UniformSource.sampleParticle on a three-segment inlet, two meshes (one only reachable through
+    containsPos), part of the inlet outside every mesh: positions, rewound velocities, ids, RNG state bit for bit."""
+    from starfish_b200.domain import LinearSpline
+    a = S.make_mesh(21, 11, DomainType.XY, 5e-3, "open", x0=(-0.1, 0.0))
+    b = S.make_mesh(11, 9, DomainType.XY, 5e-3, "open", x0=(-0.1, 0.05))  # overlaps a: getMesh takes the first that contains the point
+    pts = [(-0.1, 0.12), (-0.1, 0.03), (-0.09, -0.01), (-0.09, -0.02)]
+    km = O.OracleKM(S.QE, 16 * S.AMU, [a, b])
+    pk = pyref.KM(S.QE, 16 * S.AMU, [_py_mesh(a), _py_mesh(b)])
+    rnd = pyref.JavaRandom(12345)
+    state = O.java_seed(12345)
+    for it in range(3):
+        n_o, state = km.sampleUniformSource(LinearSpline(pts), 7000.0, 257, 1e-7, state, 1e3, born_it=it)
+        n_p = pyref.uniform_source_sample(pk, pyref.Spline(pts), 7000.0, 257, 1e-7, rnd, 1e3, born_it=it)
+        assert n_o == n_p and state == rnd.state and 0 < n_o < 257
+        km.updateFields(1e-7)
+        pk.updateFields(1e-7)
+        _compare(km, pk, 2)
+    assert km.getNp(0) > 0 and km.getNp(1) > 0
