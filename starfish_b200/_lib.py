@@ -34,6 +34,11 @@ class SlowExtra(C.Structure):
     _fields_ = [(k, c_double_p) for k in ("old_x", "old_y", "old_li", "old_lj")] + [("bounces", c_int32_p), ("mesh", c_int32_p)]
 
 
+class Spline(C.Structure):
+    """``struct sfgpu_spline``"""
+    _fields_ = [("n_seg", C.c_int32)] + [(k, c_double_p) for k in ("x1", "y1", "x2", "y2", "nx", "ny", "area", "cum_area")] + [("spline_area", C.c_double)]
+
+
 # name -> (restype, argtypes); must list every function declared in include/sfgpu.h
 EXPORTS = {
     "sfgpu_abi_version": (C.c_int, []),
@@ -45,6 +50,8 @@ EXPORTS = {
     "sfgpu_set_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfgpu_species_add": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int64, c_int32_p]),
     "sfgpu_inject": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Particles), C.c_double, C.c_uint32, c_int64_p]),
+    "sfgpu_source_uniform": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(Spline), C.c_double, C.c_double, C.c_int32, C.c_int64, C.c_double,
+                                      C.POINTER(C.c_uint64), c_int64_p]),
     "sfgpu_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_uint32]),
     "sfgpu_finish_step": (C.c_int, [C.c_void_p, C.c_int32]),
     "sfgpu_get_deposit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),

@@ -17,6 +17,7 @@
 
 #include "sf_fast.cuh"
 #include "sf_stream.cuh"
+#include "sf_source.cuh"
 #include "sf_generic.cuh"
 #include "sf_store.cuh"
 
@@ -194,6 +195,8 @@ struct sfgpu_ctx {
     bool stream_check = false; // debug: verify the output cursors after every streaming launch
     unsigned long long *d_bad = nullptr;
     Records tmp;             // staging records for download / upload of the fast store
+    char *src_tmp = nullptr; // device scratch of sfgpu_source_uniform (sampled particles, flags, ranks, spline, scan storage)
+    size_t src_bytes = 0;
     unsigned long long last_fallback = 0, last_flush = 0;
     bool force_sort = false;
     std::string err;
@@ -640,6 +643,7 @@ extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
     if (ctx->d_xfer) cudaFree(ctx->d_xfer);
     if (ctx->d_args) cudaFree(ctx->d_args);
     if (ctx->d_bad) cudaFree(ctx->d_bad);
+    if (ctx->src_tmp) cudaFree(ctx->src_tmp);
     if (ctx->h_cnt2) cudaFreeHost(ctx->h_cnt2);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
@@ -885,6 +889,32 @@ static int download_records(sfgpu_ctx *ctx, const RecPtrs &r, int64_t first, con
 }
 
 
+// addParticle(md, part) over c particles that already sit behind the fast store (state + tags at f.p[f.n .. f.n + c)):
+// XtoL, plus-edge clamp, -0.5dt rewind, finite-velocity filter (k_inject_fast); updates the store's bookkeeping
+static int inject_fast_run(sfgpu_ctx *ctx, Species &s, int mesh_id, int64_t c, double dt_step, bool rewind, int64_t *added)
+{
+    Pop &pop = s.pops[mesh_id];
+    FastStore &f = pop.fast;
+    CU(cudaMemsetAsync(&ctx->d_cnt->n_bad, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(&ctx->d_cnt->n_exc[mesh_id], 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(&ctx->d_cnt->overflow, 0, sizeof(unsigned long long), ctx->stream));
+    k_inject_fast<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, s.qm, dt_step, rewind ? 1 : 0, f.p, (unsigned long long)f.n,
+                                                                           (unsigned long long)c, pop.cur.p, (unsigned long long)pop.cur.n,
+                                                                           (unsigned long long)pop.cur.cap, ctx->d_cnt, f.stream_ok ? f.hist : nullptr, f.ntj);
+    ctx->launch_total++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(StepCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_cnt->overflow) return fail(ctx, SFGPU_EOVERFLOW, "internal: record list overflow during injection");
+    const int64_t n_exc = (int64_t)ctx->h_cnt->n_exc[mesh_id], n_bad = (int64_t)ctx->h_cnt->n_bad;
+    pop.cur.n += n_exc;
+    f.n += c;
+    f.alive += c - n_exc - n_bad;
+    if (n_exc || n_bad) f.dirty = true;
+    *added = c - n_bad;
+    return 0;
+}
+
 // bulk addParticle into the fast store (the common case: lc == null, KM:760-774): chunks of 1M through the
 // pinned stage, k_inject_fast applies XtoL + the -0.5dt rewind; the rare particle the fast store cannot
 // represent lands in the record list.
@@ -919,26 +949,10 @@ static int inject_fast(sfgpu_ctx *ctx, Species &s, int mesh_id, const sfgpu_part
             tg[q].y = p->born_it ? p->born_it[off + q] : 0;
         }
         CU(cudaMemcpyAsync(f.p.tag + f.n, tg, (size_t)c * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemsetAsync(&ctx->d_cnt->n_bad, 0, sizeof(unsigned long long), ctx->stream));
-        CU(cudaMemsetAsync(&ctx->d_cnt->n_exc[mesh_id], 0, sizeof(unsigned long long), ctx->stream));
-        CU(cudaMemsetAsync(&ctx->d_cnt->overflow, 0, sizeof(unsigned long long), ctx->stream));
-        k_inject_fast<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, s.qm, dt_step, (flags & SFGPU_INJECT_REWIND) ? 1 : 0,
-                                                                               f.p, (unsigned long long)f.n, (unsigned long long)c, pop.cur.p,
-                                                                               (unsigned long long)pop.cur.n, (unsigned long long)pop.cur.cap, ctx->d_cnt,
-                                                                               f.stream_ok ? f.hist : nullptr, f.ntj);
-        ctx->launch_total++;
-        CU(cudaGetLastError());
-        int rc2 = 0;
-        CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(StepCounters), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->h_cnt->overflow) return fail(ctx, SFGPU_EOVERFLOW, "internal: record list overflow during injection");
-        (void)rc2;
-        const int64_t n_exc = (int64_t)ctx->h_cnt->n_exc[mesh_id], n_bad = (int64_t)ctx->h_cnt->n_bad;
-        pop.cur.n += n_exc;
-        f.n += c;
-        f.alive += c - n_exc - n_bad;
-        if (n_exc || n_bad) f.dirty = true;
-        added += c - n_bad;
+        int64_t a = 0;
+        rc = inject_fast_run(ctx, s, mesh_id, c, dt_step, (flags & SFGPU_INJECT_REWIND) != 0, &a);
+        if (rc) return rc;
+        added += a;
     }
     if (assign_ids) s.id_counter += (int32_t)p->n; // KM:797
     if (n_added) *n_added = added;
@@ -1015,6 +1029,103 @@ extern "C" int sfgpu_inject(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const s
         }
     }
     r.n = first + added;
+    if (n_added) *n_added = added;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// UniformSource sampled on the device (sf_source.cuh)
+// ---------------------------------------------------------------------------------------------
+extern "C" int sfgpu_source_uniform(sfgpu_ctx *ctx, int32_t sp, const sfgpu_spline *spl, double v_drift, double mpw, int32_t born_it,
+                                    int64_t num_mp, double dt_step, uint64_t *rng_state, int64_t *n_added)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    if (n_added) *n_added = 0;
+    if (!spl || !rng_state) return fail(ctx, SFGPU_EINVAL, "sfgpu_source_uniform: spline and rng_state are required");
+    if (ctx->domain != SFGPU_XY) return fail(ctx, SFGPU_EINVAL, "sfgpu_source_uniform: Spline.randomT searches iteratively in axisymmetric domains; sample those on the host");
+    if (spl->n_seg < 1 || !spl->x1 || !spl->y1 || !spl->x2 || !spl->y2 || !spl->nx || !spl->ny || !spl->area || !spl->cum_area)
+        return fail(ctx, SFGPU_EINVAL, "sfgpu_source_uniform: incomplete spline");
+    if (num_mp < 0 || num_mp >= (1LL << 31)) return fail(ctx, SFGPU_EINVAL, "sfgpu_source_uniform: bad particle count");
+    if (num_mp == 0) return 0;
+    int rc = sync_meshes(ctx);
+    if (rc) return rc;
+    Species &s = ctx->species[sp];
+    const int nmesh = (int)ctx->meshes.size();
+    const size_t n = (size_t)num_mp, ns = (size_t)spl->n_seg;
+    // scratch layout: 6 doubles per particle, spline arrays, then mesh_of / flag / rank_all / rank_mesh, then the scan storage
+    size_t cub_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned *)nullptr, (unsigned *)nullptr, (int)n, ctx->stream));
+    const size_t dbl = 6 * n + 8 * ns + 1, need = dbl * sizeof(double) + 4 * n * sizeof(unsigned) + cub_bytes + 256;
+    if (ctx->src_bytes < need) {
+        if (ctx->src_tmp) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(ctx->src_tmp)); }
+        ctx->src_tmp = nullptr; ctx->src_bytes = 0;
+        CU(cudaMalloc(&ctx->src_tmp, need + need / 2));
+        ctx->src_bytes = need + need / 2;
+    }
+    double *d = (double *)ctx->src_tmp;
+    double *x = d, *y = x + n, *z = y + n, *u = z + n, *v = u + n, *w = v + n, *sd = w + n;
+    int *mesh_of = (int *)(d + dbl);
+    unsigned *flag = (unsigned *)mesh_of + n, *rank_all = flag + n, *rank_mesh = rank_all + n;
+    void *cub_tmp = (void *)(((uintptr_t)(rank_mesh + n) + 255) & ~(uintptr_t)255);
+    SplineDev sdv{};
+    sdv.n_seg = spl->n_seg;
+    sdv.spline_area = spl->spline_area;
+    const double *src[8] = {spl->x1, spl->y1, spl->x2, spl->y2, spl->nx, spl->ny, spl->area, spl->cum_area};
+    const double **dst[8] = {&sdv.x1, &sdv.y1, &sdv.x2, &sdv.y2, &sdv.nx, &sdv.ny, &sdv.area, &sdv.cum_area};
+    {
+        std::vector<double> h(8 * ns + 1);
+        size_t off = 0;
+        for (int k = 0; k < 8; k++) {
+            const size_t cnt = k == 7 ? ns + 1 : ns;
+            memcpy(h.data() + off, src[k], cnt * sizeof(double));
+            *dst[k] = sd + off;
+            off += cnt;
+        }
+        CU(cudaMemcpyAsync(sd, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream)); // h goes out of scope
+    }
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    k_source_uniform<<<grid, 256, 0, ctx->stream>>>(sdv, v_drift, dt_step, (unsigned long long)n, (unsigned long long)*rng_state, ctx->d_meshes, nmesh,
+                                                     x, y, z, u, v, w, mesh_of);
+    CU(cudaGetLastError());
+    k_source_flags<<<grid, 256, 0, ctx->stream>>>(mesh_of, (unsigned long long)n, -1, flag);
+    CU(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flag, rank_all, (int)n, ctx->stream));
+    unsigned last[2] = {0, 0};
+    CU(cudaMemcpyAsync(&last[0], rank_all + n - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&last[1], flag + n - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int64_t accepted = (int64_t)last[0] + last[1];
+    ctx->launch_total += 3;
+    int64_t added = 0;
+    for (int m = 0; m < nmesh && accepted > 0; m++) {
+        k_source_flags<<<grid, 256, 0, ctx->stream>>>(mesh_of, (unsigned long long)n, m, flag);
+        CU(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flag, rank_mesh, (int)n, ctx->stream));
+        CU(cudaMemcpyAsync(&last[0], rank_mesh + n - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&last[1], flag + n - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        const int64_t c = (int64_t)last[0] + last[1];
+        ctx->launch_total += 2;
+        if (c == 0) continue;
+        Pop &pop = s.pops[m];
+        FastStore &f = pop.fast;
+        int64_t want = f.n + c;
+        if (f.n == 0 && s.capacity_hint > want) want = s.capacity_hint;
+        rc = fast_reserve(ctx, f, want);
+        if (rc) return rc;
+        rc = rec_reserve(ctx, pop.cur, pop.cur.n + c, true);
+        if (rc) return rc;
+        k_source_append<<<grid, 256, 0, ctx->stream>>>(mesh_of, (unsigned long long)n, m, rank_mesh, rank_all, x, y, z, u, v, w, mpw, s.id_counter, born_it,
+                                                        f.p, (unsigned long long)f.n);
+        CU(cudaGetLastError());
+        ctx->launch_total++;
+        int64_t a = 0;
+        rc = inject_fast_run(ctx, s, m, c, dt_step, true, &a);
+        if (rc) return rc;
+        added += a;
+    }
+    s.id_counter += (int32_t)accepted; // KM:797: every particle that found a mesh took an id
+    *rng_state = sf_java_jump(*rng_state, 2ULL * (unsigned long long)num_mp);
     if (n_added) *n_added = added;
     return 0;
 }
