@@ -167,7 +167,8 @@ typedef struct sfgpu_spline {
     const double *cum_area;          /* n_seg + 1 entries, cum_area[0] = 0             */
     double spline_area;
 } sfgpu_spline;
-int sfgpu_source_uniform(sfgpu_ctx *ctx, int32_t sp, const sfgpu_spline *spline, double v_drift, double mpw, int32_t born_it,
+#define SFGPU_SOURCE_COLD_BEAM 1u /* ColdBeamSource.sampleParticle (sources/ColdBeamSource.java:56-76): the same sampling, vel[2] = 0 */
+int sfgpu_source_uniform(sfgpu_ctx *ctx, int32_t sp, const sfgpu_spline *spline, uint32_t flags, double v_drift, double mpw, int32_t born_it,
                          int64_t num_mp, double dt_step, uint64_t *rng_state, int64_t *n_added);
 
 /* closes a step opened with SFGPU_STEP_DEFER_FINISH: cross-GPU sum of the deposit and of the mover sums */

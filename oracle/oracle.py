@@ -98,7 +98,7 @@ def load():
     lib.sfo_java_next_double.restype = C.c_double
     lib.sfo_java_next_double.argtypes = [C.POINTER(C.c_uint64)]
     lib.sfo_uniform_source.restype = None
-    lib.sfo_uniform_source.argtypes = [C.POINTER(_Spline), C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(_Mesh), C.c_int,
+    lib.sfo_uniform_source.argtypes = [C.POINTER(_Spline), C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(_Mesh), C.c_int,
                                        _dp, _dp, _dp, _dp, _dp, _dp, _ip]
     _lib = lib
     return lib
@@ -225,7 +225,7 @@ class OracleKM:
         self.ms.refresh()
 
     # KM:759-802 + MeshData.addParticle KM:1356-1361
-    def sampleUniformSource(self, spline, v_drift, num_mp, dt, rng_state, mpw, born_it=0):
+    def sampleUniformSource(self, spline, v_drift, num_mp, dt, rng_state, mpw, born_it=0, cold_beam=False):
         """Source.sampleKinetic over UniformSource.sampleParticle: returns (particles added, new RNG state).
         Particles keep the order they were sampled in; ids count up over the accepted ones (KM:797)."""
         n = int(num_mp)
@@ -233,7 +233,7 @@ class OracleKM:
         mesh_of = np.zeros(n, np.int32)
         sp = _Spline(spline.n_seg, *[_d(getattr(spline, k)) for k in ("x1", "y1", "x2", "y2", "nx", "ny", "area", "cum_area")], spline.spline_area)
         st = C.c_uint64(int(rng_state))
-        self.lib.sfo_uniform_source(C.byref(sp), float(v_drift), float(dt), n, C.byref(st), self.ms.arr, len(self.meshes),
+        self.lib.sfo_uniform_source(C.byref(sp), int(bool(cold_beam)), float(v_drift), float(dt), n, C.byref(st), self.ms.arr, len(self.meshes),
                                     _d(x), _d(y), _d(z), _d(u), _d(v), _d(w), mesh_of.ctypes.data_as(_ip))
         acc = mesh_of >= 0
         ids = (self.id_counter + np.cumsum(acc) - 1).astype(np.int32)

@@ -423,7 +423,7 @@ void sfo_add_particles(const sfo_mesh *m, double qm, double dt, int compute_lc, 
 }
 
 /* ---------------------------------------------------------------------------------------------
- * particle injection by UniformSource on a Boundary of linear segments (XY domains)
+ * particle injection by UniformSource / ColdBeamSource on a Boundary of linear segments (XY domains)
  * ------------------------------------------------------------------------------------------- */
 
 /* java.util.Random: 48-bit LCG, next(bits) (the JDK's documented algorithm; Starfish.rnd() = random.nextDouble(),
@@ -461,7 +461,7 @@ static int vec_binary_search(const double *vec, int n, double val)
  * (LinearSegment.java:94-101, :20-45), the 1e-6*dt nudge off the surface (Source.java:186-188) and
  * DomainModule.getMesh (DomainModule.java:106-117: first mesh that strictly contains the point, else the first that
  * contains it within FLT_EPS).  Outputs the sampled particles in order and the mesh each one lands in (-1: dropped). */
-void sfo_uniform_source(const sfo_spline *s, double v_drift, double dt, int64_t num_mp, uint64_t *rng_state,
+void sfo_uniform_source(const sfo_spline *s, int cold_beam, double v_drift, double dt, int64_t num_mp, uint64_t *rng_state,
                         const sfo_mesh *meshes, int n_meshes, double *x, double *y, double *z, double *u, double *v,
                         double *w, int32_t *mesh_of)
 {
@@ -478,7 +478,8 @@ void sfo_uniform_source(const sfo_spline *s, double v_drift, double dt, int64_t 
         if (sn > s->n_seg - 1) sn = s->n_seg - 1;
         const double n[3] = {s->nx[sn], s->ny[sn], 0.0};
         double vel[3];
-        for (int k = 0; k < 3; k++) vel[k] = n[k] * v_drift;
+        for (int k = 0; k < 3; k++) vel[k] = n[k] * v_drift; /* UniformSource.java:68 */
+        if (cold_beam) vel[2] = 0; /* ColdBeamSource.java:69-71: the same sampling, vel[2] = 0 written out */
         for (int k = 0; k < 3; k++) pos[k] += vel[k] * 1e-6 * dt;
         int found = -1;
         for (int m = 0; m < n_meshes && found < 0; m++) { /* containsPosStrict, UM:164-171 */

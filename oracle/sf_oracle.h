@@ -90,7 +90,7 @@ typedef struct {
 uint64_t sfo_java_seed(int64_t seed);              /* java.util.Random.setSeed scrambling      */
 int32_t sfo_java_next_int(uint64_t *state);        /* java.util.Random.nextInt()               */
 double sfo_java_next_double(uint64_t *state);      /* java.util.Random.nextDouble()            */
-void sfo_uniform_source(const sfo_spline *s, double v_drift, double dt, int64_t num_mp, uint64_t *rng_state,
+void sfo_uniform_source(const sfo_spline *s, int cold_beam, double v_drift, double dt, int64_t num_mp, uint64_t *rng_state,
                         const sfo_mesh *meshes, int n_meshes, double *x, double *y, double *z, double *u, double *v,
                         double *w, int32_t *mesh_of);
 

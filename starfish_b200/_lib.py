@@ -17,6 +17,7 @@ FIELD_NAMES = ("den", "u", "v", "w", "uu", "vv", "ww", "mpc")
 
 INJECT_REWIND, INJECT_DEPOSIT_NOW, INJECT_TRANSFER = 1, 2, 4
 STEP_GENERIC, STEP_DEFER_FINISH, STEP_INPLACE, STEP_STREAM = 1, 2, 4, 8
+SOURCE_COLD_BEAM = 1
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -50,7 +51,7 @@ EXPORTS = {
     "sfgpu_set_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfgpu_species_add": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int64, c_int32_p]),
     "sfgpu_inject": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Particles), C.c_double, C.c_uint32, c_int64_p]),
-    "sfgpu_source_uniform": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(Spline), C.c_double, C.c_double, C.c_int32, C.c_int64, C.c_double,
+    "sfgpu_source_uniform": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(Spline), C.c_uint32, C.c_double, C.c_double, C.c_int32, C.c_int64, C.c_double,
                                       C.POINTER(C.c_uint64), c_int64_p]),
     "sfgpu_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_uint32]),
     "sfgpu_finish_step": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -1036,7 +1036,7 @@ extern "C" int sfgpu_inject(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const s
 // ---------------------------------------------------------------------------------------------
 // UniformSource sampled on the device (sf_source.cuh)
 // ---------------------------------------------------------------------------------------------
-extern "C" int sfgpu_source_uniform(sfgpu_ctx *ctx, int32_t sp, const sfgpu_spline *spl, double v_drift, double mpw, int32_t born_it,
+extern "C" int sfgpu_source_uniform(sfgpu_ctx *ctx, int32_t sp, const sfgpu_spline *spl, uint32_t flags, double v_drift, double mpw, int32_t born_it,
                                     int64_t num_mp, double dt_step, uint64_t *rng_state, int64_t *n_added)
 {
     CHECK_CTX();
@@ -1086,7 +1086,7 @@ extern "C" int sfgpu_source_uniform(sfgpu_ctx *ctx, int32_t sp, const sfgpu_spli
         CU(cudaStreamSynchronize(ctx->stream)); // h goes out of scope
     }
     const unsigned grid = (unsigned)((n + 255) / 256);
-    k_source_uniform<<<grid, 256, 0, ctx->stream>>>(sdv, v_drift, dt_step, (unsigned long long)n, (unsigned long long)*rng_state, ctx->d_meshes, nmesh,
+    k_source_uniform<<<grid, 256, 0, ctx->stream>>>(sdv, (flags & SFGPU_SOURCE_COLD_BEAM) ? 1 : 0, v_drift, dt_step, (unsigned long long)n, (unsigned long long)*rng_state, ctx->d_meshes, nmesh,
                                                      x, y, z, u, v, w, mesh_of);
     CU(cudaGetLastError());
     k_source_flags<<<grid, 256, 0, ctx->stream>>>(mesh_of, (unsigned long long)n, -1, flag);

@@ -1,4 +1,4 @@
-// sf_source.cuh -- SURVEY 8f-1: particle injection by the reference's UniformSource, sampled on the device.
+// sf_source.cuh -- SURVEY 8f-1: particle injection by the reference's UniformSource / ColdBeamSource, sampled on the device.
 //
 // Restates Source.sampleKinetic (core/source/Source.java:167-198) over UniformSource.sampleParticle
 // (sources/UniformSource.java:56-72) for a Boundary of linear segments in an XY domain: Spline.randomT (Spline.java:582-641),
@@ -65,7 +65,7 @@ __device__ __forceinline__ int sf_vec_binary_search(const double *__restrict__ v
 
 // one thread per sampled particle: position, velocity, and the mesh DomainModule.getMesh() picks (-1: outside every mesh)
 __global__ void __launch_bounds__(256)
-k_source_uniform(SplineDev s, double v_drift, double dt, unsigned long long n, unsigned long long rng_state, const MeshDev *__restrict__ meshes,
+k_source_uniform(SplineDev s, int cold_beam, double v_drift, double dt, unsigned long long n, unsigned long long rng_state, const MeshDev *__restrict__ meshes,
                  int n_meshes, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z, double *__restrict__ u,
                  double *__restrict__ v, double *__restrict__ w, int *__restrict__ mesh_of)
 {
@@ -86,6 +86,7 @@ k_source_uniform(SplineDev s, double v_drift, double dt, unsigned long long n, u
     double vel[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) vel[k] = nrm[k] * v_drift; // UniformSource.java:68
+    if (cold_beam) vel[2] = 0.0; // ColdBeamSource.java:69-71: the same sampling with vel[2] = 0 written out (+0 even for a negative drift)
 #pragma unroll
     for (int k = 0; k < 3; k++) pos[k] += vel[k] * 1e-6 * dt; // Source.java:186-188
     int found = -1;

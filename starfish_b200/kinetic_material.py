@@ -224,16 +224,16 @@ class KineticMaterial:
         self._check(self.lib.sfgpu_inject(self._ctx, self._sp, mesh.index, C.byref(v), float(dt), int(flags), C.byref(added)))
         return added.value
 
-    def sampleUniformSource(self, spline, v_drift, num_mp, rng_state, dt=None, mpw=None, born_it=0):
+    def sampleUniformSource(self, spline, v_drift, num_mp, rng_state, dt=None, mpw=None, born_it=0, cold_beam=False):
         """``Source.sampleKinetic`` over ``UniformSource.sampleParticle`` (Source.java:167-198, UniformSource.java:56-72) sampled
-        on the device with the draws of ``java.util.Random`` (SURVEY 8f-1).  ``spline``: a ``domain.LinearSpline``;
+        on the device with the draws of ``java.util.Random`` (SURVEY 8f-1); ``cold_beam``: ``ColdBeamSource.sampleParticle``.  ``spline``: a ``domain.LinearSpline``;
         ``rng_state``: the 48-bit internal state of the Random behind ``Starfish.rnd()``.  Returns (added, new state)."""
         dt = self.dt if dt is None else dt
         ptr = lambda a: a.ctypes.data_as(_lib.c_double_p)
         sp = _lib.Spline(int(spline.n_seg), *[ptr(getattr(spline, k)) for k in ("x1", "y1", "x2", "y2", "nx", "ny", "area", "cum_area")],
                          float(spline.spline_area))
         st, added = C.c_uint64(int(rng_state)), C.c_int64(0)
-        self._check(self.lib.sfgpu_source_uniform(self._ctx, self._sp, C.byref(sp), float(v_drift), float(self.spwt0 if mpw is None else mpw),
+        self._check(self.lib.sfgpu_source_uniform(self._ctx, self._sp, C.byref(sp), _lib.SOURCE_COLD_BEAM if cold_beam else 0, float(v_drift), float(self.spwt0 if mpw is None else mpw),
                                                   int(born_it), int(num_mp), float(dt), C.byref(st), C.byref(added)))
         return added.value, int(st.value)
 

@@ -501,14 +501,15 @@ class Spline:  # boundaries/Spline.java (linear segments, XY)
         return list(self.segments[si].normal)
 
 
-def uniform_source_sample(km, spline, v_drift, num_mp, dt, rnd, spwt0, born_it=0):
+def uniform_source_sample(km, spline, v_drift, num_mp, dt, rnd, spwt0, born_it=0, cold_beam=False):
     """Source.sampleKinetic (Source.java:167-198) with UniformSource.sampleParticle (sources/UniformSource.java:56-72) and
     KineticMaterial.addParticle(Particle) (KM:810-818) + DomainModule.getMesh (DomainModule.java:106-117)."""
     count = 0
     while num_mp > 0:
         t = spline.randomT(rnd)
         x, n = spline.pos(t), spline.normal(t)
-        part = Particle([x[0], x[1], 0.0], [n[k] * v_drift for k in range(3)], spwt0)
+        vel = [n[0] * v_drift, n[1] * v_drift, 0.0] if cold_beam else [n[k] * v_drift for k in range(3)]  # ColdBeamSource.java:56-76 / UniformSource.java:56-72
+        part = Particle([x[0], x[1], 0.0], vel, spwt0)
         part.born_it = born_it
         num_mp -= 1
         for k in range(3):

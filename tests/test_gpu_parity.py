@@ -329,8 +329,9 @@ def test_sort_interval_does_not_change_results(every, flags):
         compare_fields(km, ok)
 
 
+@pytest.mark.parametrize("cold,v_drift", [(False, 7000.0), (True, -7000.0)])
 @pytest.mark.parametrize("flags", PATHS)
-def test_device_side_uniform_source(flags):
+def test_device_side_uniform_source(flags, cold, v_drift):
     """UniformSource sampled on the device with java.util.Random's draws (LCG jump-ahead per particle) against the
     oracle's sequential loop: same particles in the same meshes with the same ids, same RNG state afterwards, and the same
     simulation when sampling and stepping alternate (inlet partly outside every mesh, two overlapping meshes)."""
@@ -338,13 +339,14 @@ def test_device_side_uniform_source(flags):
     a = S.make_mesh(21, 11, DomainType.XY, 5e-3, "open", x0=(-0.1, 0.0))
     b = S.make_mesh(11, 9, DomainType.XY, 5e-3, "open", x0=(-0.1, 0.05))
     wl = S.Workload("t", a, 1e-7, S.QE, 16 * S.AMU, 9, kick_frac=0.05)
-    sp = LinearSpline([(-0.1, 0.12), (-0.1, 0.03), (-0.09, -0.01), (-0.09, -0.02)])
+    pts = [(-0.1, 0.12), (-0.1, 0.03), (-0.09, -0.01), (-0.09, -0.02)]
+    sp = LinearSpline(pts if v_drift > 0 else pts[::-1])  # a negative drift along the flipped normal: -0.0 vs +0.0 in vel[2]
     km, ok = make_pair([a, b], wl, [None, None], flags, dom=DomainType.XY)
     state_g = state_o = O.java_seed(2026)
     with km:
         for it in range(6):
-            n_g, state_g = km.sampleUniformSource(sp, 7000.0, 3001, state_g, dt=wl.dt, mpw=1e3, born_it=it)
-            n_o, state_o = ok.sampleUniformSource(sp, 7000.0, 3001, wl.dt, state_o, 1e3, born_it=it)
+            n_g, state_g = km.sampleUniformSource(sp, v_drift, 3001, state_g, dt=wl.dt, mpw=1e3, born_it=it, cold_beam=cold)
+            n_o, state_o = ok.sampleUniformSource(sp, v_drift, 3001, wl.dt, state_o, 1e3, born_it=it, cold_beam=cold)
             assert n_g == n_o and state_g == state_o and 0 < n_g < 3001
             compare_state(km, ok)
             km.updateFields()

@@ -364,22 +364,27 @@ def test_kat_spline_random_t_and_binary_search():
     assert sp.normal(t) == [-1.0, 0.0, 0.0] and sp.pos(t)[0] == 1.0
 
 
-def test_oracle_uniform_source_matches_python_restatement():
+@pytest.mark.parametrize("cold,v_drift", [(False, 7000.0), (True, -7000.0), (False, -7000.0)])
+def test_oracle_uniform_source_matches_python_restatement(cold, v_drift):
     """Source.sampleKinetic over UniformSource.sampleParticle on a three-segment inlet, two meshes (one only reachable through
     containsPos), part of the inlet outside every mesh: positions, rewound velocities, ids, RNG state bit for bit."""
     from starfish_b200.domain import LinearSpline
     a = S.make_mesh(21, 11, DomainType.XY, 5e-3, "open", x0=(-0.1, 0.0))
     b = S.make_mesh(11, 9, DomainType.XY, 5e-3, "open", x0=(-0.1, 0.05))  # overlaps a: getMesh takes the first that contains the point
     pts = [(-0.1, 0.12), (-0.1, 0.03), (-0.09, -0.01), (-0.09, -0.02)]
+    if v_drift < 0:
+        pts = pts[::-1]  # flipped normal, negative drift: UniformSource gives vel[2] = -0.0, ColdBeamSource +0.0
     km = O.OracleKM(S.QE, 16 * S.AMU, [a, b])
     pk = pyref.KM(S.QE, 16 * S.AMU, [_py_mesh(a), _py_mesh(b)])
     rnd = pyref.JavaRandom(12345)
     state = O.java_seed(12345)
     for it in range(3):
-        n_o, state = km.sampleUniformSource(LinearSpline(pts), 7000.0, 257, 1e-7, state, 1e3, born_it=it)
-        n_p = pyref.uniform_source_sample(pk, pyref.Spline(pts), 7000.0, 257, 1e-7, rnd, 1e3, born_it=it)
+        n_o, state = km.sampleUniformSource(LinearSpline(pts), v_drift, 257, 1e-7, state, 1e3, born_it=it, cold_beam=cold)
+        n_p = pyref.uniform_source_sample(pk, pyref.Spline(pts), v_drift, 257, 1e-7, rnd, 1e3, born_it=it, cold_beam=cold)
         assert n_o == n_p and state == rnd.state and 0 < n_o < 257
         km.updateFields(1e-7)
         pk.updateFields(1e-7)
         _compare(km, pk, 2)
     assert km.getNp(0) > 0 and km.getNp(1) > 0
+    wz = km.sorted_parts(0)["w"]
+    assert np.all(np.signbit(wz) == (v_drift < 0 and not cold))  # the one observable difference between the two sources
