@@ -283,7 +283,10 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
     __shared__ __align__(8) unsigned long long sBar[2];
     __shared__ __align__(16) SDesc sDesc[3];
     __shared__ double sSums[5];
-    __shared__ int sNPieces, sNRows, sNFall, sBox[8], sNextPiece; // sBox: [2 sets][i min, i max, j min, j max]
+    __shared__ int sNRows, sNFall, sBox[8]; // sBox: [2 sets][i min, i max, j min, j max]
+#if SFS_DYNAMIC
+    __shared__ int sNextPiece;
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const MeshDev &m = a.b.m;
@@ -434,8 +437,9 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 }
                 if (c == SFS_NCELL - 1) { // inclusive totals
                     const unsigned rows = ic >> 22, pieces = (ic >> 12) & 0x3ffu;
+#if SFS_DYNAMIC
                     sNextPiece = 0;
-                    sNPieces = (int)pieces;
+#endif
                     sNRows = (int)rows;
                     rndStart[rows ? (rows + SFS_MAXP - 1) / SFS_MAXP : 1] = (unsigned short)pieces; // end of the last round
                     if (!rows) rndStart[0] = 0;
@@ -503,7 +507,9 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
             const int pbeg = rndStart[rnd], pend = rndStart[rnd + 1];
             if (rnd > 0) { // (round 0 was prepared before B3)
                 __syncthreads(); // S is reused
+#if SFS_DYNAMIC
                 if (tid == 0) sNextPiece = 0;
+#endif
                 sfs_zero_shared_rows(S, pcOrd, pbeg, pend, tid);
                 __syncthreads();
             }
