@@ -68,3 +68,61 @@ def test_cuda_reproduces_golden(path):
         got = {k: getattr(p, k) for k in ("id", "x", "y", "z", "u", "v", "w", "li", "lj", "dt")}
         sums = np.array([km.mass_sum, *km.momentum_sum, km.energy_sum]) / km.mass
         _check(g, got, km.last_deposit[0], sums, km.n_exited, theta_exact=m.domain_type == DomainType.XY)
+
+
+# ---------------------------------------------------------------- UniformSource / ColdBeamSource fixtures
+SRC_FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "source", "*.npz")))
+
+
+def _src_case(path):
+    from starfish_b200.domain import LinearSpline
+    g = np.load(path)
+    cold, seed, num_mp, steps = [int(v) for v in g["meta"]]
+    m = S.make_mesh(21, 11, DomainType.XY, 5e-3, "open", x0=(-0.1, 0.0))
+    m.efi, m.efj = g["efi"], g["efj"]
+    return g, m, LinearSpline(g["pts"]), bool(cold), seed, num_mp, steps
+
+
+def _src_check(g, got, raw, n_exited, state):
+    assert state == int(g["rng_state"])
+    assert np.array_equal(got["id"], g["id"]) and np.array_equal(got["born_it"], g["born_it"])
+    for key in ("x", "y", "z", "u", "v", "w"):
+        assert np.array_equal(got[key], g[key]) and np.array_equal(np.signbit(got[key]), np.signbit(g[key])), key
+    scale = np.abs(g["raw"]).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(raw - g["raw"]) <= 1e-10 * scale) and np.array_equal(raw[7], g["raw"][7])
+    assert n_exited == int(g["n_exited"])
+
+
+def test_source_fixtures_exist():
+    assert len(SRC_FIXTURES) >= 2
+
+
+@pytest.mark.parametrize("path", SRC_FIXTURES, ids=[os.path.basename(p)[:-4] for p in SRC_FIXTURES])
+def test_oracle_reproduces_source_golden(path):
+    from oracle import oracle as O
+    g, m, spline, cold, seed, num_mp, steps = _src_case(path)
+    ok = O.OracleKM(float(g["charge"]), float(g["mass"]), [m])
+    state = O.java_seed(seed)
+    for it in range(steps):
+        n, state = ok.sampleUniformSource(spline, float(g["v_drift"]), num_mp, float(g["dt"]), state, 1e3, born_it=it, cold_beam=cold)
+        assert n == int(g["added"][it])
+        ok.updateFields(float(g["dt"]))
+    _src_check(g, ok.sorted_parts(0), ok.raw[0], ok.n_exited, state)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [0, 8], ids=["default", "stream"])
+@pytest.mark.parametrize("path", SRC_FIXTURES, ids=[os.path.basename(p)[:-4] for p in SRC_FIXTURES])
+def test_cuda_reproduces_source_golden(path, flags):
+    from starfish_b200 import KineticMaterial
+    g, m, spline, cold, seed, num_mp, steps = _src_case(path)
+    with KineticMaterial("ion", float(g["charge"]), float(g["mass"]), [m], m.domain_type, step_flags=flags) as km:
+        km.dt = float(g["dt"])
+        state = (seed ^ 0x5DEECE66D) & ((1 << 48) - 1)  # java.util.Random.setSeed scrambling
+        for it in range(steps):
+            n, state = km.sampleUniformSource(spline, float(g["v_drift"]), num_mp, state, mpw=1e3, born_it=it, cold_beam=cold)
+            assert n == int(g["added"][it])
+            km.updateFields()
+        p = km.getParticles(m).sorted_by_id()
+        got = {k: getattr(p, k) for k in ("id", "born_it", "x", "y", "z", "u", "v", "w")}
+        _src_check(g, got, km.last_deposit[0], km.n_exited, state)
