@@ -152,18 +152,18 @@ int sfgpu_inject(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const sfgpu_partic
  * cross-GPU sum of the deposit when a communicator is attached. */
 int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags);
 /* Source.sampleKinetic over UniformSource.sampleParticle (core/source/Source.java:167-198,
- * sources/UniformSource.java:56-72) sampled on the device, for a Boundary of linear segments in an XY domain.  The caller passes
+ * sources/UniformSource.java:56-72) sampled on the device, for a Boundary of linear segments (XY; RZ / ZR with the secant search of Spline.java:594-637).  The caller passes
  * the Spline as the Java object holds it (segment end points, LinearSegment.normal, Segment.area, cum_area, spline_area) and the
  * 48-bit internal state of the java.util.Random behind Starfish.rnd(); particle p uses draws 2p, 2p+1 of that stream, so the
  * particles are the ones the sequential Java loop would create, and *rng_state returns advanced by 2*num_mp draws.  Each particle
  * gets pos = spline.pos(t) + vel*1e-6*dt, vel = normal*v_drift, mpw (the material's spwt0), born_it, lands in the mesh
  * DomainModule.getMesh picks (dropped when none contains it) and then goes through addParticle(md, part) (KM:759-802: XtoL,
- * -0.5dt rewind, id = part_id_counter++).  Axisymmetric domains (iterative randomT, Spline.java:594-637) return SFGPU_EINVAL. */
+ * -0.5dt rewind, id = part_id_counter++). */
 typedef struct sfgpu_spline {
     int32_t n_seg;
     const double *x1, *y1, *x2, *y2; /* LinearSegment end points, n_seg each           */
     const double *nx, *ny;           /* LinearSegment.normal[0..1]                     */
-    const double *area;              /* Segment.area (XY: the segment length)          */
+    const double *area;              /* Segment.area = area(1): XY length, RZ / ZR frustum area */
     const double *cum_area;          /* n_seg + 1 entries, cum_area[0] = 0             */
     double spline_area;
 } sfgpu_spline;

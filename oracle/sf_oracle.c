@@ -461,20 +461,62 @@ static int vec_binary_search(const double *vec, int n, double val)
  * (LinearSegment.java:94-101, :20-45), the 1e-6*dt nudge off the surface (Source.java:186-188) and
  * DomainModule.getMesh (DomainModule.java:106-117: first mesh that strictly contains the point, else the first that
  * contains it within FLT_EPS).  Outputs the sampled particles in order and the mesh each one lands in (-1: dropped). */
+/* LinearSegment.area(t), LinearSegment.java:50-80: swept area up to t (XY: t*length; RZ / ZR: lateral area of the conical frustum) */
+static double seg_area(const sfo_spline *s, int i, double t, int domain_type)
+{
+    if (domain_type == SFO_XY) return t * s->area[i]; /* length = area(1) */
+    const double px = s->x1[i] + t * (s->x2[i] - s->x1[i]), py = s->y1[i] + t * (s->y2[i] - s->y1[i]);
+    double r1, z1, r2, z2;
+    if (domain_type == SFO_RZ) { r1 = s->x1[i]; z1 = s->y1[i]; r2 = px; z2 = py; }
+    else { r1 = s->y1[i]; z1 = s->x1[i]; r2 = py; z2 = px; }
+    const double dr = r1 - r2, dz = z1 - z2;
+    double A = M_PI * (r1 + r2) * sqrt(dr * dr + dz * dz);
+    if (A < 0) A *= -1.0;
+    return A;
+}
+
+/* Spline.randomT, Spline.java:582-641: XY takes the area fraction; axisymmetric domains search the t that sweeps the wanted
+ * area with <= 10 secant steps (quirk kept: when the first guess is already within tolerance the result is x0 + (f_goal - f0)) */
+static double spline_random_t(const sfo_spline *s, uint64_t *rng_state, int domain_type)
+{
+    const double A1 = sfo_java_next_double(rng_state) * s->spline_area;
+    const int i = vec_binary_search(s->cum_area, s->n_seg + 1, A1);
+    const double area = s->area[i];
+    double frac = (A1 - s->cum_area[i]) / area;
+    if (domain_type != SFO_XY) {
+        enum { max_steps = 10 };
+        const double tol = 1e-6;
+        double x[max_steps], f[max_steps];
+        const double f_goal = frac * area;
+        x[0] = frac;
+        f[0] = seg_area(s, i, x[0], domain_type);
+        double diff = fabs(f[0] - f_goal) / area;
+        int k = 1;
+        x[1] = x[0] + (f_goal - f[0]);
+        f[1] = 0;
+        if (diff > tol) f[1] = seg_area(s, i, x[1], domain_type);
+        while (diff > tol && k < max_steps - 1) {
+            x[k + 1] = (x[k] - x[k - 1]) * (f_goal - f[k - 1]) / (f[k] - f[k - 1]) + x[k - 1];
+            f[k + 1] = seg_area(s, i, x[k + 1], domain_type);
+            diff = fabs(f[k + 1] - f_goal) / area;
+            k++;
+        }
+        frac = x[k];
+    }
+    return i + frac;
+}
+
 void sfo_uniform_source(const sfo_spline *s, int cold_beam, double v_drift, double dt, int64_t num_mp, uint64_t *rng_state,
                         const sfo_mesh *meshes, int n_meshes, double *x, double *y, double *z, double *u, double *v,
                         double *w, int32_t *mesh_of)
 {
     for (int64_t q = 0; q < num_mp; q++) {
-        const double A1 = sfo_java_next_double(rng_state) * s->spline_area;
-        const int i = vec_binary_search(s->cum_area, s->n_seg + 1, A1);
-        const double frac = (A1 - s->cum_area[i]) / s->area[i];
-        const double t = i + frac;
-        int si = (int)t; /* Spline.pos */
+        const double t = spline_random_t(s, rng_state, n_meshes > 0 ? meshes[0].domain_type : SFO_XY);
+        int si = j2i(t); /* Spline.pos */
         double seg_t = t - si;
         if (si > s->n_seg - 1) { si = s->n_seg - 1; seg_t = 1.0; }
         double pos[3] = {s->x1[si] + seg_t * (s->x2[si] - s->x1[si]), s->y1[si] + seg_t * (s->y2[si] - s->y1[si]), 0.0};
-        int sn = (int)t; /* Spline.normal */
+        int sn = j2i(t); /* Spline.normal */
         if (sn > s->n_seg - 1) sn = s->n_seg - 1;
         const double n[3] = {s->nx[sn], s->ny[sn], 0.0};
         double vel[3];

@@ -1043,7 +1043,6 @@ extern "C" int sfgpu_source_uniform(sfgpu_ctx *ctx, int32_t sp, const sfgpu_spli
     CHECK_SP();
     if (n_added) *n_added = 0;
     if (!spl || !rng_state) return fail(ctx, SFGPU_EINVAL, "sfgpu_source_uniform: spline and rng_state are required");
-    if (ctx->domain != SFGPU_XY) return fail(ctx, SFGPU_EINVAL, "sfgpu_source_uniform: Spline.randomT searches iteratively in axisymmetric domains; sample those on the host");
     if (spl->n_seg < 1 || !spl->x1 || !spl->y1 || !spl->x2 || !spl->y2 || !spl->nx || !spl->ny || !spl->area || !spl->cum_area)
         return fail(ctx, SFGPU_EINVAL, "sfgpu_source_uniform: incomplete spline");
     if (num_mp < 0 || num_mp >= (1LL << 31)) return fail(ctx, SFGPU_EINVAL, "sfgpu_source_uniform: bad particle count");
@@ -1086,7 +1085,7 @@ extern "C" int sfgpu_source_uniform(sfgpu_ctx *ctx, int32_t sp, const sfgpu_spli
         CU(cudaStreamSynchronize(ctx->stream)); // h goes out of scope
     }
     const unsigned grid = (unsigned)((n + 255) / 256);
-    k_source_uniform<<<grid, 256, 0, ctx->stream>>>(sdv, (flags & SFGPU_SOURCE_COLD_BEAM) ? 1 : 0, v_drift, dt_step, (unsigned long long)n, (unsigned long long)*rng_state, ctx->d_meshes, nmesh,
+    k_source_uniform<<<grid, 256, 0, ctx->stream>>>(sdv, ctx->domain, (flags & SFGPU_SOURCE_COLD_BEAM) ? 1 : 0, v_drift, dt_step, (unsigned long long)n, (unsigned long long)*rng_state, ctx->d_meshes, nmesh,
                                                      x, y, z, u, v, w, mesh_of);
     CU(cudaGetLastError());
     k_source_flags<<<grid, 256, 0, ctx->stream>>>(mesh_of, (unsigned long long)n, -1, flag);

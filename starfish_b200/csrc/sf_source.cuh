@@ -1,7 +1,7 @@
 // sf_source.cuh -- SURVEY 8f-1: particle injection by the reference's UniformSource / ColdBeamSource, sampled on the device.
 //
 // Restates Source.sampleKinetic (core/source/Source.java:167-198) over UniformSource.sampleParticle
-// (sources/UniformSource.java:56-72) for a Boundary of linear segments in an XY domain: Spline.randomT (Spline.java:582-641),
+// (sources/UniformSource.java:56-72) for a Boundary of linear segments (XY, RZ and ZR domains): Spline.randomT (Spline.java:582-641),
 // Vec.binarySearch (Vec.java:529-546), Spline.pos / normal (:700-707, :947-954), LinearSegment.pos (LinearSegment.java:94-101),
 // the 1e-6*dt nudge off the surface, DomainModule.getMesh (DomainModule.java:106-117).  The random numbers are those of
 // java.util.Random: particle p of a call uses draws 2p and 2p+1 of the stream (nextDouble = next(26), next(27)), reached by
@@ -63,19 +63,55 @@ __device__ __forceinline__ int sf_vec_binary_search(const double *__restrict__ v
     }
 }
 
+// LinearSegment.area(t), LinearSegment.java:50-80: area swept up to t (XY: t*length; RZ / ZR: lateral area of the conical frustum)
+__device__ __forceinline__ double sf_seg_area(const SplineDev &s, int i, double t, int domain)
+{
+    if (domain == SFGPU_XY) return t * s.area[i];
+    const double px = s.x1[i] + t * (s.x2[i] - s.x1[i]), py = s.y1[i] + t * (s.y2[i] - s.y1[i]);
+    double r1, z1, r2, z2;
+    if (domain == SFGPU_RZ) { r1 = s.x1[i]; z1 = s.y1[i]; r2 = px; z2 = py; }
+    else { r1 = s.y1[i]; z1 = s.x1[i]; r2 = py; z2 = px; }
+    const double dr = r1 - r2, dz = z1 - z2;
+    double A = 3.141592653589793 * (r1 + r2) * sqrt(dr * dr + dz * dz); // Math.PI
+    if (A < 0) A *= -1.0;
+    return A;
+}
+
+// Spline.randomT, Spline.java:582-641.  XY: segment + area fraction.  Axisymmetric: <= 10 secant steps towards the t that sweeps
+// the sampled area (quirk kept: an already converged first guess returns x0 + (f_goal - f0)).
+__device__ __forceinline__ double sf_spline_random_t(const SplineDev &s, unsigned long long &st, int domain)
+{
+    const double A1 = sf_java_next_double(st) * s.spline_area;
+    const int i = sf_vec_binary_search(s.cum_area, s.n_seg + 1, A1);
+    const double area = s.area[i];
+    double frac = (A1 - s.cum_area[i]) / area;
+    if (domain != SFGPU_XY) {
+        const double tol = 1e-6, f_goal = frac * area;
+        double x0 = frac, f0 = sf_seg_area(s, i, x0, domain); // x[k-1], f[k-1]
+        double diff = fabs(f0 - f_goal) / area;
+        double x1 = x0 + (f_goal - f0), f1 = 0;               // x[k], f[k]
+        if (diff > tol) f1 = sf_seg_area(s, i, x1, domain);
+        for (int k = 1; diff > tol && k < 9; k++) {
+            const double x2 = (x1 - x0) * (f_goal - f0) / (f1 - f0) + x0;
+            const double f2 = sf_seg_area(s, i, x2, domain);
+            diff = fabs(f2 - f_goal) / area;
+            x0 = x1; f0 = f1; x1 = x2; f1 = f2;
+        }
+        frac = x1;
+    }
+    return i + frac;
+}
+
 // one thread per sampled particle: position, velocity, and the mesh DomainModule.getMesh() picks (-1: outside every mesh)
 __global__ void __launch_bounds__(256)
-k_source_uniform(SplineDev s, int cold_beam, double v_drift, double dt, unsigned long long n, unsigned long long rng_state, const MeshDev *__restrict__ meshes,
+k_source_uniform(SplineDev s, int domain, int cold_beam, double v_drift, double dt, unsigned long long n, unsigned long long rng_state, const MeshDev *__restrict__ meshes,
                  int n_meshes, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z, double *__restrict__ u,
                  double *__restrict__ v, double *__restrict__ w, int *__restrict__ mesh_of)
 {
     const unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     unsigned long long st = sf_java_jump(rng_state, 2ULL * q);
-    const double A1 = sf_java_next_double(st) * s.spline_area;
-    const int i = sf_vec_binary_search(s.cum_area, s.n_seg + 1, A1);
-    const double frac = (A1 - s.cum_area[i]) / s.area[i];
-    const double t = i + frac;
+    const double t = sf_spline_random_t(s, st, domain);
     int si = sf_j2i(t); // Spline.pos
     double seg_t = t - si;
     if (si > s.n_seg - 1) { si = s.n_seg - 1; seg_t = 1.0; }

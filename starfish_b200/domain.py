@@ -168,9 +168,10 @@ class LinearSpline:
     """A Boundary made of linear segments as the reference's ``Spline`` holds it for an XY domain: per segment the end
     points, ``LinearSegment.normal`` = (-dy, dx, 0)/length (LinearSegment.java:20-45) and ``area`` = length
     (LinearSegment.area, XY), plus ``cum_area`` and ``spline_area`` (Spline.java).  Geometry set-up stays in Java; this
-    mirror only builds the INPUT of the source sampling for the tests and examples."""
+    mirror only builds the INPUT of the source sampling for the tests and examples.  (pos(1) = x1 + 1*(x2 - x1) is used for the
+    axisymmetric area, like LinearSegment.area(1).)"""
 
-    def __init__(self, points):
+    def __init__(self, points, domain_type=DomainType.XY):
         pts = np.asarray(points, np.float64)
         assert pts.ndim == 2 and pts.shape[1] == 2 and len(pts) >= 2
         self.x1, self.y1 = np.ascontiguousarray(pts[:-1, 0]), np.ascontiguousarray(pts[:-1, 1])
@@ -179,7 +180,13 @@ class LinearSpline:
         length = np.sqrt(dx * dx + dy * dy)
         dx, dy = dx / length, dy / length
         self.nx, self.ny = np.ascontiguousarray(-dy), np.ascontiguousarray(dx)
-        self.area = np.ascontiguousarray(length)  # XY: t*length at t = 1
+        if domain_type == DomainType.XY:
+            self.area = np.ascontiguousarray(length)  # LinearSegment.area(1) = length
+        else:  # lateral area of the conical frustum swept by the segment, LinearSegment.java:62-79
+            px, py = self.x1 + 1.0 * (self.x2 - self.x1), self.y1 + 1.0 * (self.y2 - self.y1)  # pos(1), not x2: same rounding as the Java
+            r1, z1, r2, z2 = (self.x1, self.y1, px, py) if domain_type == DomainType.RZ else (self.y1, self.x1, py, px)
+            dr, dz = r1 - r2, z1 - z2
+            self.area = np.ascontiguousarray(np.abs(np.pi * (r1 + r2) * np.sqrt(dr * dr + dz * dz)))
         self.cum_area = np.zeros(len(length) + 1)
         for k in range(len(length)):  # sequential sum, like the Java loop
             self.cum_area[k + 1] = self.cum_area[k] + self.area[k]

@@ -444,6 +444,20 @@ class JavaRandom:
 
 
 class LinearSegment:  # boundaries/LinearSegment.java:20-101
+    domain_type = XY  # Starfish.getDomainType()
+
+    def area_to(self, t):  # LinearSegment.area(t), :50-80
+        if self.domain_type == XY:
+            return t * self.length
+        pos = self.pos(t)
+        if self.domain_type == RZ:
+            r1, z1, r2, z2 = self.x1[0], self.x1[1], pos[0], pos[1]
+        else:
+            r1, z1, r2, z2 = self.x1[1], self.x1[0], pos[1], pos[0]
+        dr, dz = r1 - r2, z1 - z2
+        A = math.pi * (r1 + r2) * math.sqrt(dr * dr + dz * dz)
+        return -A if A < 0 else A
+
     def __init__(self, x1, x2):
         self.x1, self.x2 = [float(x1[0]), float(x1[1])], [float(x2[0]), float(x2[1])]
         dx, dy = self.x2[0] - self.x1[0], self.x2[1] - self.x1[1]
@@ -451,15 +465,17 @@ class LinearSegment:  # boundaries/LinearSegment.java:20-101
         dx /= self.length
         dy /= self.length
         self.normal = [-dy, dx, 0.0]
-        self.area = 1.0 * self.length  # area(1) in XY
+        self.area = self.area_to(1.0)  # Segment.area = area(1)
 
     def pos(self, t):
         return [self.x1[0] + t * (self.x2[0] - self.x1[0]), self.x1[1] + t * (self.x2[1] - self.x1[1]), 0.0]
 
 
-class Spline:  # boundaries/Spline.java (linear segments, XY)
-    def __init__(self, points):
-        self.segments = [LinearSegment(points[k], points[k + 1]) for k in range(len(points) - 1)]
+class Spline:  # boundaries/Spline.java (linear segments)
+    def __init__(self, points, domain_type=XY):
+        self.domain_type = domain_type
+        seg_cls = type("LinearSegment%d" % domain_type, (LinearSegment,), {"domain_type": domain_type})
+        self.segments = [seg_cls(points[k], points[k + 1]) for k in range(len(points) - 1)]
         self.cum_area = [0.0]
         for s in self.segments:
             self.cum_area.append(self.cum_area[-1] + s.area)
@@ -483,21 +499,40 @@ class Spline:  # boundaries/Spline.java (linear segments, XY)
             if i2 - i1 <= 1:
                 return i1
 
-    def randomT(self, rnd):  # Spline.java:582-641, XY branch
+    def randomT(self, rnd):  # Spline.java:582-641
         A1 = rnd.nextDouble() * self.spline_area
         i = self.binarySearch(self.cum_area, A1)
-        frac = (A1 - self.cum_area[i]) / self.segments[i].area
+        seg = self.segments[i]
+        seg_area = seg.area
+        frac = (A1 - self.cum_area[i]) / seg_area
+        if self.domain_type != XY:  # search the t that sweeps the wanted area (:594-637)
+            max_steps, tol = 10, 1e-6
+            x, f = [0.0] * max_steps, [0.0] * max_steps
+            f_goal = frac * seg_area
+            x[0] = frac
+            f[0] = seg.area_to(x[0])
+            diff = abs(f[0] - f_goal) / seg_area
+            k = 1
+            x[1] = x[0] + (f_goal - f[0])
+            if diff > tol:
+                f[1] = seg.area_to(x[1])
+            while diff > tol and k < max_steps - 1:
+                x[k + 1] = (x[k] - x[k - 1]) * (f_goal - f[k - 1]) / (f[k] - f[k - 1]) + x[k - 1]
+                f[k + 1] = seg.area_to(x[k + 1])
+                diff = abs(f[k + 1] - f_goal) / seg_area
+                k += 1
+            frac = x[k]
         return i + frac
 
     def pos(self, t):  # Spline.java:700-707
-        si = int(t)
+        si = jint(t)
         seg_t = t - si
         if si > len(self.segments) - 1:
             si, seg_t = len(self.segments) - 1, 1.0
         return self.segments[si].pos(seg_t)
 
     def normal(self, t):  # Spline.java:947-954
-        si = min(int(t), len(self.segments) - 1)
+        si = min(jint(t), len(self.segments) - 1)
         return list(self.segments[si].normal)
 
 

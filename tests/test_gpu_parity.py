@@ -358,6 +358,29 @@ def test_device_side_uniform_source(flags, cold, v_drift):
 
 
 @pytest.mark.parametrize("flags", BOTH)
+@pytest.mark.parametrize("dom", [DomainType.RZ, DomainType.ZR])
+def test_device_side_uniform_source_axisymmetric(dom, flags):
+    """Spline.randomT in RZ / ZR (secant search over the frustum area, Spline.java:594-637) on the device against the oracle."""
+    from starfish_b200.domain import LinearSpline
+    m = S.make_mesh(21, 31, dom, 1e-3, "open")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 9, kick_frac=0.05)
+    pts = [(0.0021, 1e-9), (0.0102, 1e-9), (0.0198, 0.0007)] if dom == DomainType.RZ else [(1e-9, 0.0198), (1e-9, 0.0102), (0.0007, 0.0021)]
+    sp = LinearSpline(pts, dom)
+    km, ok = make_pair([m], wl, [None], flags, dom=dom)
+    state_g = state_o = O.java_seed(99)
+    with km:
+        for it in range(5):
+            n_g, state_g = km.sampleUniformSource(sp, 5000.0, 2500, state_g, dt=wl.dt, mpw=1e3, born_it=it)
+            n_o, state_o = ok.sampleUniformSource(sp, 5000.0, 2500, wl.dt, state_o, 1e3, born_it=it)
+            assert n_g == n_o > 0 and state_g == state_o
+            compare_state(km, ok)
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            compare_state(km, ok)
+            compare_fields(km, ok)
+
+
+@pytest.mark.parametrize("flags", BOTH)
 def test_restart_records_round_trip(flags):
     """restart.bin particle section (KM:904-1000): the saved bytes are the DataOutputStream layout (checked with Python's
     big-endian struct), and loading them goes through addParticle like the reference (rewind re-applied, ids renumbered)."""

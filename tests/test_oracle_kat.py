@@ -364,6 +364,30 @@ def test_kat_spline_random_t_and_binary_search():
     assert sp.normal(t) == [-1.0, 0.0, 0.0] and sp.pos(t)[0] == 1.0
 
 
+@pytest.mark.parametrize("dom", [DomainType.RZ, DomainType.ZR])
+def test_oracle_uniform_source_axisymmetric_matches_python_restatement(dom):
+    """Spline.randomT in RZ / ZR: secant search for the t that sweeps the sampled area of the conical frustum
+    (Spline.java:594-637, LinearSegment.area :50-80), incl. the quirk of the already-converged first guess."""
+    from starfish_b200.domain import LinearSpline
+    m = S.make_mesh(21, 31, dom, 1e-3, "open")
+    pts = [(0.0021, 1e-9), (0.0102, 1e-9), (0.0198, 0.0007)] if dom == DomainType.RZ else [(1e-9, 0.0198), (1e-9, 0.0102), (0.0007, 0.0021)]
+    km = O.OracleKM(S.QE, 16 * S.AMU, [m])
+    pk = pyref.KM(S.QE, 16 * S.AMU, [_py_mesh(m)])
+    rnd, state = pyref.JavaRandom(7), O.java_seed(7)
+    sp_o, sp_p = LinearSpline(pts, dom), pyref.Spline(pts, int(dom))
+    assert np.array_equal(sp_o.area, [s_.area for s_ in sp_p.segments]) and sp_o.spline_area == sp_p.spline_area
+    for it in range(3):
+        n_o, state = km.sampleUniformSource(sp_o, 5000.0, 301, 1e-7, state, 1e3, born_it=it)
+        n_p = pyref.uniform_source_sample(pk, sp_p, 5000.0, 301, 1e-7, rnd, 1e3, born_it=it)
+        assert n_o == n_p > 0 and state == rnd.state
+        km.updateFields(1e-7)
+        pk.updateFields(1e-7)
+        _compare(km, pk, 1)
+    # area-weighted sampling: more particles at large r
+    r = km.sorted_parts(0)["x" if dom == DomainType.RZ else "y"]
+    assert np.mean(r > 0.011) > 0.6
+
+
 @pytest.mark.parametrize("cold,v_drift", [(False, 7000.0), (True, -7000.0), (False, -7000.0)])
 def test_oracle_uniform_source_matches_python_restatement(cold, v_drift):
     """Source.sampleKinetic over UniformSource.sampleParticle on a three-segment inlet, two meshes (one only reachable through
