@@ -114,6 +114,7 @@ struct FastStore { // cell-sorted SoA store of the normal particles of one speci
     // streaming step (sf_stream.cuh): histogram accumulated for the next launch, output segment offsets, output cursors
     unsigned *hist_next = nullptr, *offs_out = nullptr, *cursor = nullptr;
     bool stream_ok = false; // hist counts every live particle of p[0,n) and offs describes p[0,n_sorted)
+    bool tiled_ok = false;  // items/offs describe the interleaved layout fast_sort writes (what k_fast_step expects)
     WorkItem *items = nullptr;
     unsigned *d_nitems = nullptr;
     unsigned max_items = 0, n_items = 0;
@@ -186,6 +187,7 @@ struct sfgpu_ctx {
     bool timing_valid = false;
     int sort_every = 3;      // steps between cell sorts of the fast store (2..5 give the same step time on config B; 3 keeps the kernel on a fresher order)
     int fast_grid = 0;       // CTAs of the tiled kernel (persistent)
+    void (*fast_kernel)(const FastStepArgs, const FastStepArgs *) = nullptr; // k_fast_step of the context's domain type
     int path = 0;            // default step kernel: 0 = tiled in-place step + periodic sort (sf_fast.cuh), 1 = streaming step (sf_stream.cuh)
     int stream_grid = 0;     // CTAs of the streaming kernel (persistent)
     bool hybrid = false;     // tiled path: run the step in which a re-sort is due with the streaming kernel instead of sorting separately
@@ -377,6 +379,7 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     f.n_items = tot[1] < f.max_items ? tot[1] : f.max_items;
     f.dirty = false;
     f.stream_ok = true; // hist = live particles per key, offs = their segment offsets
+    f.tiled_ok = true;
     return 0;
 }
 
@@ -455,6 +458,7 @@ static int fast_resort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     f.dirty = false;
     f.steps_since_sort = 0;
     f.stream_ok = true;
+    f.tiled_ok = false;
     return 0;
 }
 
@@ -480,7 +484,7 @@ static FastStepArgs fast_args(sfgpu_ctx *ctx, Species &s, int m, double dt, cons
     a.m = ctx->meshes[m].dev; a.meshes = ctx->d_meshes; a.mesh_id = m; a.qm = s.qm; a.charge = s.charge; a.dt = dt;
     a.fs = pop.fast.p; a.items = pop.fast.items; a.n_items = pop.fast.d_nitems; a.ntj = pop.fast.ntj;
     a.exc = pop.nxt.p; a.exc_cap = (unsigned long long)pop.nxt.cap;
-    a.xfer = ctx->d_xfer; a.slow = slow; a.dep = pop.dep; a.c = ctx->d_cnt;
+    a.xfer = ctx->d_xfer; a.slow = slow; a.dep = pop.dep; a.c = ctx->d_cnt; a.offs = pop.fast.offs;
     return a;
 }
 
@@ -570,10 +574,11 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaMalloc(&ctx->d_xfer, sizeof(XferDev) * SF_MAX_MESHES));
         CU(cudaMalloc(&ctx->d_args, sizeof(FastStepArgs) * SF_MAX_MESHES));
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
-        CU(cudaFuncSetAttribute(k_fast_step, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
+        ctx->fast_kernel = domain_type == SFGPU_XY ? k_fast_step<SFGPU_XY> : (domain_type == SFGPU_RZ ? k_fast_step<SFGPU_RZ> : k_fast_step<SFGPU_ZR>);
+        CU(cudaFuncSetAttribute(ctx->fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         int nsm = 0, per_sm = 0;
         CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_step, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctx->fast_kernel, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         if (per_sm < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
         ctx->fast_grid = nsm * per_sm;
         if (const char *e = getenv("SFGPU_FAST_GRID")) ctx->fast_grid = atoi(e) > 0 ? atoi(e) : ctx->fast_grid; // occupancy experiments
@@ -1215,8 +1220,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         f.stream_ok = false; // the in-place step moves particles between cells without telling the histogram
         if (f.n == 0) continue;
         const int64_t tail = f.n - f.n_sorted;
-        if (f.n_sorted == 0 || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n || ctx->force_sort) {
-            rc = fast_resort(ctx, m, f); // streaming re-sort when the store is still roughly ordered, counting sort otherwise
+        if (f.n_sorted == 0 || !f.tiled_ok || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n || ctx->force_sort) {
+            rc = fast_sort(ctx, m, f); // (also after a streaming step: its output is not in the interleaved item layout)
             if (rc) return rc;
             f.stream_ok = false;
         }
@@ -1326,7 +1331,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             int64_t tail_first = 0;
             if (!untiled && f.n_sorted > 0 && f.n_items > 0) {
                 CU(cudaMemcpyAsync(ctx->d_args + m, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
-                k_fast_step<<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                ctx->fast_kernel<<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
                 tail_first = f.n_sorted;
@@ -1410,6 +1415,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             f.n = fn;
             f.n_sorted = n_sorted;
             f.stream_ok = true;
+            f.tiled_ok = false;
             f.steps_since_sort = 1; // the output is ordered by the cell each particle had BEFORE this push
             if (ctx->path == 0) f.n_items = ctx->h_cnt2[m] < f.max_items ? ctx->h_cnt2[m] : f.max_items;
         } else {
