@@ -19,34 +19,34 @@
 #pragma once
 #include "sf_generic.cuh"
 
-#ifndef SF_FAST_WARPS
-#define SF_FAST_WARPS 4 // warps per CTA of the tiled kernel
+#ifndef SF_FAST_PAIRS
+#define SF_FAST_PAIRS 4 // (push warp, deposit warp) pairs per CTA of the tiled kernel: warps 0..P-1 push, warps P..2P-1 deposit
 #endif
+#define SF_FAST_THREADS (2 * SF_FAST_PAIRS * 32)
 #ifndef SF_FAST_MIN_CTAS
-#define SF_FAST_MIN_CTAS 3
+#define SF_FAST_MIN_CTAS 2
 #endif
 #define SF_FHALO 1 // cells kept around the 8x8 tile: the 3x3-cell window around any cell of the tile stays inside
-#define SF_FNT (SF_TILE + 2 * SF_FHALO + 1) // nodes per edge of the warp tile
+#define SF_FNT (SF_TILE + 2 * SF_FHALO + 1) // nodes per edge of the deposit warp's tile
 #define SF_TILE_DOUBLES (SFGPU_NFIELDS * SF_FNT * SF_FNT)
-#ifndef SF_STAGE
-#define SF_STAGE 0 // 1: cp.async prefetch of the next batch through shared memory; 0: plain loads, 3.5 KB less per warp
-#endif
 #ifndef SF_INTERLEAVE
 #define SF_INTERLEAVE 1 // the sort interleaves every work item eight ways (one run per deposit quad)
 #endif
-#define SF_EXTRA 6 // per-warp sums next to the tile: (unused), fallback N/Px/Py/Pz/E
-// deposit operands of one 32-particle batch, published by the push lanes for the deposit quads:
-//   wi = (1-di, di), wj = (1-dj, dj) (Ruyten-corrected, F2D:265-283), values 0..5 as three pairs, value 6, packed cell
-#define SF_SCR_DOUBLES (32 * (6 + 6 + 7) + 16) // weight rows [0,0,w0,w1,0,0] per axis, 7 values, packed cell
-#define SF_NOFFS (SF_TILE * SF_TILE + 4)
+#define SF_EXTRA 6 // per-warp sums of particles that missed the tile: [1..5] = N, Px, Py, Pz, (E)
+// deposit operands of one 32-particle batch, published by the push warp for the deposit quads (two buffers per pair):
+//   per slot: weight rows [0,0,1-d,d,0,0] per axis (Ruyten-corrected, F2D:265-283), 7 values, packed cell; then a header
+#define SF_BUF_DOUBLES (32 * (6 + 6 + 7) + 16 + 4)
+#define SF_NOFFS (SF_TILE * SF_TILE + 4) // cell boundaries of the item's tile, relative to the item
 #ifndef SF_EHALO
 #define SF_EHALO 2 // cells around the tile whose E nodes are staged in shared memory (particles drift between sorts)
 #endif
 #define SF_ENT (SF_TILE + 2 * SF_EHALO + 1) // nodes per edge of the staged E tile
-#define SF_ETILE_DOUBLES (2 * SF_ENT * SF_ENT + (2 * SF_ENT * SF_ENT) % 2) // cell boundaries of the item's tile, relative to the item
-#define SF_SCRATCH_DOUBLES (SF_EXTRA + SF_SCR_DOUBLES + 2 + SF_NOFFS / 2 + SF_ETILE_DOUBLES + SF_STAGE * 2 * 7 * 32)
-#define SF_WARP_SMEM_BYTES ((SF_TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8)
-static_assert(SF_WARP_SMEM_BYTES % 16 == 0 && (SF_TILE_DOUBLES + SF_EXTRA) % 2 == 0, "128-bit shared-memory rows");
+#define SF_ETILE_DOUBLES (2 * SF_ENT * SF_ENT + (2 * SF_ENT * SF_ENT) % 2)
+// one pair: tile | extra (deposit) | extra (push) | 2 buffers | offs | E tile | 4 mbarriers | 2 fallback counters (+pad)
+#define SF_PAIR_DOUBLES (SF_TILE_DOUBLES + 2 * SF_EXTRA + 2 * SF_BUF_DOUBLES + SF_NOFFS / 2 + SF_ETILE_DOUBLES + 4 + 2)
+#define SF_PAIR_SMEM_BYTES (SF_PAIR_DOUBLES * 8)
+#define SF_FAST_SMEM_BYTES (SF_FAST_PAIRS * SF_PAIR_SMEM_BYTES)
+static_assert(SF_PAIR_SMEM_BYTES % 16 == 0 && SF_TILE_DOUBLES % 2 == 0 && SF_BUF_DOUBLES % 2 == 0, "128-bit shared-memory rows");
 
 __device__ __forceinline__ double sf_vacant() { return __longlong_as_double(0x7ff8000000000001LL); }
 
@@ -239,22 +239,6 @@ __device__ __forceinline__ bool sf_move_simple(const MeshDev &m, double qm, doub
     return ok;
 }
 
-// asynchronous global -> shared copy of one batch (7 state doubles per particle, each lane fetches the slots it will
-// read back itself, so no cross-lane synchronisation is needed): LDGSTS, no registers held while in flight
-__device__ __forceinline__ void sf_prefetch_batch(const FastPtrs &fs, double *stage, size_t begin, int b, int count, int lane)
-{
-    const double *src[7] = {fs.x, fs.y, fs.z, fs.u, fs.v, fs.w, fs.mpw};
-    const int o = b + lane;
-    if (o < count) {
-#pragma unroll
-        for (int f = 0; f < 7; f++) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + f * 32 + lane);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src[f] + begin + o) : "memory");
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // deposit of the tiled kernel.  FP64 shared-memory atomics are CAS loops on sm_100a and a transposition of the batch
 // through shared memory ((node, field) lanes walking the particles) is bound by its operand loads, so the sums are
@@ -318,8 +302,10 @@ __device__ __forceinline__ void quad_advance(const BatchScratch &S, int q, int t
 
 // a particle outside its quad's window (it drifted more than a cell from where the last sort put it): global reductions
 __device__ __noinline__ void quad_fallback(const FastStepArgs *__restrict__ ga, int a, int gi, int gj, double wx, double wj0, double wj1,
-                                           const double *v, double *extra, int *nfall)
+                                           const BatchScratch *Sp, int slot, double *extra, int *nfall)
 {
+    const double2 v01 = Sp->v01[slot], v23 = Sp->v23[slot], v45 = Sp->v45[slot];
+    const double v[7] = {v01.x, v01.y, v23.x, v23.y, v45.x, v45.y, Sp->v6[slot]};
     const FastStepArgs &g = *ga;
     const size_t plane = (size_t)g.m.ni * g.m.nj;
     if (a < 2) { // node rows gi, gi + 1
@@ -363,7 +349,7 @@ __device__ __forceinline__ void quad_substep(const FastStepArgs *__restrict__ ga
     if (__any_sync(0xffffffffu, outside)) {
         if (outside)
             quad_fallback(ga, a, ti0 + (pc >> 8) - SF_PC_BIAS, tj0 + (pc & 255) - SF_PC_BIAS, S.wi[6 * slot + 2 + (a & 1)], S.wj[6 * slot + 2],
-                          S.wj[6 * slot + 3], v, extra, nfall);
+                          S.wj[6 * slot + 3], &S, slot, extra, nfall);
         __syncwarp();
         if (outside && a == 0) S.wi[6 * slot + 2] = S.wi[6 * slot + 3] = 0.0; // nothing of it goes through the window
         __syncwarp();
@@ -384,109 +370,128 @@ __device__ __forceinline__ void quad_substep(const FastStepArgs *__restrict__ ga
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// tiled kernel: persistent warps pull work items from a queue; one particle per lane and batch in the push,
-// one particle per quad and sub-step in the deposit
+// shared-memory barriers between the two warps of a pair (mbarrier, 32 arrivals per phase: every lane arrives after
+// its own shared-memory accesses, every lane of the waiting warp acquires)
 // ---------------------------------------------------------------------------------------------------------
-template <int DOMAIN> // SFGPU_XY / RZ / ZR: the rotation code of the axisymmetric movers stays out of the planar kernel
-__global__ void __launch_bounds__(SF_FAST_WARPS * 32, SF_FAST_MIN_CTAS)
-k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restrict__ ga)
+__device__ __forceinline__ unsigned sf_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sf_mbar_init(unsigned long long *bar, int count)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double *tile = reinterpret_cast<double *>(smem_raw + (size_t)wid * SF_WARP_SMEM_BYTES);
-    double *extra = tile + SF_TILE_DOUBLES; // fallback N/Px/Py/Pz/E of the warp in [1..5]
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sf_saddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sf_mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sf_saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void sf_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(sf_saddr(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+struct BatchHeader { // written by lane 0 of the push warp into every buffer it fills
+    int kind;        // 0: a batch, 1: first batch of a work item, 2: no more work
+    int count, tile; // of the work item
+    int pad;
+    unsigned long long begin;
+};
+static_assert(sizeof(BatchHeader) <= 4 * 8, "header slot");
+
+struct PairSmem {
+    double *tile, *extraD, *extraP, *buf[2], *etile;
+    int *offs, *nfall; // nfall[0]: deposit warp, nfall[1]: push warp
+    unsigned long long *full, *empty; // [2] each
+};
+__device__ __forceinline__ PairSmem sf_pair_smem(unsigned char *base)
+{
+    PairSmem P;
+    P.tile = reinterpret_cast<double *>(base);
+    P.extraD = P.tile + SF_TILE_DOUBLES;
+    P.extraP = P.extraD + SF_EXTRA;
+    P.buf[0] = P.extraP + SF_EXTRA;
+    P.buf[1] = P.buf[0] + SF_BUF_DOUBLES;
+    P.offs = reinterpret_cast<int *>(P.buf[1] + SF_BUF_DOUBLES);
+    P.etile = reinterpret_cast<double *>(P.offs + SF_NOFFS);
+    P.full = reinterpret_cast<unsigned long long *>(P.etile + SF_ETILE_DOUBLES);
+    P.empty = P.full + 2;
+    P.nfall = reinterpret_cast<int *>(P.empty + 2);
+    return P;
+}
+__device__ __forceinline__ BatchScratch sf_buf_view(double *b, const int *offs)
+{
     BatchScratch S;
-    S.wi = extra + SF_EXTRA;
+    S.wi = b;
     S.wj = S.wi + 32 * 6;
     S.v01 = reinterpret_cast<double2 *>(S.wj + 32 * 6);
     S.v23 = S.v01 + 32;
     S.v45 = S.v23 + 32;
     S.v6 = reinterpret_cast<double *>(S.v45 + 32);
     S.cell = reinterpret_cast<int *>(S.v6 + 32);
-    int *sFall = S.cell + 32; // fallback count of the work item
-    int *sOffs = sFall + 4;
-    S.offs = sOffs;
-    double *sE = reinterpret_cast<double *>(sOffs + SF_NOFFS); // efi, efj over the tile + SF_EHALO cells, [2][SF_ENT][SF_ENT]
-    double *sIn = sE + SF_ETILE_DOUBLES; // [2 stages][7][32] prefetched particle state
+    S.offs = offs;
+    return S;
+}
+__device__ __forceinline__ BatchHeader *sf_buf_header(double *b) { return reinterpret_cast<BatchHeader *>(b + 32 * 19 + 16); }
+
+// ---------------------------------------------------------------------------------------------------------
+// push warp: gather (E tile in shared memory) -> kick -> move -> locate -> boundaries -> in-place store, one particle
+// per lane; publishes every particle's deposit operands to the deposit warp of its pair
+// ---------------------------------------------------------------------------------------------------------
+template <int DOMAIN>
+__device__ __forceinline__ void sf_push_role(const FastStepArgs &a, const FastStepArgs *__restrict__ ga, const PairSmem &P, int lane)
+{
     const MeshDev &m = a.m;
-    const size_t plane = (size_t)m.ni * m.nj;
     const bool simple_ok = !m.has_b && !m.any_seg && a.dt > 0;
-    const int qa = lane & 3, qq = lane >> 2; // deposit role: node row of the window, quad
-
-    for (int k = lane; k < SF_TILE_DOUBLES + SF_EXTRA + 2 * 32 * 6; k += 32) tile[k] = 0.0; // (the padding of the weight rows stays zero)
-    if (lane == 0) sFall[0] = 0;
-    __syncwarp();
-
-    QuadAcc A;
-#pragma unroll
-    for (int b = 0; b < 4; b++)
-#pragma unroll
-        for (int f = 0; f < 7; f++) A.s[b][f] = 0.0;
-    A.cnt = 0;
-    A.bi = A.bj = 1;
-    A.cur = 0;
-    A.t_next = 0;
-
+    double *sE = P.etile;
     const unsigned n_items = *a.n_items;
+    unsigned ph_empty[2] = {1u, 1u}; // a fresh barrier lets the first wait on "empty" pass
+    int k = 0;
+    double esum = 0.0; // sum of mpw*|vel| of this lane's particles (KM:412)
     for (;;) {
         unsigned it = 0;
         if (lane == 0) it = atomicAdd(&a.c->queue[a.mesh_id], 1u);
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= n_items) break;
         const WorkItem wi = a.items[it];
-        const int ti0 = (wi.tile / a.ntj) * SF_TILE - SF_FHALO; // first node row / column held by the tile
+        const int ti0 = (wi.tile / a.ntj) * SF_TILE - SF_FHALO; // first node row / column of the deposit tile
         const int tj0 = (wi.tile % a.ntj) * SF_TILE - SF_FHALO;
         const int ei0 = ti0 + SF_FHALO - SF_EHALO, ej0 = tj0 + SF_FHALO - SF_EHALO; // first node of the staged E tile
-        const int L = wi.count >> 3; // particles per run (sf_item_slot)
-#if SF_STAGE
-        sf_prefetch_batch(a.fs, sIn, (size_t)wi.begin, 0, wi.count, lane);
-#endif
-        // cell boundaries of the sorted layout inside this item (positions relative to its first particle)
-        for (int k = lane; k < SF_TILE * SF_TILE + 1; k += 32) {
-            const long long d = (long long)a.offs[(size_t)wi.tile * (SF_TILE * SF_TILE) + k] - (long long)wi.begin;
-            sOffs[k] = d < 0 ? 0 : (d > wi.count ? wi.count : (int)d);
-        }
         // E field of the tile's neighbourhood: the gathers of the common path read shared memory (F2D:300-350)
-        for (int k = lane; k < SF_ENT * SF_ENT; k += 32) {
-            const int gi = ei0 + k / SF_ENT, gj = ej0 + k % SF_ENT;
+        __syncwarp();
+        for (int e = lane; e < SF_ENT * SF_ENT; e += 32) {
+            const int gi = ei0 + e / SF_ENT, gj = ej0 + e % SF_ENT;
             double fi = 0.0, fj = 0.0;
             if (gi >= 0 && gj >= 0 && gi < m.ni && gj < m.nj) {
                 fi = __ldg(m.efi + (size_t)gi * m.nj + gj);
                 fj = __ldg(m.efj + (size_t)gi * m.nj + gj);
             }
-            sE[k] = fi;
-            sE[SF_ENT * SF_ENT + k] = fj;
+            sE[e] = fi;
+            sE[SF_ENT * SF_ENT + e] = fj;
         }
         __syncwarp();
-        A.cur = 0;
-        A.t_next = 0; // the first sub-step places the window
-        double esum = 0.0; // sum of mpw*|vel| of this lane's particles (KM:412)
+        // the state of the next batch is fetched into registers while the current one is pushed
+        double nx = 0, ny = 0, nz = 0, nu = 0, nv = 0, nw = 0, nm = sf_vacant();
+        if (lane < wi.count) {
+            const size_t q0 = (size_t)wi.begin + lane;
+            nx = a.fs.x[q0]; ny = a.fs.y[q0]; nz = a.fs.z[q0];
+            nu = a.fs.u[q0]; nv = a.fs.v[q0]; nw = a.fs.w[q0];
+            nm = a.fs.mpw[q0];
+        }
         for (int b = 0; b < wi.count; b += 32) {
             PState p;
             const int o = b + lane;
-            bool present = o < wi.count;
+            const bool present = o < wi.count;
             const size_t q = (size_t)wi.begin + o;
-            p.mpw = sf_vacant();
-            // ---- the batch was prefetched into shared memory with cp.async while the previous one was processed ----
-#if SF_STAGE
-            const int stage = (b >> 5) & 1;
-            const bool more = b + 32 < wi.count;
-            if (more) sf_prefetch_batch(a.fs, sIn + (stage ^ 1) * (7 * 32), (size_t)wi.begin, b + 32, wi.count, lane);
-            if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            if (present) {
-                const double *in = sIn + stage * (7 * 32) + lane;
-                p.x = in[0 * 32]; p.y = in[1 * 32]; p.z = in[2 * 32];
-                p.u = in[3 * 32]; p.v = in[4 * 32]; p.w = in[5 * 32];
-                p.mpw = in[6 * 32];
+            p.x = nx; p.y = ny; p.z = nz; p.u = nu; p.v = nv; p.w = nw; p.mpw = nm;
+            nm = sf_vacant();
+            if (o + 32 < wi.count) {
+                nx = a.fs.x[q + 32]; ny = a.fs.y[q + 32]; nz = a.fs.z[q + 32];
+                nu = a.fs.u[q + 32]; nv = a.fs.v[q + 32]; nw = a.fs.w[q + 32];
+                nm = a.fs.mpw[q + 32];
             }
-#else
-            if (present) {
-                p.x = a.fs.x[q]; p.y = a.fs.y[q]; p.z = a.fs.z[q];
-                p.u = a.fs.u[q]; p.v = a.fs.v[q]; p.w = a.fs.w[q];
-                p.mpw = a.fs.mpw[q];
-            }
-#endif
             // ---- common case, straight line: one sub-step, no B field, no segments, the particle starts inside the staged E tile
             //      and ends strictly inside the mesh.  Every expression is the one sf_move() evaluates, in the same order (KM:336-381,
             //      F2D:345-348, UM:158-159), so both paths are bit-identical; anything else re-runs through sf_move() below ----
@@ -570,9 +575,13 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                     esum += p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w); // KM:412
                 } else {
                     const PState t = p;
-                    fast_fallback(&ga->m, &t, a.dep, extra, sFall);
+                    fast_fallback(&ga->m, &t, a.dep, P.extraP, P.nfall + 1);
                 }
             }
+            // ---- hand the batch to the deposit warp ----
+            sf_mbar_wait(P.empty + k, ph_empty[k]);
+            ph_empty[k] ^= 1u;
+            const BatchScratch S = sf_buf_view(P.buf[k], P.offs);
             S.cell[lane] = pc;
             *reinterpret_cast<double2 *>(S.wi + 6 * lane + 2) = wi2;
             *reinterpret_cast<double2 *>(S.wj + 6 * lane + 2) = wj2;
@@ -580,49 +589,161 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
             S.v23[lane] = make_double2(val[2], val[3]);
             S.v45[lane] = make_double2(val[4], val[5]);
             S.v6[lane] = val[6];
-            __syncwarp();
-            // ---- four sub-steps: quad q takes the particles of push lanes q, 8+q, 16+q, 24+q (consecutive in its run) ----
-#pragma unroll 1
-            for (int s = 0; s < 4; s++) quad_substep(ga, tile, extra, sFall, S, 8 * s + qq, qa, qq, (b >> 3) + s, L, ti0, tj0, A);
-            __syncwarp();
-        }
-        // ---- end of the work item: every quad empties its registers into the warp tile, one quad at a time ----
-#pragma unroll 1
-        for (int ql = 0; ql < 8; ql++) {
-            if (qq == ql) quad_flush(tile, qa, A);
-            __syncwarp();
-        }
-        // ---- add the warp tile to the global deposit and clear it; the mover sums N, Px, Py, Pz (KM:406-411) of the
-        //      particles that went through the tile are the tile totals of Den, U, V, W (the weights sum to 1) ----
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        for (int k = lane; k < SF_TILE_DOUBLES; k += 32) {
-            const double v = tile[k];
-            if (v != 0.0) {
-                const int f = k / (SF_FNT * SF_FNT), r = k % (SF_FNT * SF_FNT);
-                const int gi = ti0 + r / SF_FNT, gj = tj0 + r % SF_FNT;
-                if (gi >= 0 && gj >= 0 && gi < m.ni && gj < m.nj) atomicAdd(a.dep + f * plane + (size_t)gi * m.nj + gj, v);
-                tile[k] = 0.0;
-                if (f == 0) s0 += v;
-                else if (f == 1) s1 += v;
-                else if (f == 2) s2 += v;
-                else if (f == 3) s3 += v;
+            if (lane == 0) {
+                BatchHeader h;
+                h.kind = b == 0 ? 1 : 0;
+                h.count = wi.count;
+                h.tile = wi.tile;
+                h.pad = 0;
+                h.begin = wi.begin;
+                *sf_buf_header(P.buf[k]) = h;
             }
+            sf_mbar_arrive(P.full + k);
+            k ^= 1;
         }
-        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-        esum = warp_sum(esum);
-        if (lane == 0) {
-            const int nf = sFall[0];
-            if (s0 != 0 || nf != 0 || esum != 0) {
-                atomicAdd(&a.c->sums[0], s0 + extra[1]); atomicAdd(&a.c->sums[1], s1 + extra[2]); atomicAdd(&a.c->sums[2], s2 + extra[3]);
-                atomicAdd(&a.c->sums[3], s3 + extra[4]); atomicAdd(&a.c->sums[4], esum + extra[5]);
-                if (nf != 0) atomicAdd(&a.c->n_fallback, (unsigned long long)nf);
-            }
-#pragma unroll
-            for (int k = 0; k < SF_EXTRA; k++) extra[k] = 0.0;
-            sFall[0] = 0;
+    }
+    // no more work: tell the deposit warp
+    sf_mbar_wait(P.empty + k, ph_empty[k]);
+    if (lane == 0) sf_buf_header(P.buf[k])->kind = 2;
+    sf_mbar_arrive(P.full + k);
+    // mover sums of this warp: energy of the particles it published, everything of those that missed the operand range
+    esum = warp_sum(esum);
+    __syncwarp();
+    if (lane == 0) {
+        const int nf = P.nfall[1];
+        if (esum != 0 || nf != 0) {
+            atomicAdd(&a.c->sums[0], P.extraP[1]); atomicAdd(&a.c->sums[1], P.extraP[2]); atomicAdd(&a.c->sums[2], P.extraP[3]);
+            atomicAdd(&a.c->sums[3], P.extraP[4]); atomicAdd(&a.c->sums[4], esum + P.extraP[5]);
+            if (nf != 0) atomicAdd(&a.c->n_fallback, (unsigned long long)nf);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// deposit warp: eight quads accumulate the published batches in registers, flush into the warp's tile, and add the
+// tile to the global deposit at the end of every work item
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sf_deposit_item_end(const FastStepArgs &a, const PairSmem &P, int lane, int ti0, int tj0, QuadAcc &A)
+{
+    const MeshDev &m = a.m;
+    const size_t plane = (size_t)m.ni * m.nj;
+    const int qa = lane & 3, qq = lane >> 2;
+    double *tile = P.tile;
+#pragma unroll 1
+    for (int ql = 0; ql < 8; ql++) { // every quad empties its registers into the warp tile, one quad at a time
+        if (qq == ql) quad_flush(tile, qa, A);
         __syncwarp();
     }
+    // the mover sums N, Px, Py, Pz (KM:406-411) of the particles that went through the tile are the tile totals of
+    // Den, U, V, W (the weights of a particle sum to 1)
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int e = lane; e < SF_TILE_DOUBLES; e += 32) {
+        const double v = tile[e];
+        if (v != 0.0) {
+            const int f = e / (SF_FNT * SF_FNT), r = e % (SF_FNT * SF_FNT);
+            const int gi = ti0 + r / SF_FNT, gj = tj0 + r % SF_FNT;
+            if (gi >= 0 && gj >= 0 && gi < m.ni && gj < m.nj) atomicAdd(a.dep + f * plane + (size_t)gi * m.nj + gj, v);
+            tile[e] = 0.0;
+            if (f == 0) s0 += v;
+            else if (f == 1) s1 += v;
+            else if (f == 2) s2 += v;
+            else if (f == 3) s3 += v;
+        }
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    if (lane == 0) {
+        const int nf = P.nfall[0];
+        if (s0 != 0 || nf != 0) {
+            atomicAdd(&a.c->sums[0], s0 + P.extraD[1]); atomicAdd(&a.c->sums[1], s1 + P.extraD[2]); atomicAdd(&a.c->sums[2], s2 + P.extraD[3]);
+            atomicAdd(&a.c->sums[3], s3 + P.extraD[4]);
+            if (nf != 0) atomicAdd(&a.c->n_fallback, (unsigned long long)nf);
+        }
+#pragma unroll
+        for (int e = 0; e < SF_EXTRA; e++) P.extraD[e] = 0.0;
+        P.nfall[0] = 0;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void sf_deposit_role(const FastStepArgs &a, const FastStepArgs *__restrict__ ga, const PairSmem &P, int lane)
+{
+    const int qa = lane & 3, qq = lane >> 2; // node row of the window, quad
+    QuadAcc A;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int f = 0; f < 7; f++) A.s[b][f] = 0.0;
+    A.cnt = 0;
+    A.bi = A.bj = 1;
+    A.cur = 0;
+    A.t_next = 0;
+    unsigned ph_full[2] = {0u, 0u};
+    int k = 0, b = 0, L = 0, ti0 = 0, tj0 = 0;
+    bool have_item = false;
+    for (;;) {
+        sf_mbar_wait(P.full + k, ph_full[k]);
+        ph_full[k] ^= 1u;
+        const BatchHeader h = *sf_buf_header(P.buf[k]);
+        if (h.kind != 0) {
+            if (have_item) sf_deposit_item_end(a, P, lane, ti0, tj0, A);
+            have_item = false;
+            if (h.kind == 2) break;
+            // a new work item: cell boundaries of the sorted layout inside it (positions relative to its first particle)
+            ti0 = (h.tile / a.ntj) * SF_TILE - SF_FHALO;
+            tj0 = (h.tile % a.ntj) * SF_TILE - SF_FHALO;
+            L = h.count >> 3; // particles per run (sf_item_slot)
+            for (int e = lane; e < SF_TILE * SF_TILE + 1; e += 32) {
+                const long long d = (long long)a.offs[(size_t)h.tile * (SF_TILE * SF_TILE) + e] - (long long)h.begin;
+                P.offs[e] = d < 0 ? 0 : (d > h.count ? h.count : (int)d);
+            }
+            __syncwarp();
+            // first cell of every run: the number of boundaries at or before its first position
+            {
+                const int pos = qq * L;
+                int n = 0;
+                for (int e = qa; e < SF_TILE * SF_TILE; e += 4) n += (P.offs[e] <= pos) ? 1 : 0;
+                n += __shfl_xor_sync(0xffffffffu, n, 1);
+                n += __shfl_xor_sync(0xffffffffu, n, 2);
+                A.cur = n > 0 ? n - 1 : 0;
+            }
+            A.t_next = 0; // the first sub-step places the window
+            b = 0;
+            have_item = true;
+        }
+        const BatchScratch S = sf_buf_view(P.buf[k], P.offs);
+#pragma unroll 1
+        for (int s = 0; s < 4; s++) quad_substep(ga, P.tile, P.extraD, P.nfall, S, 8 * s + qq, qa, qq, (b >> 3) + s, L, ti0, tj0, A);
+        sf_mbar_arrive(P.empty + k);
+        k ^= 1;
+        b += 32;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tiled kernel: persistent CTAs of SF_FAST_PAIRS (push warp, deposit warp) pairs; the push warp of a pair pulls work
+// items from a queue and feeds its deposit warp batch by batch through two shared-memory buffers
+// ---------------------------------------------------------------------------------------------------------
+template <int DOMAIN> // SFGPU_XY / RZ / ZR: the rotation code of the axisymmetric movers stays out of the planar kernel
+__global__ void __launch_bounds__(SF_FAST_THREADS, SF_FAST_MIN_CTAS)
+k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restrict__ ga)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int pair = wid % SF_FAST_PAIRS;
+    const bool pusher = wid < SF_FAST_PAIRS;
+    const PairSmem P = sf_pair_smem(smem_raw + (size_t)pair * SF_PAIR_SMEM_BYTES);
+    if (pusher) { // the pair's region starts zeroed (tile, sums, the padding of the weight rows); barriers: 32 arrivals
+        for (int e = lane; e < SF_PAIR_DOUBLES; e += 32) P.tile[e] = 0.0;
+        __syncwarp();
+        if (lane < 2) {
+            sf_mbar_init(P.full + lane, 32);
+            sf_mbar_init(P.empty + lane, 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (pusher) sf_push_role<DOMAIN>(a, ga, P, lane);
+    else sf_deposit_role(a, ga, P, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -575,10 +575,10 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaMalloc(&ctx->d_args, sizeof(FastStepArgs) * SF_MAX_MESHES));
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
         ctx->fast_kernel = domain_type == SFGPU_XY ? k_fast_step<SFGPU_XY> : (domain_type == SFGPU_RZ ? k_fast_step<SFGPU_RZ> : k_fast_step<SFGPU_ZR>);
-        CU(cudaFuncSetAttribute(ctx->fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(ctx->fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_SMEM_BYTES));
         int nsm = 0, per_sm = 0;
         CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctx->fast_kernel, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctx->fast_kernel, SF_FAST_THREADS, SF_FAST_SMEM_BYTES));
         if (per_sm < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
         ctx->fast_grid = nsm * per_sm;
         if (const char *e = getenv("SFGPU_FAST_GRID")) ctx->fast_grid = atoi(e) > 0 ? atoi(e) : ctx->fast_grid; // occupancy experiments
@@ -592,7 +592,7 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         ctx->stream_check = getenv("SFGPU_STREAM_CHECK") != nullptr;
         CU(cudaMalloc(&ctx->d_bad, sizeof(unsigned long long)));
         if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_stream_step %d CTAs/SM x %d threads, %d B dynamic smem per CTA, grid %d, path %s\n", per_sm_s, SFS_THREADS, (int)SFS_SMEM_BYTES, ctx->stream_grid, ctx->path ? "stream" : "tiled");
-        if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_fast_step %d CTAs/SM x %d warps, %d B dynamic smem per CTA, grid %d\n", per_sm, SF_FAST_WARPS, (int)(SF_FAST_WARPS * SF_WARP_SMEM_BYTES), ctx->fast_grid);
+        if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_fast_step %d CTAs/SM x %d warps, %d B dynamic smem per CTA, grid %d\n", per_sm, 2 * SF_FAST_PAIRS, (int)(SF_FAST_SMEM_BYTES), ctx->fast_grid);
         // bit-parity self test: a*b+c must round twice
         double *d = nullptr, h = 0;
         CU(cudaMalloc(&d, sizeof(double)));
@@ -1331,7 +1331,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             int64_t tail_first = 0;
             if (!untiled && f.n_sorted > 0 && f.n_items > 0) {
                 CU(cudaMemcpyAsync(ctx->d_args + m, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
-                ctx->fast_kernel<<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                ctx->fast_kernel<<<ctx->fast_grid, SF_FAST_THREADS, SF_FAST_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
                 tail_first = f.n_sorted;
