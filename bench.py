@@ -7,10 +7,10 @@ One "step" = one KineticMaterial.updateFields() pass (move + deposit + moment su
 particle population; one "push" = one particle advanced one step including its deposit contribution.
 
 Workloads (BASELINE.json configs):
-  b  (default at N=1)  XY 512x512 nodes, 16,777,216 uniformly loaded particles, all faces periodic
-  N>1 default           the same shard on every rank (weak scaling: N x 16M particles on the replicated mesh,
-                        per-step NCCL allreduce of the deposit)
-  e                     XY 2048x2048 nodes, 2^30 particles partitioned by index over the ranks
+  b  (default at N=1)  XY 512x512 nodes, 16,777,216 uniformly loaded particles, all faces periodic; with N>1 ranks
+                        (--workload b) the same shard on every rank: weak scaling
+  e  (default at N>1)  XY 2048x2048 nodes, 2^30 particles partitioned by index over the ranks (north_star's multi-GPU
+                        config): STRONG scaling, per-step NCCL allreduce of the deposit
   c                     RZ 1024x1024, beam over r < 0.25 Rmax, LEFT symmetry, other faces open
 Particle arrays (1 GiB at 16M) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
 
@@ -100,16 +100,16 @@ def cpu_reference_run(wl, n_sample, steps, warmup, threads):
     return n_sample * steps / t, t
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, wname):
     if rank != 0:
         return
-    wl, _n = workload("b" if args.workload == "auto" else args.workload, world)
+    wl, _n = workload(wname, world)
     threads = os.cpu_count() or 1
     n_sample = args.ref_particles
     value, t = cpu_reference_run(wl, n_sample, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": "particle pushes/sec (move+deposit)", "value": value, "unit": "pushes/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong" if wname == "e" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl.name, "mesh_nodes": [wl.mesh.ni, wl.mesh.nj], "particles": n_sample,
                    "note": "bounded sample of the workload on the host cores; JVM unavailable, C restatement of the Java algorithm"},
@@ -124,8 +124,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 340 for config B, 40 for the 2^30-particle config E)")
+    ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "b", "b_beam", "c", "e"])
     ap.add_argument("--particles", type=int, default=0, help="particles per rank (default: the config's)")
@@ -136,11 +136,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wname = args.workload if args.workload != "auto" else ("b" if world == 1 else "e")
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        args.steps = args.steps or 3
+        args.warmup = args.warmup or 1
+        run_reference(args, rank, world, wname)
         return
+    if args.steps <= 0:  # timed region >= 0.5 s
+        args.steps = {"b": 340, "b_beam": 340, "c": 60, "e": 40}[wname]
     if args.warmup < 3:
-        args.warmup = 3
+        args.warmup = 6 if wname.startswith("b") else 3
 
     import torch
     import torch.distributed as dist
@@ -153,7 +158,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    wname = args.workload if args.workload != "auto" else "b"
     wl, n_rank = workload(wname, world)
     if args.particles:
         n_rank = args.particles
@@ -166,8 +170,9 @@ def main():
         pinned[...] = getattr(m, name)
         setattr(m, name, pinned)
     attach_communicator(km)  # NCCL communicator of the library: rank 0 makes the id, torch.distributed carries it
+    km.download_fields = rank == 0  # the deposit is identical on every rank after the allreduce: read back once
     # this rank's shard: particle indices [rank*n_rank, (rank+1)*n_rank) of the global population
-    chunk = 1 << 22
+    chunk = 1 << 23
     for first in range(0, n_rank, chunk):
         c = min(chunk, n_rank - first)
         arr = wl.particles(rank * n_rank + first, c)
@@ -268,7 +273,29 @@ def main():
     clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions
     e2e_value = allsum(float(e_pushes)) / e2e_s
     plane = m.ni * m.nj * 8
-    h2d, d2h = 2 * plane, 4 * plane + 5 * 8
+    h2d, d2h = 2 * plane, plane + 5 * 8  # per rank up: efi, efj; down (rank 0): nd + the mover sums (u, v, w on demand)
+
+    # ---- multi-GPU consistency of the last step (every rank): counts, conservation, identical deposit everywhere ----
+    multi_check = None
+    if world > 1:
+        import hashlib
+        dep = km.last_deposit[0]
+        np_total = int(allsum(float(km.getNp())))
+        problems = []
+        if int(dep[7].sum()) != np_total:
+            problems.append("sum(mpc) %d != particles %d" % (int(dep[7].sum()), np_total))
+        want = np_total * wl.mpw
+        if abs(float(dep[0].sum()) - want) > 1e-10 * want:
+            problems.append("sum(Den) %.17g != sum(mpw) %.17g" % (float(dep[0].sum()), want))
+        digest = hashlib.sha1(dep.tobytes()).hexdigest()
+        box = [None] * world
+        dist.all_gather_object(box, digest)
+        if len(set(box)) != 1:
+            problems.append("deposit differs between ranks")
+        allp = [None] * world
+        dist.all_gather_object(allp, problems)
+        flat = [q for pr in allp for q in pr]
+        multi_check = "ok" if not flat else "FAILED: " + "; ".join(sorted(set(flat)))
 
     if rank == 0:
         peaks, peak_src = None, "fallback"
@@ -285,16 +312,24 @@ def main():
         achieved = ALGO_BYTES_PER_PUSH * float(d_pushes) / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
         kernels = {names[k]: {"steps": v[0], "kernel_ms_per_step": v[1] / v[0], "GB/s": ALGO_BYTES_PER_PUSH * v[2] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0}
                    for k, v in by_kind.items()}
+        # dram bytes per launch of the dominant kernel from an ncu --set full capture: valid only for the kernel sources it was taken on
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wname)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            import hashlib
+            h = hashlib.sha1()
+            for fn in sorted(os.listdir(os.path.join(ROOT, "starfish_b200", "csrc"))):
+                if fn.endswith((".cu", ".cuh")):
+                    h.update(open(os.path.join(ROOT, "starfish_b200", "csrc", fn), "rb").read())
+            if tj.get("csrc_sha1") == h.hexdigest():
+                traffic = tj.get(wname)
         except Exception:
             pass
         line = {
             "metric": "particle pushes/sec (move+deposit)", "value": value, "unit": "pushes/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if wname == "e" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.name, "mesh_nodes": [m.ni, m.nj], "particles_per_gpu": n_local, "particles_total": int(allsum(float(n_local))) if world == 1 else int(n_local * world),
+            "config": {"workload": wl.name, "mesh_nodes": [m.ni, m.nj], "particles_per_gpu": n_local, "particles_total": int(n_local * world),
                        "l2": "particle arrays (64 B x N per GPU) exceed the 126 MB L2; no flush needed",
                        "parallelism": "particles partitioned by index, mesh replicated, NCCL allreduce of the deposit" if world > 1 else "single GPU"},
             "wall_ms_per_step": wall_ms / args.steps,
@@ -309,6 +344,8 @@ def main():
                          "pushes_per_s_at_peak": peak * 1e9 / ALGO_BYTES_PER_PUSH},
             "clocks": clocks,
         }
+        if multi_check is not None:
+            line["multi_gpu_check"] = multi_check
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n_sample = args.ref_particles

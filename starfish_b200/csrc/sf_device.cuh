@@ -366,25 +366,6 @@ __device__ __forceinline__ bool sf_deposit_weights(const MeshDev &m, double fi, 
     return true;
 }
 
-// the same weights per axis, F2D:254-283: cell (i, j) and the (Ruyten-corrected) fractions; the four node weights
-// are (1-di)(1-dj), di(1-dj), di*dj, (1-di)dj.  false when scatter() returns early.
-__device__ __forceinline__ bool sf_deposit_axis_weights(const MeshDev &m, double fi, double fj, int &i, int &j, double &di, double &dj)
-{
-    i = sf_j2i(fi);
-    j = sf_j2i(fj);
-    if (i < 0 || j < 0 || i >= m.ni - 1 || j >= m.nj - 1) return false;
-    di = fi - i;
-    dj = fj - j;
-    if (m.domain == SFGPU_RZ) {
-        double rp = m.x0 + (i + 1) * m.dhx, rm = m.x0 + i * m.dhx, r = m.x0 + fi * m.dhx;
-        di = 1 - (0.5 * (rp - r) * (2 * rp + 3 * rm - r) / (rp * rp - rm * rm));
-    } else if (m.domain == SFGPU_ZR) {
-        double rp = m.y0 + (j + 1) * m.dhy, rm = m.y0 + j * m.dhy, r = m.y0 + fj * m.dhy;
-        dj = 1 - (0.5 * (rp - r) * (2 * rp + 3 * rm - r) / (rp * rp - rm * rm));
-    }
-    return true;
-}
-
 // the seven bilinear deposit values of one particle: KM:184-187, KM:1584-1590
 __device__ __forceinline__ void sf_deposit_values(const PState &p, double val[7])
 {

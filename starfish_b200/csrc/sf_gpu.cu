@@ -114,7 +114,7 @@ struct FastStore { // cell-sorted SoA store of the normal particles of one speci
     // streaming step (sf_stream.cuh): histogram accumulated for the next launch, output segment offsets, output cursors
     unsigned *hist_next = nullptr, *offs_out = nullptr, *cursor = nullptr;
     bool stream_ok = false; // hist counts every live particle of p[0,n) and offs describes p[0,n_sorted)
-    bool tiled_ok = false;  // items/offs describe the interleaved layout fast_sort writes (what k_fast_step expects)
+    bool items_ok = false;  // items / d_nitems are the work items of k_fast_step for the current slab (not the streaming kernel's chunks)
     WorkItem *items = nullptr;
     unsigned *d_nitems = nullptr;
     unsigned max_items = 0, n_items = 0;
@@ -187,7 +187,6 @@ struct sfgpu_ctx {
     bool timing_valid = false;
     int sort_every = 3;      // steps between cell sorts of the fast store (2..5 give the same step time on config B; 3 keeps the kernel on a fresher order)
     int fast_grid = 0;       // CTAs of the tiled kernel (persistent)
-    void (*fast_kernel)(const FastStepArgs, const FastStepArgs *) = nullptr; // k_fast_step of the context's domain type
     int path = 0;            // default step kernel: 0 = tiled in-place step + periodic sort (sf_fast.cuh), 1 = streaming step (sf_stream.cuh)
     int stream_grid = 0;     // CTAs of the streaming kernel (persistent)
     bool hybrid = false;     // tiled path: run the step in which a re-sort is due with the streaming kernel instead of sorting separately
@@ -379,7 +378,7 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     f.n_items = tot[1] < f.max_items ? tot[1] : f.max_items;
     f.dirty = false;
     f.stream_ok = true; // hist = live particles per key, offs = their segment offsets
-    f.tiled_ok = true;
+    f.items_ok = true;
     return 0;
 }
 
@@ -458,7 +457,7 @@ static int fast_resort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     f.dirty = false;
     f.steps_since_sort = 0;
     f.stream_ok = true;
-    f.tiled_ok = false;
+    f.items_ok = true;
     return 0;
 }
 
@@ -484,7 +483,7 @@ static FastStepArgs fast_args(sfgpu_ctx *ctx, Species &s, int m, double dt, cons
     a.m = ctx->meshes[m].dev; a.meshes = ctx->d_meshes; a.mesh_id = m; a.qm = s.qm; a.charge = s.charge; a.dt = dt;
     a.fs = pop.fast.p; a.items = pop.fast.items; a.n_items = pop.fast.d_nitems; a.ntj = pop.fast.ntj;
     a.exc = pop.nxt.p; a.exc_cap = (unsigned long long)pop.nxt.cap;
-    a.xfer = ctx->d_xfer; a.slow = slow; a.dep = pop.dep; a.c = ctx->d_cnt; a.offs = pop.fast.offs;
+    a.xfer = ctx->d_xfer; a.slow = slow; a.dep = pop.dep; a.c = ctx->d_cnt;
     return a;
 }
 
@@ -574,11 +573,10 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaMalloc(&ctx->d_xfer, sizeof(XferDev) * SF_MAX_MESHES));
         CU(cudaMalloc(&ctx->d_args, sizeof(FastStepArgs) * SF_MAX_MESHES));
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
-        ctx->fast_kernel = domain_type == SFGPU_XY ? k_fast_step<SFGPU_XY> : (domain_type == SFGPU_RZ ? k_fast_step<SFGPU_RZ> : k_fast_step<SFGPU_ZR>);
-        CU(cudaFuncSetAttribute(ctx->fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_fast_step, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         int nsm = 0, per_sm = 0;
         CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctx->fast_kernel, SF_FAST_THREADS, SF_FAST_SMEM_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_step, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         if (per_sm < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
         ctx->fast_grid = nsm * per_sm;
         if (const char *e = getenv("SFGPU_FAST_GRID")) ctx->fast_grid = atoi(e) > 0 ? atoi(e) : ctx->fast_grid; // occupancy experiments
@@ -592,7 +590,7 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         ctx->stream_check = getenv("SFGPU_STREAM_CHECK") != nullptr;
         CU(cudaMalloc(&ctx->d_bad, sizeof(unsigned long long)));
         if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_stream_step %d CTAs/SM x %d threads, %d B dynamic smem per CTA, grid %d, path %s\n", per_sm_s, SFS_THREADS, (int)SFS_SMEM_BYTES, ctx->stream_grid, ctx->path ? "stream" : "tiled");
-        if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_fast_step %d CTAs/SM x %d warps, %d B dynamic smem per CTA, grid %d\n", per_sm, 2 * SF_FAST_PAIRS, (int)(SF_FAST_SMEM_BYTES), ctx->fast_grid);
+        if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_fast_step %d CTAs/SM x %d warps, %d B dynamic smem per CTA, grid %d\n", per_sm, SF_FAST_WARPS, (int)(SF_FAST_WARPS * SF_WARP_SMEM_BYTES), ctx->fast_grid);
         // bit-parity self test: a*b+c must round twice
         double *d = nullptr, h = 0;
         CU(cudaMalloc(&d, sizeof(double)));
@@ -756,8 +754,7 @@ extern "C" int sfgpu_set_fields(sfgpu_ctx *ctx, int32_t mesh_id, const double *e
             m.dev.has_b = hb;
             ctx->meshes_dirty = true;
         }
-        CU(cudaStreamSynchronize(ctx->stream)); // the caller may reuse its buffers on return
-        return 0;
+        return 0; // stream ordered: page-locked sources must stay unchanged until the next sfgpu_step / sfgpu_sync returns (sfgpu.h)
     }
     int rc = stage_reserve(ctx, nf * bytes);
     if (rc) return rc;
@@ -1158,6 +1155,7 @@ static int push_xfer_table(sfgpu_ctx *ctx, Species &s)
 }
 
 extern "C" int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp);
+static int enqueue_finish(sfgpu_ctx *ctx, Species &s);
 
 extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
 {
@@ -1193,6 +1191,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         if (rc) return rc;
     }
     bool stream = !untiled && !(flags & SFGPU_STEP_INPLACE) && (ctx->path == 1 || (flags & SFGPU_STEP_STREAM));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream)); // "whole step" of sfgpu_last_step_timing: the periodic sort included
     // K3: cell sort + compaction of the fast store.
     //  * streaming step: the kernel re-sorts as it writes; a separate pass only (re-)establishes its invariant;
     //  * tiled step: needs a re-sort every few steps.  When one is due, that step is run by the streaming kernel instead
@@ -1220,8 +1219,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         f.stream_ok = false; // the in-place step moves particles between cells without telling the histogram
         if (f.n == 0) continue;
         const int64_t tail = f.n - f.n_sorted;
-        if (f.n_sorted == 0 || !f.tiled_ok || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n || ctx->force_sort) {
-            rc = fast_sort(ctx, m, f); // (also after a streaming step: its output is not in the interleaved item layout)
+        if (f.n_sorted == 0 || !f.items_ok || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n || ctx->force_sort) {
+            rc = fast_resort(ctx, m, f); // streaming re-sort when the store is still roughly ordered, counting sort otherwise
             if (rc) return rc;
             f.stream_ok = false;
         }
@@ -1252,7 +1251,6 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             }
         }
     }
-    CU(cudaEventRecord(ctx->ev0, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(StepCounters), ctx->stream));
     {
         // cursors that do not start at zero: transfer lists pre-filled by the host, fast-store tails
@@ -1283,10 +1281,12 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             CU(cudaMemcpyAsync(f.cursor, f.offs_out, (size_t)f.nkeys * sizeof(unsigned), cudaMemcpyDeviceToDevice, ctx->stream));
             CU(cudaMemsetAsync(f.hist_next, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
             { ctx->last_launches++; ctx->launch_total++; }
+            ctx->h_cnt2[m] = 0;
             if (f.n > 0) {
                 const unsigned chunk = SFS_CHUNK;
                 CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
                 CU(cudaMemsetAsync(f.items, 0, (size_t)f.max_items * sizeof(WorkItem), ctx->stream)); // count 0 ends a CTA's round-robin walk
+                f.items_ok = false; // the list now holds the streaming kernel's chunks
                 if (f.n_sorted > 0) {
                     const int n_tiles = f.nti * f.ntj;
                     k_build_chunks<<<(n_tiles + 127) / 128, 128, 0, ctx->stream>>>(f.offs, n_tiles, f.items, f.d_nitems, f.max_items, chunk);
@@ -1309,7 +1309,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                 k_stream_step<<<ctx->stream_grid, SFS_THREADS, SFS_SMEM_BYTES, ctx->stream>>>(sa, ctx->d_args + m);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
-                if (ctx->path == 0) { // the tiled kernel runs the next steps: its work items follow the new layout
+                { // a later step may be a tiled one (SFGPU_STEP_INPLACE, or the context default): its work items follow the new layout
                     CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
                     const int n_tiles = f.nti * f.ntj;
                     k_build_items<<<(n_tiles + 127) / 128, 128, 0, ctx->stream>>>(f.offs_out, n_tiles, f.items, f.d_nitems, f.max_items);
@@ -1331,7 +1331,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             int64_t tail_first = 0;
             if (!untiled && f.n_sorted > 0 && f.n_items > 0) {
                 CU(cudaMemcpyAsync(ctx->d_args + m, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
-                ctx->fast_kernel<<<ctx->fast_grid, SF_FAST_THREADS, SF_FAST_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                k_fast_step<<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
                 tail_first = f.n_sorted;
@@ -1352,6 +1352,13 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         { ctx->last_launches++; ctx->launch_total++; }
     }
     CU(cudaEventRecord(ctx->evk1, ctx->stream));
+    // single mesh, nothing deferred: the cross-GPU sum and the running sums are enqueued behind the step kernels, so the
+    // whole step costs ONE host synchronisation (the counters below)
+    const bool fused_finish = !multi && !(flags & SFGPU_STEP_DEFER_FINISH);
+    if (fused_finish) {
+        rc = enqueue_finish(ctx, s);
+        if (rc) return rc;
+    }
     rc = read_counters(ctx);
     if (rc) return rc;
     // transfer sweeps, KM:131-142
@@ -1415,9 +1422,9 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             f.n = fn;
             f.n_sorted = n_sorted;
             f.stream_ok = true;
-            f.tiled_ok = false;
             f.steps_since_sort = 1; // the output is ordered by the cell each particle had BEFORE this push
-            if (ctx->path == 0) f.n_items = ctx->h_cnt2[m] < f.max_items ? ctx->h_cnt2[m] : f.max_items;
+            f.n_items = ctx->h_cnt2[m] < f.max_items ? ctx->h_cnt2[m] : f.max_items;
+            f.items_ok = true;
         } else {
             if (fn > f.cap) fn = f.cap;
             if (fn < f.n) fn = f.n;
@@ -1434,19 +1441,20 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     // too many particles drifted out of their warp tiles: sort before the next step instead of waiting for the interval
     ctx->force_sort = !untiled && !stream && (int64_t)ctx->last_fallback * 64 > n_total;
     ctx->last_kernel = untiled ? 2 : (stream ? 1 : 0);
+    if (fused_finish) {
+        ctx->timing_valid = true;
+        for (int k = 0; k < 5; k++) s.sums[k] = ctx->h_cnt->sums[k];
+        return 0;
+    }
     s.step_open = true;
     if (flags & SFGPU_STEP_DEFER_FINISH) return 0;
     return sfgpu_finish_step(ctx, sp);
 }
 
-// cross-GPU sum of the deposit (particles are partitioned, the mesh is replicated) and of the
-// mover sums; closes the step opened by sfgpu_step
-extern "C" int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp)
+// stream-ordered tail of a step: cross-GPU sum of the deposit and of the mover sums (particles are partitioned,
+// the mesh is replicated), then updateSamples (KM:1570-1595: the per-step increments of the running sums are the raw deposit)
+static int enqueue_finish(sfgpu_ctx *ctx, Species &s)
 {
-    CHECK_CTX();
-    CHECK_SP();
-    Species &s = ctx->species[sp];
-    if (!s.step_open) return fail(ctx, SFGPU_ESTATE, "sfgpu_finish_step without an open step");
     const int nmesh = (int)ctx->meshes.size();
     if (ctx->comm) {
         for (int m = 0; m < nmesh; m++) {
@@ -1457,7 +1465,6 @@ extern "C" int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp)
         int r = g_nccl.AllReduce(ctx->d_cnt->sums, ctx->d_cnt->sums, 5, SF_NCCL_FLOAT64, SF_NCCL_SUM, ctx->comm, ctx->stream);
         if (r) return fail(ctx, SFGPU_ENCCL, "ncclAllReduce(sums): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     }
-    // updateSamples, KM:1570-1595: the per-step increments of the running sums are the raw deposit
     for (int m = 0; m < nmesh; m++) {
         const size_t cnt = (size_t)SFGPU_NFIELDS * ctx->meshes[m].dev.ni * ctx->meshes[m].dev.nj;
         k_accumulate<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(s.pops[m].samp, s.pops[m].dep, cnt);
@@ -1465,8 +1472,20 @@ extern "C" int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp)
         CU(cudaGetLastError());
     }
     s.num_samples++;
-    CU(cudaMemcpyAsync(ctx->h_cnt->sums, ctx->d_cnt->sums, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    return 0;
+}
+
+// closes the step opened by sfgpu_step(SFGPU_STEP_DEFER_FINISH) (or a multi-mesh step)
+extern "C" int sfgpu_finish_step(sfgpu_ctx *ctx, int32_t sp)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    Species &s = ctx->species[sp];
+    if (!s.step_open) return fail(ctx, SFGPU_ESTATE, "sfgpu_finish_step without an open step");
+    int rc = enqueue_finish(ctx, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_cnt->sums, ctx->d_cnt->sums, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->timing_valid = true;
     for (int k = 0; k < 5; k++) s.sums[k] = ctx->h_cnt->sums[k];

@@ -628,13 +628,14 @@ __global__ void k_build_chunks(const unsigned *__restrict__ offs, int n_tiles, W
     const unsigned b = offs[(size_t)t * SF_TILE * SF_TILE], e = offs[(size_t)(t + 1) * SF_TILE * SF_TILE];
     if (e <= b) return;
     const unsigned cnt = e - b, pieces = (cnt + chunk - 1) / chunk;
-    const unsigned per = (cnt + pieces - 1) / pieces;
     const unsigned s = atomicAdd(n_items, pieces);
     for (unsigned k = 0; k < pieces && s + k < max_items; k++) {
-        const unsigned pb = b + k * per, pe = min(e, pb + per);
+        // piece k = [b + k*cnt/pieces, b + (k+1)*cnt/pieces): never empty (pieces <= cnt), so a count of 0 can only be the
+        // end-of-list marker the round-robin walk of k_stream_step stops at
+        const unsigned pb = b + (unsigned)((unsigned long long)k * cnt / pieces), pe = b + (unsigned)((unsigned long long)(k + 1) * cnt / pieces);
         WorkItem w;
         w.begin = pb;
-        w.count = pe > pb ? (int)(pe - pb) : 0;
+        w.count = (int)(pe - pb);
         w.tile = t;
         items[s + k] = w;
     }

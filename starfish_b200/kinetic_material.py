@@ -76,8 +76,9 @@ _SAMPLE_NAMES = ("count-sum", "u-sum", "v-sum", "w-sum", "uu-sum", "vv-sum", "ww
 
 
 class _Fields(dict):
-    """Per-mesh result fields.  nd/u/v/w are refreshed by every updateFields(); the running velocity-moment sums live
-    on the device (KM:1570-1595) and are fetched when somebody reads them, like Java's computeFields() every 10 steps."""
+    """Per-mesh result fields.  ``nd`` is refreshed by every updateFields() (the field solver reads it every step,
+    SolverModule.java:144-171); the mean velocities u/v/w and the running velocity-moment sums (KM:1570-1595) stay on
+    the device and are fetched when somebody reads them, like Java's computeFields() every 10 steps and the output writers."""
 
     def __init__(self, km, k):
         super().__init__()
@@ -86,6 +87,8 @@ class _Fields(dict):
     def __getitem__(self, name):
         if name in _SAMPLE_NAMES:
             self._km._fetch_samples(self._k)
+        elif name in ("u", "v", "w"):
+            self._km._fetch_velocities(self._k)
         return super().__getitem__(name)
 
 
@@ -151,6 +154,8 @@ class KineticMaterial:
         self._dep = [self.hostArray((NFIELDS, m.ni, m.nj)) for m in self.meshes]
         self._dep_step = [-1] * len(self.meshes)
         self._samp_step = [-1] * len(self.meshes)
+        self._vel_step = [-1] * len(self.meshes)
+        self.download_fields = True  # False on the ranks of a multi-GPU run that do not feed the host solver (read back once)
         self._step_no = 0
         self.last_deposit = _LazyDeposit(self)
         self.mass_sum = 0.0
@@ -275,9 +280,15 @@ class KineticMaterial:
         self._step_no += 1
         for k in range(len(self.meshes)):
             f = self.fields[k]
-            # nd,u,v,w of updateFields(MeshData), KM:168-197: what the rest of Starfish reads every step
-            self._check(self.lib.sfgpu_get_moments(self._ctx, self._sp, k, *[C.c_void_p(dict.__getitem__(f, q).ctypes.data)
-                                                                              for q in ("nd", "u", "v", "w")]))
+            # nd of updateFields(MeshData), KM:168-197: what the field solver reads every step; u,v,w follow on first access
+            if self.download_fields:
+                self._check(self.lib.sfgpu_get_moments(self._ctx, self._sp, k, C.c_void_p(dict.__getitem__(f, "nd").ctypes.data), None, None, None))
+
+    def _fetch_velocities(self, k):
+        if self._vel_step[k] != self._step_no:
+            f = self.fields[k]
+            self._check(self.lib.sfgpu_get_moments(self._ctx, self._sp, k, None, *[C.c_void_p(dict.__getitem__(f, q).ctypes.data) for q in ("u", "v", "w")]))
+            self._vel_step[k] = self._step_no
 
     def _fetch_deposit(self, k):
         if self._dep_step[k] != self._step_no:

@@ -109,6 +109,30 @@ def test_streaming_resort_and_hybrid_schedule(knob, monkeypatch):
         compare_fields(km, ok)
 
 
+@pytest.mark.parametrize("path", ["stream", "tiled"])
+def test_step_kernels_alternate_from_step_to_step(path, monkeypatch):
+    """The step flags are interchangeable from one step to the next (sfgpu.h): a tiled in-place step right after a streaming
+    step must see work items of the slab the streaming step wrote (round-1 advisor finding: under SFGPU_PATH=stream the items
+    still described the previous slab), with injection and exits in between."""
+    monkeypatch.setenv("SFGPU_PATH", path)
+    monkeypatch.setenv("SFGPU_STREAM_CHECK", "1")
+    m = S.make_mesh(70, 50, DomainType.XY, 1e-3, "open")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 6, vth_cells=0.6, kick_frac=0.1)
+    km, ok = make_pair([m], wl, [wl.particles(0, 30000)], 0)
+    seq = [_lib.STEP_STREAM, _lib.STEP_INPLACE, _lib.STEP_INPLACE, _lib.STEP_STREAM, 0, _lib.STEP_INPLACE, _lib.STEP_STREAM, _lib.STEP_STREAM, _lib.STEP_INPLACE]
+    with km:
+        km.setSortInterval(5)
+        for it, fl in enumerate(seq):
+            if it in (2, 6):
+                arr = wl.particles(100000 * (it + 1), 3000)
+                assert km.addParticles(m, to_particles(arr), wl.dt) == ok.addParticles(0, arr, wl.dt)
+            km.step_flags = fl
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            compare_state(km, ok)
+            compare_fields(km, ok)
+
+
 @pytest.mark.parametrize("flags", PATHS)
 def test_fast_particles_many_bounces_and_residual_dt(flags):
     """CFL >> 1 on a tiny symmetric box: >10 bounces leaves dt > 0 that is added to the next step (KM:333, :360)."""
@@ -464,3 +488,54 @@ def test_full_size_properties_config_b(n, flags):
         lx = (m.ni - 1) * m.dh[0]
         assert p.x.min() >= 0 and p.x.max() <= lx and p.y.min() >= 0 and p.y.max() <= lx
         assert np.array_equal(np.sort(p.id), np.arange(n, dtype=np.int32))  # a permutation: nobody lost or duplicated
+
+
+def _full_size_vs_oracle(wl, n, steps, flags, inject_every=0, theta_tol=1e-12):
+    """Whole BASELINE configuration against the oracle (threads = host cores for the mover, serial deposit): ids, cell
+    indices and x/y/u/v/w bit exact, deposit within 1e-10, cell counts exact."""
+    import os
+    m = wl.mesh
+    km = KineticMaterial("O+", wl.charge, wl.mass, [m], m.domain_type, capacity_hint=n + (n // 8 if inject_every else 0), step_flags=flags)
+    ok = O.OracleKM(wl.charge, wl.mass, [m], threads=min(os.cpu_count() or 1, 32))
+    km.dt = wl.dt
+    with km:
+        chunk = 1 << 22
+        for first in range(0, n, chunk):
+            c = min(chunk, n - first)
+            arr = wl.particles(first, c)
+            assert km.addParticles(m, to_particles(arr), wl.dt) == ok.addParticles(0, arr, wl.dt)
+        for it in range(steps):
+            if inject_every and it % inject_every == 0:  # beam injection plane: the first half cell above z = 0
+                c = n // 64
+                arr = wl.particles(n + it * c, c)
+                arr["y"] = m.x0[1] + (arr["y"] - m.x0[1]) * (0.5 / (m.nj - 1))
+                assert km.addParticles(m, to_particles(arr), wl.dt) == ok.addParticles(0, arr, wl.dt)
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            assert km.getNp() == ok.getNp() and km.n_exited == ok.n_exited
+        compare_fields(km, ok)
+        g = km.getParticles(m).sorted_by_id()
+        o = ok.sorted_parts(0)
+        assert np.array_equal(g.id, o["id"])
+        for key in ("x", "y", "u", "v", "w", "mpw", "li", "lj", "dt"):
+            assert np.array_equal(getattr(g, key), o[key], equal_nan=True), key
+        if m.domain_type == DomainType.XY:
+            assert np.array_equal(g.z, o["z"])
+        else:
+            assert np.allclose(g.z, o["z"], rtol=theta_tol, atol=1e-300)
+        return km.n_exited
+
+
+@pytest.mark.parametrize("flags", BOTH)
+def test_full_size_config_b_matches_oracle(flags):
+    """BASELINE config B at full size (XY 512x512, 16,777,216 particles, periodic), 3 steps: every work-item split, tile
+    boundary and >2048-particles-per-tile path of the tiled kernel against the oracle, not only by conservation."""
+    _full_size_vs_oracle(S.config_b(), 1 << 24, 3, flags)
+
+
+@pytest.mark.parametrize("flags", BOTH)
+def test_config_c_beam_with_injection_and_exits_matches_oracle(flags):
+    """BASELINE config C geometry (RZ 1024x1024, beam over r < 0.25 Rmax, LEFT symmetry, open exits) at 2^24 particles with
+    beam injection every step; the rotation, the Ruyten weights, the symmetry axis and compaction at full mesh size."""
+    exited = _full_size_vs_oracle(S.config_c(), 1 << 24, 4, flags, inject_every=1)
+    assert exited > 0
