@@ -85,7 +85,8 @@ extern "C" {
 #define SFGPU_F_UU 4  /* += mpw*vel[0]^2   KM:1587         */
 #define SFGPU_F_VV 5  /* += mpw*vel[1]^2   KM:1588         */
 #define SFGPU_F_WW 6  /* += mpw*vel[2]^2   KM:1589         */
-#define SFGPU_F_MPC 7 /* += 1 per particle in cell ((int)lc0,(int)lc1), KM:1593 */
+#define SFGPU_F_MPC 7 /* += 1 per particle in cell ((int)lc0,(int)lc1), KM:1593; a particle whose (int)lc falls outside
+                         [0,ni) x [0,nj) is not counted (Java would throw ArrayIndexOutOfBounds there) */
 #define SFGPU_NFIELDS 8
 
 typedef struct sfgpu_ctx sfgpu_ctx;
@@ -133,7 +134,25 @@ void sfgpu_host_free(void *p);
 int sfgpu_mesh_add(sfgpu_ctx *ctx, int32_t ni, int32_t nj, const double x0[2], const double dh[2],
                    const int8_t *const bc[4], const int32_t *const nbr[4], const uint8_t *has_seg,
                    const double *node_vol, int32_t *mesh_id);
-/* efi/efj/bfi/bfj of MeshData, KM:1319-1322; bfi/bfj nullable => zero field */
+/* surface hits on the device.  The DIRICHLET / SINK LinearSegments (boundaries/LinearSegment.java) of node[i][j].segments
+ * (Mesh.setNodeControlVolumes, MESH:1215-1290) as a CSR over nodes i*nj+j (node_offs: ni*nj+1 entries, node_ids: segment indices), and per
+ * segment what Material.performSurfaceInteraction (Material.java:279-300) does to THIS material's particles: kind 0 = the particle is
+ * removed (no interaction listed, or ABSORB), kind 1 = it lives on unchanged (NONE; SPECULAR as SurfaceInteraction.java:82-125 is written);
+ * sink[k] != 0: the boundary is a SINK (KM:593-594).  With the table set, the segment part of ProcessBoundary (KM:482-603: nearest
+ * LinearSegment.intersect, start-of-step exclusion, 0.9999 back-off, dt_rem) runs inside sfgpu_step and such particles no longer come back
+ * through sfgpu_take_slowpath; hits are listed for sfgpu_take_surface_hits.  Models that draw random numbers (DIFFUSE / COSINE, sputtering,
+ * species change) keep the host path: do not register those boundaries' segments (has_seg of sfgpu_mesh_add still flags them).
+ * The node table replaces has_seg.  n_seg = 0 clears it. */
+int sfgpu_mesh_set_segments(sfgpu_ctx *ctx, int32_t mesh_id, int32_t n_seg, const double *x1, const double *y1, const double *x2,
+                            const double *y2, const int32_t *kind, const int32_t *sink, const int32_t *node_offs, const int32_t *node_ids);
+/* the surface hits of the last sfgpu_step in any order: mesh, segment index, t along the segment, velocity at impact, mpw, survived?
+ * (the arguments of addSurfaceMomentum / addSurfaceMassDeposit and the boundary_charge sum, KM:586-602).  Every array nullable;
+ * *n = hits of the step (min(*n, max) copied), *n_absorbed = particles the surfaces removed. */
+int sfgpu_take_surface_hits(sfgpu_ctx *ctx, int32_t sp, int64_t max, int32_t *mesh, int32_t *seg, double *t, double *u, double *v,
+                            double *w, double *mpw, int8_t *alive, int64_t *n, int64_t *n_absorbed);
+
+/* efi/efj/bfi/bfj of MeshData, KM:1319-1322; bfi/bfj nullable => zero field.  Page-locked sources (sfgpu_host_alloc) are copied
+ * asynchronously in stream order: leave them unchanged until the next sfgpu_step / sfgpu_sync returns. */
 int sfgpu_set_fields(sfgpu_ctx *ctx, int32_t mesh_id, const double *efi, const double *efj,
                      const double *bfi, const double *bfj);
 
@@ -214,7 +233,8 @@ int sfgpu_restart_load(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const void *
 
 /* explicit cell sort + compaction (sortParticlesToCells, KM:1150-1179: order only, no result change) */
 int sfgpu_sort(sfgpu_ctx *ctx, int32_t sp);
-/* sfgpu_step re-sorts the store by cell every `steps` steps (default 4, env SFGPU_SORT_EVERY) */
+/* sfgpu_step re-sorts the store by cell every `steps` steps (default 3, env SFGPU_SORT_EVERY).
+ * KineticMaterial.mergeParticles (KM:1008-1143, particle_merge_skip > 0) is NOT offered: materials that merge keep type="kinetic". */
 int sfgpu_set_sort_interval(sfgpu_ctx *ctx, int32_t steps);
 
 /* ---- multi GPU: particles are partitioned over contexts, meshes replicated ------------- */
@@ -225,14 +245,42 @@ int sfgpu_comm_init(sfgpu_ctx *ctx, int32_t nranks, int32_t rank, const void *id
  * run their own collective */
 int sfgpu_deposit_device_ptr(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, void **ptr, int64_t *count);
 
+/* ---- single-caller multi GPU ------------------------------------------- */
+/* Starfish's main loop is one thread (Starfish.java:77-121).  A group owns one context per GPU and a worker thread per context:
+ * every call below fans out to all GPUs concurrently and returns when all are done, so the single Java thread drives 8 GPUs
+ * without deadlocking on the NCCL all-reduce.  Meshes, segments and fields are replicated; injected particles are partitioned
+ * by index (contiguous, balanced; ids assigned from one counter so they stay unique); sfgpu_multi_step = sfgpu_step everywhere
+ * with the deposit and the mover sums all-reduced inside; results are read back once, from rank 0.  device_ids NULL: 0..n-1.
+ * Per-GPU entry points (slow path, download / upload, restart, surface hits) remain available through sfgpu_multi_ctx(g, rank). */
+typedef struct sfgpu_multi sfgpu_multi;
+int sfgpu_multi_create(int32_t n, const int32_t *device_ids, int domain_type, sfgpu_multi **out);
+void sfgpu_multi_destroy(sfgpu_multi *g);
+int32_t sfgpu_multi_size(sfgpu_multi *g);
+sfgpu_ctx *sfgpu_multi_ctx(sfgpu_multi *g, int32_t rank);
+const char *sfgpu_multi_last_error(sfgpu_multi *g);
+int sfgpu_multi_mesh_add(sfgpu_multi *g, int32_t ni, int32_t nj, const double x0[2], const double dh[2], const int8_t *const bc[4],
+                         const int32_t *const nbr[4], const uint8_t *has_seg, const double *node_vol, int32_t *mesh_id);
+int sfgpu_multi_mesh_set_segments(sfgpu_multi *g, int32_t mesh_id, int32_t n_seg, const double *x1, const double *y1, const double *x2,
+                                  const double *y2, const int32_t *kind, const int32_t *sink, const int32_t *node_offs, const int32_t *node_ids);
+int sfgpu_multi_set_fields(sfgpu_multi *g, int32_t mesh_id, const double *efi, const double *efj, const double *bfi, const double *bfj);
+int sfgpu_multi_species_add(sfgpu_multi *g, double charge, double mass, int64_t capacity_hint, int32_t *sp);
+int sfgpu_multi_inject(sfgpu_multi *g, int32_t sp, int32_t mesh_id, const sfgpu_particles *p, double dt_step, uint32_t flags, int64_t *n_added);
+int sfgpu_multi_step(sfgpu_multi *g, int32_t sp, double dt, uint32_t flags);
+int sfgpu_multi_finish_step(sfgpu_multi *g, int32_t sp);
+int sfgpu_multi_get_moments(sfgpu_multi *g, int32_t sp, int32_t mesh_id, double *nd, double *u, double *v, double *w);
+int sfgpu_multi_get_deposit(sfgpu_multi *g, int32_t sp, int32_t mesh_id, double *const out[SFGPU_NFIELDS]);
+int sfgpu_multi_get_samples(sfgpu_multi *g, int32_t sp, int32_t mesh_id, double *const out[SFGPU_NFIELDS], int64_t *num_samples);
+int sfgpu_multi_clear_samples(sfgpu_multi *g, int32_t sp);
+int sfgpu_multi_get_sums(sfgpu_multi *g, int32_t sp, double sums5[5], int64_t *np_alive, int64_t *n_exited, int64_t *n_slow);
+
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* device milliseconds of the last step, from CUDA events on the context's own stream: ms_total spans the
- * whole step (memsets, kernels, collective), ms_kernel only the fused move+deposit kernel(s) of the main
- * pass; launches = kernels launched by the step.  Any pointer nullable. */
+ * whole step (the periodic cell sort when one ran, memsets, kernels, collective, running sums), ms_kernel only the fused
+ * move+deposit kernel(s) of the main pass; launches = kernels launched by the step.  Any pointer nullable. */
 int sfgpu_last_step_timing(sfgpu_ctx *ctx, float *ms_total, float *ms_kernel, int32_t *launches);
-/* which step kernel ran in the last sfgpu_step: 0 = tiled in-place kernel, 1 = streaming kernel (moves, deposits and re-sorts),
- * 2 = generic.  The default path alternates: three tiled steps, then one streaming step where the reference's
- * sortParticlesToCells-style re-ordering (KM:1150-1179) is due. */
+/* which step kernel ran in the last sfgpu_step: 0 = tiled in-place kernel (the default; the store is re-sorted by cell every
+ * few steps, KM:1150-1179 being the closest reference member), 1 = streaming kernel (moves, deposits and re-sorts in one pass;
+ * SFGPU_STEP_STREAM or SFGPU_PATH=stream), 2 = generic (SFGPU_STEP_GENERIC). */
 int sfgpu_last_step_kernel(sfgpu_ctx *ctx, int32_t *kind);
 /* diagnostics of the last step: particles whose deposit missed the warp tile of their sort position and went
  * through global atomics instead (grows between cell sorts; the step re-sorts early when it passes 1/64) */

@@ -21,15 +21,25 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsf_oracle.so")
 
-ALIVE, REMOVED, DEAD, SLOW, TRANSFER = 0, 1, 2, 3, 4
+ALIVE, REMOVED, DEAD, SLOW, TRANSFER, ABSORBED = 0, 1, 2, 3, 4, 5
 _PK = ("x", "y", "z", "u", "v", "w", "mpw", "li", "lj", "dt")
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 
 
+class _Segment(C.Structure):
+    _fields_ = [("x1", C.c_double), ("y1", C.c_double), ("x2", C.c_double), ("y2", C.c_double), ("kind", C.c_int32), ("sink", C.c_int32)]
+
+
+class _Hits(C.Structure):
+    _fields_ = [("cap", C.c_int64), ("n", C.c_int64), ("seg", _ip), ("t", _dp), ("u", _dp), ("v", _dp), ("w", _dp), ("mpw", _dp),
+                ("alive", C.POINTER(C.c_int8))]
+
+
 class _Mesh(C.Structure):
     _fields_ = [("ni", C.c_int32), ("nj", C.c_int32), ("x0", C.c_double * 2), ("dh", C.c_double * 2),
                 ("domain_type", C.c_int32), ("bc", C.c_void_p * 4), ("nbr", C.c_void_p * 4), ("has_seg", C.c_void_p),
+                ("seg_offs", C.c_void_p), ("seg_ids", C.c_void_p), ("segs", C.c_void_p), ("hits", C.c_void_p),
                 ("efi", C.c_void_p), ("efj", C.c_void_p), ("bfi", C.c_void_p), ("bfj", C.c_void_p)]
 
 
@@ -117,14 +127,27 @@ class MeshSet:
     """C view of a list of mesh objects (duck typed: ni, nj, x0, dh, domain_type, bc[4], nbr[4], has_seg,
     efi, efj, bfi, bfj -- starfish_b200.domain.UniformMesh fits)."""
 
-    def __init__(self, meshes):
+    def __init__(self, meshes, use_segments=True, hit_cap=1 << 20):
         self.meshes = list(meshes)
         self.keep = []
+        self.use_segments, self.hit_cap = use_segments, hit_cap
+        self.hits = {}
         self.arr = (_Mesh * len(self.meshes))()
         self.refresh()
 
+    def take_hits(self, k):
+        """Surface hits recorded for mesh k since the last call (KM:586-602), as arrays."""
+        if k not in self.hits:
+            return None
+        h, hb = self.hits[k]
+        n = int(min(h.n, h.cap))
+        out = {key: v[:n].copy() for key, v in hb.items()}
+        h.n = 0
+        return out
+
     def refresh(self):
         self.keep = []
+        self.hits = {}
         for k, m in enumerate(self.meshes):
             c = self.arr[k]
             c.ni, c.nj = int(m.ni), int(m.nj)
@@ -140,6 +163,23 @@ class MeshSet:
             hs = np.ascontiguousarray(m.has_seg, np.uint8)
             self.keep.append(hs)
             c.has_seg = hs.ctypes.data if hs.any() else None
+            # segment tables (starfish_b200.domain.set_boundaries): with them the oracle runs the segment part of
+            # ProcessBoundary itself (KM:504-603), without them such particles come back as SLOW
+            c.seg_offs = c.seg_ids = c.segs = c.hits = None
+            sg = getattr(m, "segments", None)
+            if sg is not None and self.use_segments and hs.any():
+                arr = (_Segment * len(sg["x1"]))()
+                for q in range(len(sg["x1"])):
+                    arr[q] = _Segment(float(sg["x1"][q]), float(sg["y1"][q]), float(sg["x2"][q]), float(sg["y2"][q]), int(sg["kind"][q]), int(sg["sink"][q]))
+                offs, ids = np.ascontiguousarray(m.seg_offs, np.int32), np.ascontiguousarray(m.seg_ids, np.int32)
+                cap = self.hit_cap
+                hb = dict(seg=np.zeros(cap, np.int32), t=np.zeros(cap), u=np.zeros(cap), v=np.zeros(cap), w=np.zeros(cap), mpw=np.zeros(cap),
+                          alive=np.zeros(cap, np.int8))
+                h = _Hits(cap, 0, hb["seg"].ctypes.data_as(_ip), _d(hb["t"]), _d(hb["u"]), _d(hb["v"]), _d(hb["w"]), _d(hb["mpw"]),
+                          hb["alive"].ctypes.data_as(C.POINTER(C.c_int8)))
+                self.keep += [arr, offs, ids, hb, h]
+                self.hits[k] = (h, hb)
+                c.seg_offs, c.seg_ids, c.segs, c.hits = offs.ctypes.data, ids.ctypes.data, C.addressof(arr), C.addressof(h)
             for name in ("efi", "efj", "bfi", "bfj"):
                 a = getattr(m, name, None)
                 if a is None:
@@ -201,12 +241,14 @@ class OracleKM:
 
     FIELDS = ("count-sum", "u-sum", "v-sum", "w-sum", "uu-sum", "vv-sum", "ww-sum", "mpc-sum")
 
-    def __init__(self, charge, mass, meshes, threads=1):
+    def __init__(self, charge, mass, meshes, threads=1, use_segments=True):
         self.lib = load()
         self.charge, self.mass = float(charge), float(mass)
         self.qm = self.charge / self.mass  # Material.java:711
         self.meshes = list(meshes)
-        self.ms = MeshSet(self.meshes)
+        self.ms = MeshSet(self.meshes, use_segments=use_segments)
+        self.n_absorbed = 0
+        self.hits = []  # per step: surface hits per mesh (dict of arrays) in the order the mover met them
         self.threads = threads
         self.parts = [empty_parts() for _ in self.meshes]
         self.transfer = [empty_parts() for _ in self.meshes]
@@ -301,6 +343,7 @@ class OracleKM:
         self.slow = []
         self.n_exited = 0
         self.n_removed = 0
+        self.n_absorbed = 0
         sums = np.zeros(5)
         # moveParticles(false), KM:126
         for k in range(len(self.meshes)):
@@ -311,6 +354,7 @@ class OracleKM:
             self._slow(k, p, st, aux)
             self.n_exited += int((st == DEAD).sum())
             self.n_removed += int((st == REMOVED).sum())
+            self.n_absorbed += int((st == ABSORBED).sum())
             self.parts[k] = _take(p, st == ALIVE)
         self.sums5 = sums
         self.mass_sum = sums[0] * self.mass  # KM:252-258
@@ -328,10 +372,12 @@ class OracleKM:
                 self._slow(k, tp, st, aux)
                 self.n_exited += int((st == DEAD).sum())
                 self.n_removed += int((st == REMOVED).sum())
+                self.n_absorbed += int((st == ABSORBED).sum())
                 ok = (st == ALIVE) & np.isfinite(tp["u"]) & np.isfinite(tp["v"]) & np.isfinite(tp["w"])
                 self.parts[k] = _concat(self.parts[k], _take(tp, ok))
             if sum(len(t["x"]) for t in self.transfer) == 0:
                 break
+        self.hits = [self.ms.take_hits(k) for k in range(len(self.meshes))]
         self.deposit()
 
     def deposit(self):

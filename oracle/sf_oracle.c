@@ -168,6 +168,94 @@ static int bbox_has_segments(const sfo_mesh *m, double li, double lj, double lio
     return 0;
 }
 
+/* LinearSegment.InfiniteLineIntersect + intersect, LinearSegment.java:113-179 */
+void sfo_segment_intersect(const sfo_segment *s, const double p3[2], const double p4[2], double t[2])
+{
+    const double x1 = s->x1, x2 = s->x2, x3 = p3[0], x4 = p4[0];
+    const double y1 = s->y1, y2 = s->y2, y3 = p3[1], y4 = p4[1];
+    const double den = (x1 - x2) * (y3 - y4) - (y1 - y2) * (x3 - x4);
+    t[0] = -1;
+    t[1] = -1;
+    if (den == 0) return;
+    const double xp0 = ((x1 * y2 - y1 * x2) * (x3 - x4) - (x1 - x2) * (x3 * y4 - y3 * x4)) / den;
+    const double xp1 = ((x1 * y2 - y1 * x2) * (y3 - y4) - (y1 - y2) * (x3 * y4 - y3 * x4)) / den;
+    double t0, t1;
+    if (fabs(x2 - x1) > 1e-6) t0 = (xp0 - x1) / (x2 - x1);
+    else t0 = (xp1 - y1) / (y2 - y1);
+    if (t0 < -FLT_EPS || t0 > (1 + FLT_EPS)) return;
+    if (fabs(x4 - x3) > 1e-6) t1 = (xp0 - x3) / (x4 - x3);
+    else t1 = (xp1 - y3) / (y4 - y3);
+    if (t1 < -FLT_EPS || t1 > (1 + FLT_EPS)) return;
+    if (t0 < 0) t0 = 0;
+    if (t1 < 0) t1 = 0;
+    if (t0 > 1) t0 = 1;
+    if (t1 > 1) t1 = 1;
+    t[0] = t0;
+    t[1] = t1;
+}
+
+/* segment part of ProcessBoundary, KM:504-603, for LinearSegments with a deterministic surface outcome.
+ * Returns 0: no hit, 1: hit and alive (pos, lc, *dtp updated), 2: hit and removed. */
+static int process_segments(const sfo_mesh *m, double dt0, const double old[2], double lio, double ljo, double pos[3], const double vel[3],
+                            double mpw, double *li, double *lj, double *dtp)
+{
+    /* the node bounding box of the sub-step, KM:482-502 */
+    double mn0 = (*li != *li || lio != lio) ? NAN : (*li < lio ? *li : lio);
+    double mn1 = (*lj != *lj || ljo != ljo) ? NAN : (*lj < ljo ? *lj : ljo);
+    double mx0 = (*li != *li || lio != lio) ? NAN : (*li > lio ? *li : lio);
+    double mx1 = (*lj != *lj || ljo != ljo) ? NAN : (*lj > ljo ? *lj : ljo);
+    int i_min = j2i(mn0), i_max = j2i(mx0), j_min = j2i(mn1), j_max = j2i(mx1);
+    if (i_min < 0) i_min = 0;
+    if (j_min < 0) j_min = 0;
+    if (i_max >= m->ni) i_max = m->ni - 1;
+    if (j_max >= m->nj) j_max = m->nj - 1;
+    double tp_min = 2.0, tsurf_min = 0;
+    int seg_min = -1;
+    for (int i = i_min; i <= i_max; i++)
+        for (int j = j_min; j <= j_max; j++) {
+            const int64_t node = (int64_t)i * m->nj + j;
+            for (int k = m->seg_offs[node]; k < m->seg_offs[node + 1]; k++) { /* (a segment met twice gives the same t: the set of KM:505 is not needed) */
+                const sfo_segment *seg = &m->segs[m->seg_ids[k]];
+                double t[2];
+                sfo_segment_intersect(seg, old, pos, t);
+                const double t_part = t[1];
+                if (t_part > 0) { /* KM:535 */
+                    double dx = seg->x2 - seg->x1, dy = seg->y2 - seg->y1; /* LinearSegment.java:26-44 */
+                    const double len = sqrt(dx * dx + dy * dy);
+                    dx /= len;
+                    dy /= len;
+                    const double acos_ = (-dy * vel[0] + dx * vel[1]) / sqrt(vel[0] * vel[0] + vel[1] * vel[1]);
+                    if (t_part < FLT_EPS && acos_ > 0) continue; /* KM:541-544 */
+                    if (t_part < tp_min) {
+                        tp_min = t_part;
+                        tsurf_min = t[0];
+                        seg_min = m->seg_ids[k];
+                    }
+                }
+            }
+        }
+    if (seg_min < 0) return 0;
+    tp_min *= 0.9999; /* KM:562 */
+    pos[0] = old[0] + tp_min * (pos[0] - old[0]);
+    pos[1] = old[1] + tp_min * (pos[1] - old[1]);
+    sfo_xtol(m, pos[0], pos[1], li, lj);
+    *dtp = dt0 * (1 - tp_min);
+    if (*li < 0 && *li > -FLT_EPS) *li = 0; /* KM:574-577 */
+    if (*lj < 0 && *lj > -FLT_EPS) *lj = 0;
+    const sfo_segment *seg = &m->segs[seg_min];
+    int alive = seg->kind != 0; /* performSurfaceInteraction, KM:586-587 */
+    if (seg->sink) alive = 0;   /* KM:593-594 */
+    if (m->hits) {
+        const int64_t h = __sync_fetch_and_add(&m->hits->n, 1);
+        if (h < m->hits->cap) {
+            m->hits->seg[h] = seg_min; m->hits->t[h] = tsurf_min;
+            m->hits->u[h] = vel[0]; m->hits->v[h] = vel[1]; m->hits->w[h] = vel[2];
+            m->hits->mpw[h] = mpw; m->hits->alive[h] = (int8_t)alive;
+        }
+    }
+    return alive ? 1 : 2;
+}
+
 /* ParticleMover.run, KM:298-422 with ProcessBoundary's domain-exit part, KM:605-749 */
 void sfo_move(const sfo_mesh *meshes, int mesh_id, double qm, double charge, double dt,
               int particle_transfer, sfo_particles *p, int64_t first, int64_t count,
@@ -223,7 +311,8 @@ void sfo_move(const sfo_mesh *meshes, int mesh_id, double qm, double charge, dou
             sfo_xtol(m, pos[0], pos[1], &li, &lj); /* KM:384 */
 
             /* ---- ProcessBoundary, KM:471-750 ---- */
-            if (bbox_has_segments(m, li, lj, lio, ljo)) {
+            const int near_segments = bbox_has_segments(m, li, lj, lio, ljo);
+            if (near_segments && !m->segs) {
                 /* segment intersection + surface interaction stay in Java; hand the particle
                  * over in its pre-ProcessBoundary state */
                 st = SFO_SLOW;
@@ -231,8 +320,17 @@ void sfo_move(const sfo_mesh *meshes, int mesh_id, double qm, double charge, dou
                 alive = 0;
                 break;
             }
-            const double dt0 = dtp, xs = pos[0], ys = pos[1], lis = li, ljs = lj;
+            const double dt0 = dtp;
             dtp = 0; /* KM:475-476 */
+            if (near_segments) {
+                const double old[2] = {xo, yo};
+                if (process_segments(m, dt0, old, lio, ljo, pos, vel, p->mpw[q], &li, &lj, &dtp) == 2) {
+                    st = SFO_ABSORBED;
+                    alive = 0;
+                    break;
+                }
+            }
+            const double xs = pos[0], ys = pos[1], lis = li, ljs = lj;
             if (li < 0 || lj < 0 || li >= ni - 1 || lj >= nj - 1) { /* KM:606 */
                 double t_right = 99, t_top = 99, t_left = 99, t_bottom = 99;
                 if (li >= ni - 1) t_right = (ni - 1.0 - lio) / (li - lio);

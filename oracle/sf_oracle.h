@@ -42,8 +42,30 @@ enum {
     SFO_DEAD = 2,      /* left through OPEN / default face, or CIRCUIT ion                 */
     SFO_SLOW = 3,      /* needs the Java slow path: a DIRICHLET/SINK segment is attached to
                           a node of the move's bounding box (KM:504-603) or CIRCUIT electron */
-    SFO_TRANSFER = 4   /* crossed a MESH face, KM:708-722; dead here, copies listed        */
+    SFO_TRANSFER = 4,  /* crossed a MESH face, KM:708-722; dead here, copies listed        */
+    SFO_ABSORBED = 5   /* hit a segment whose surface model removes it, KM:586-603          */
 };
+
+/* a DIRICHLET / SINK LinearSegment of a solid Boundary as ProcessBoundary sees it (LinearSegment.java:21-47, :113-179)
+ * with the outcome of Material.performSurfaceInteraction (Material.java:279-300) folded into `kind` */
+typedef struct {
+    double x1, y1, x2, y2;
+    int32_t kind;  /* 0: the particle dies (no interaction listed, or ABSORB: SurfaceInteraction.java:72-79);
+                      1: it lives on with unchanged velocity (NONE, and SPECULAR as the reference implements it:
+                         the reflection arithmetic of SurfaceInteraction.java:86-104 sits inside a comment) */
+    int32_t sink;  /* the Boundary is of type SINK: dies regardless, KM:593-594 */
+} sfo_segment;
+
+/* surface hits of a mover pass, in the order they happen (single thread) / any order (sfo_move_mt): what the Java
+ * side needs for addSurfaceMomentum / addSurfaceMassDeposit / boundary_charge, KM:590-602 */
+typedef struct {
+    int64_t cap, n;
+    int32_t *seg;      /* segment index                     */
+    double *t;         /* position along the segment [0,1]  */
+    double *u, *v, *w; /* velocity at impact                */
+    double *mpw;
+    int8_t *alive;
+} sfo_hits;
 
 typedef struct {
     int32_t ni, nj;            /* node counts                                  */
@@ -53,6 +75,12 @@ typedef struct {
                                   TOP/BOTTOM: ni entries (MESH:167, :215)        */
     const int32_t *nbr[4];     /* per-face per-node 2 neighbour mesh ids (or -1), nullable */
     const uint8_t *has_seg;    /* ni*nj, 1 where node.segments holds a DIRICHLET/SINK segment; nullable */
+    /* node.segments (MESH:1215-1290) restricted to DIRICHLET / SINK segments, as CSR over nodes i*nj+j; all nullable:
+     * without them a particle whose sub-step touches a has_seg node is handed back as SFO_SLOW */
+    const int32_t *seg_offs;   /* ni*nj + 1 */
+    const int32_t *seg_ids;
+    const sfo_segment *segs;
+    sfo_hits *hits;            /* nullable */
     const double *efi, *efj;   /* ni*nj each                                   */
     const double *bfi, *bfj;   /* nullable => zero field                       */
 } sfo_mesh;
@@ -94,6 +122,8 @@ void sfo_uniform_source(const sfo_spline *s, int cold_beam, double v_drift, doub
                         const sfo_mesh *meshes, int n_meshes, double *x, double *y, double *z, double *u, double *v,
                         double *w, int32_t *mesh_of);
 
+/* LinearSegment.intersect(p3, p4), LinearSegment.java:113-160: t[0] along the segment, t[1] along p3->p4, (-1,-1) if none */
+void sfo_segment_intersect(const sfo_segment *s, const double p3[2], const double p4[2], double t[2]);
 double sfo_gather(const double *d, int ni, int nj, double fi, double fj);      /* F2D:300-350 */
 double sfo_gather_safe(const double *d, int ni, int nj, double fi, double fj); /* F2D:371-390 */
 void sfo_scatter(double *d, const sfo_mesh *m, double fi, double fj, double val); /* F2D:244-295 */

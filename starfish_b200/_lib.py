@@ -48,6 +48,26 @@ EXPORTS = {
     "sfgpu_last_error": (C.c_char_p, [C.c_void_p]),
     "sfgpu_mesh_add": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, c_int32_p]),
+    "sfgpu_mesh_set_segments": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
+    "sfgpu_take_surface_hits": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, c_int32_p, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                          C.POINTER(C.c_int8), c_int64_p, c_int64_p]),
+    "sfgpu_multi_create": (C.c_int, [C.c_int32, c_int32_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "sfgpu_multi_destroy": (None, [C.c_void_p]),
+    "sfgpu_multi_size": (C.c_int32, [C.c_void_p]),
+    "sfgpu_multi_ctx": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "sfgpu_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "sfgpu_multi_mesh_add": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, c_int32_p]),
+    "sfgpu_multi_mesh_set_segments": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
+    "sfgpu_multi_set_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sfgpu_multi_species_add": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int64, c_int32_p]),
+    "sfgpu_multi_inject": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Particles), C.c_double, C.c_uint32, c_int64_p]),
+    "sfgpu_multi_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_uint32]),
+    "sfgpu_multi_finish_step": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sfgpu_multi_get_moments": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sfgpu_multi_get_deposit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "sfgpu_multi_get_samples": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),
+    "sfgpu_multi_clear_samples": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sfgpu_multi_get_sums": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_int64_p, c_int64_p, c_int64_p]),
     "sfgpu_set_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfgpu_species_add": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int64, c_int32_p]),
     "sfgpu_inject": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Particles), C.c_double, C.c_uint32, c_int64_p]),

@@ -25,6 +25,16 @@ enum : int {
     SF_DEAD = 2,     // OPEN / default face, CIRCUIT ion
     SF_SLOW = 3,     // host must run ProcessBoundary
     SF_TRANSFER = 4, // MESH hand-off, KM:708-722
+    SF_ABSORBED = 5, // removed by the surface it hit, KM:586-603
+};
+
+// surface hits of a step (what the host needs for addSurfaceMomentum / addSurfaceMassDeposit / boundary_charge, KM:590-602)
+struct HitList {
+    int *seg, *mesh;
+    double *t, *u, *v, *w, *mpw;
+    signed char *alive;
+    unsigned long long cap;
+    unsigned long long *n; // cursor (device)
 };
 
 struct MeshDev {
@@ -40,6 +50,13 @@ struct MeshDev {
     const int8_t *bc[4];
     const int *nbr[4];
     const uint8_t *has_seg;
+    // node.segments restricted to DIRICHLET / SINK linear segments (sfgpu_mesh_set_segments): CSR over nodes i*nj+j.
+    // Null: particles near a has_seg node are handed to the host (SF_SLOW) instead.
+    const int *seg_offs, *seg_ids;
+    const double4 *seg_xy; // x1, y1, x2, y2
+    const int2 *seg_kind;  // {0: dies / 1: lives on unchanged, boundary is a SINK}
+    HitList hits;
+    int id;                // index of this mesh
     const double *efi, *efj, *bfi, *bfj;
     const double *node_vol;
 };
@@ -211,6 +228,86 @@ __device__ __forceinline__ bool sf_bbox_has_segments(const MeshDev &m, double li
     return false;
 }
 
+// LinearSegment.intersect(p3, p4), LinearSegment.java:113-179: t0 along the segment, t1 along p3 -> p4; false if none
+__device__ __forceinline__ bool sf_segment_intersect(const double4 sg, double x3, double y3, double x4, double y4, double &t0, double &t1)
+{
+    const double x1 = sg.x, y1 = sg.y, x2 = sg.z, y2 = sg.w;
+    const double den = (x1 - x2) * (y3 - y4) - (y1 - y2) * (x3 - x4);
+    if (den == 0) return false;
+    const double xp0 = ((x1 * y2 - y1 * x2) * (x3 - x4) - (x1 - x2) * (x3 * y4 - y3 * x4)) / den;
+    const double xp1 = ((x1 * y2 - y1 * x2) * (y3 - y4) - (y1 - y2) * (x3 * y4 - y3 * x4)) / den;
+    if (fabs(x2 - x1) > 1e-6) t0 = (xp0 - x1) / (x2 - x1);
+    else t0 = (xp1 - y1) / (y2 - y1);
+    if (t0 < -SF_FLT_EPS || t0 > (1 + SF_FLT_EPS)) return false;
+    if (fabs(x4 - x3) > 1e-6) t1 = (xp0 - x3) / (x4 - x3);
+    else t1 = (xp1 - y3) / (y4 - y3);
+    if (t1 < -SF_FLT_EPS || t1 > (1 + SF_FLT_EPS)) return false;
+    if (t0 < 0) t0 = 0;
+    if (t1 < 0) t1 = 0;
+    if (t0 > 1) t0 = 1;
+    if (t1 > 1) t1 = 1;
+    return true;
+}
+
+// segment part of ProcessBoundary, KM:482-603, for linear segments whose surface outcome is deterministic.
+// 0: no hit; 1: hit, alive (p.x, p.y, p.li, p.lj, p.dt updated); 2: hit and removed.
+__device__ __noinline__ int sf_process_segments(const MeshDev *mp, double dt0, double xo, double yo, double lio, double ljo, PState *pp)
+{
+    const MeshDev &m = *mp;
+    PState &p = *pp;
+    int i_min = sf_min_i(p.li, lio), i_max = sf_max_i(p.li, lio);
+    int j_min = sf_min_i(p.lj, ljo), j_max = sf_max_i(p.lj, ljo);
+    if (i_min < 0) i_min = 0;
+    if (j_min < 0) j_min = 0;
+    if (i_max >= m.ni) i_max = m.ni - 1;
+    if (j_max >= m.nj) j_max = m.nj - 1;
+    double tp_min = 2.0, tsurf_min = 0;
+    int seg_min = -1;
+    for (int i = i_min; i <= i_max; i++)
+        for (int j = j_min; j <= j_max; j++) {
+            const size_t node = (size_t)i * m.nj + j;
+            for (int k = m.seg_offs[node]; k < m.seg_offs[node + 1]; k++) { // (a segment met twice gives the same t: no set needed)
+                const int sid = m.seg_ids[k];
+                const double4 sg = m.seg_xy[sid];
+                double t0, t1;
+                if (!sf_segment_intersect(sg, xo, yo, p.x, p.y, t0, t1)) continue;
+                if (t1 > 0) { // KM:535
+                    double dx = sg.z - sg.x, dy = sg.w - sg.y; // LinearSegment.java:26-44
+                    const double len = sqrt(dx * dx + dy * dy);
+                    dx /= len;
+                    dy /= len;
+                    const double acos_ = (-dy * p.u + dx * p.v) / sqrt(p.u * p.u + p.v * p.v);
+                    if (t1 < SF_FLT_EPS && acos_ > 0) continue; // KM:541-544
+                    if (t1 < tp_min) {
+                        tp_min = t1;
+                        tsurf_min = t0;
+                        seg_min = sid;
+                    }
+                }
+            }
+        }
+    if (seg_min < 0) return 0;
+    tp_min *= 0.9999; // KM:562
+    p.x = xo + tp_min * (p.x - xo);
+    p.y = yo + tp_min * (p.y - yo);
+    p.li = (p.x - m.x0) / m.dhx;
+    p.lj = (p.y - m.y0) / m.dhy;
+    p.dt = dt0 * (1 - tp_min);
+    if (p.li < 0 && p.li > -SF_FLT_EPS) p.li = 0; // KM:574-577
+    if (p.lj < 0 && p.lj > -SF_FLT_EPS) p.lj = 0;
+    const int2 kd = m.seg_kind[seg_min];
+    const bool alive = kd.x != 0 && kd.y == 0; // performSurfaceInteraction KM:586-587, SINK KM:593-594
+    if (m.hits.n) {
+        const unsigned long long h = atomicAdd(m.hits.n, 1ULL);
+        if (h < m.hits.cap) {
+            m.hits.seg[h] = seg_min; m.hits.mesh[h] = m.id; m.hits.t[h] = tsurf_min;
+            m.hits.u[h] = p.u; m.hits.v[h] = p.v; m.hits.w[h] = p.w; m.hits.mpw[h] = p.mpw;
+            m.hits.alive[h] = alive ? 1 : 0;
+        }
+    }
+    return alive ? 1 : 2;
+}
+
 // MESH:1476-1483 on a uniform mesh
 __device__ __forceinline__ bool sf_contains_pos(const MeshDev &m, double x, double y, double &li, double &lj)
 {
@@ -263,13 +360,19 @@ __device__ __forceinline__ int sf_move(const MeshDev &m, const MeshDev *__restri
         exact_lc = true;
 
         // ---- ProcessBoundary ----
-        if (m.any_seg && sf_bbox_has_segments(m, p.li, p.lj, lio, ljo)) {
+        const bool near_segments = m.any_seg && sf_bbox_has_segments(m, p.li, p.lj, lio, ljo);
+        if (near_segments && !m.seg_offs) {
             aux.xo = xo; aux.yo = yo; aux.lio = lio; aux.ljo = ljo;
             aux.bounces = bounces;
             return SF_SLOW; // pre-ProcessBoundary state, dt still holds dt0
         }
         const double dt0 = p.dt;
         p.dt = 0; // KM:475-476
+        if (near_segments) {
+            const int hit = sf_process_segments(&m, dt0, xo, yo, lio, ljo, &p);
+            if (hit == 2) return SF_ABSORBED;
+            if (hit == 1) exact_lc = (p.li == (p.x - m.x0) / m.dhx) && (p.lj == (p.y - m.y0) / m.dhy); // (the tiny-negative clamp of KM:574-577)
+        }
         if (p.li < 0 || p.lj < 0 || p.li >= ni - 1 || p.lj >= nj - 1) { // KM:606
             const double xs = p.x, ys = p.y, lis = p.li, ljs = p.lj;
             double t_right = 99, t_top = 99, t_left = 99, t_bottom = 99;

@@ -93,6 +93,8 @@ __device__ __forceinline__ void fast_epilogue(const FastStepArgs &a, const MeshD
         deposit = true;
     } else if (st == SF_DEAD) {
         atomicAdd(&a.c->n_exited, 1ULL);
+    } else if (st == SF_ABSORBED) {
+        atomicAdd(&a.c->n_absorbed, 1ULL);
     } else if (st == SF_REMOVED) {
         atomicAdd(&a.c->n_removed, 1ULL);
     } else if (st == SF_TRANSFER) {
@@ -178,6 +180,7 @@ __device__ __noinline__ void fast_fallback(const MeshDev *mp, const PState *pp, 
 // paths are bit-identical; `ok` false means "not the common case": the caller re-runs the particle through
 // sf_move() from its original state.
 // ---------------------------------------------------------------------------------------------------------
+template <bool SEG> // SEG: the mesh has segment nodes; a sub-step whose node box touches one is not the common case
 __device__ __forceinline__ bool sf_move_simple(const MeshDev &m, double qm, double dt, PState &p)
 {
     const int ni = m.ni, nj = m.nj;
@@ -221,6 +224,12 @@ __device__ __forceinline__ bool sf_move_simple(const MeshDev &m, double qm, doub
     const double li = sf_div_exact(x - m.x0, m.dhx, m.rdhx, m.fastdiv); // UM:158-159
     const double lj = sf_div_exact(y - m.y0, m.dhy, m.rdhy, m.fastdiv);
     ok = ok && li >= 0 && lj >= 0 && li < m.nim1 && lj < m.njm1; // KM:606 (a NaN takes the general path)
+    if (SEG && ok) { // KM:482-518: a segment node in the node box of the sub-step sends it through ProcessBoundary proper
+        const int i2 = sf_j2i(li), j2 = sf_j2i(lj);
+        const uint8_t *hs = m.has_seg;
+        ok = abs(i2 - i) <= 1 && abs(j2 - j) <= 1 &&
+             !(hs[(size_t)i * nj + j] | hs[(size_t)i2 * nj + j] | hs[(size_t)i * nj + j2] | hs[(size_t)i2 * nj + j2]);
+    }
     if (ok) {
         p.x = x; p.y = y; p.z = z; p.u = un; p.v = vn; p.w = wn; p.li = li; p.lj = lj;
     }
@@ -249,6 +258,7 @@ __device__ __forceinline__ void sf_prefetch_batch(const FastPtrs &fs, double *st
 // ---------------------------------------------------------------------------------------------------------
 // tiled kernel: persistent warps pull work items from a queue; every lane carries SF_PPT particles per batch
 // ---------------------------------------------------------------------------------------------------------
+template <bool SEG>
 __global__ void __launch_bounds__(SF_FAST_WARPS * 32, SF_FAST_MIN_CTAS)
 k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restrict__ ga)
 {
@@ -262,7 +272,7 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     double *sIn = reinterpret_cast<double *>(sKey + 32 * SF_PPT + 4); // [2 stages][7][32 * SF_PPT] prefetched particle state
     const MeshDev &m = a.m;
     const size_t plane = (size_t)m.ni * m.nj;
-    const bool simple_ok = !m.has_b && !m.any_seg && a.dt > 0;
+    const bool simple_ok = !m.has_b && a.dt > 0 && (SEG || !m.any_seg);
 
     for (int k = lane; k < SF_TILE_DOUBLES + SF_EXTRA; k += 32) tile[k] = 0.0;
     if (lane == 0) sKey[32 * SF_PPT] = 0;
@@ -334,7 +344,7 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                 p[j].li = sf_div_exact(p[j].x - m.x0, m.dhx, m.rdhx, m.fastdiv); // the stored lc of a normal particle is exactly XtoL(pos)
                 p[j].lj = sf_div_exact(p[j].y - m.y0, m.dhy, m.rdhy, m.fastdiv);
                 p[j].dt = 0;
-                done[j] = present[j] && simple_ok && sf_move_simple(m, a.qm, a.dt, p[j]);
+                done[j] = present[j] && simple_ok && sf_move_simple<SEG>(m, a.qm, a.dt, p[j]);
             }
             int key[SF_PPT];
             DepW dw[SF_PPT];

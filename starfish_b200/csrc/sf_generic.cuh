@@ -158,6 +158,8 @@ k_generic_step(const MeshDev *__restrict__ meshes, int mesh_id, double qm, doubl
                 }
             }
         }
+        const unsigned absorbed = __ballot_sync(0xffffffffu, valid && st == SF_ABSORBED);
+        if ((threadIdx.x & 31) == 0 && absorbed) atomicAdd(&c->n_absorbed, (unsigned long long)__popc(absorbed));
         const unsigned dead = __ballot_sync(0xffffffffu, valid && st == SF_DEAD);
         const unsigned rem = __ballot_sync(0xffffffffu, valid && st == SF_REMOVED);
         if ((threadIdx.x & 31) == 0) {

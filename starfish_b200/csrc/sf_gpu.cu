@@ -137,6 +137,9 @@ struct MeshHost {
     int8_t *bc[4] = {nullptr, nullptr, nullptr, nullptr};
     int *nbr[4] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t *has_seg = nullptr;
+    int *seg_offs = nullptr, *seg_ids = nullptr; // node.segments as CSR (sfgpu_mesh_set_segments)
+    double4 *seg_xy = nullptr;
+    int2 *seg_kind = nullptr;
     double *fields = nullptr; // efi, efj, bfi, bfj packed
     double *node_vol = nullptr;
     bool needs_slow = false; // segments or a CIRCUIT face present
@@ -159,7 +162,7 @@ struct Species {
     int *slow_extra_i = nullptr;    // bounces, mesh
     int64_t slow_cap = 0, slow_n = 0;
     double sums[5] = {0, 0, 0, 0, 0};
-    int64_t n_exited = 0, n_removed = 0;
+    int64_t n_exited = 0, n_removed = 0, n_absorbed = 0, n_hits = 0;
     int64_t capacity_hint = 0;
     bool step_open = false; // sfgpu_step ran, sfgpu_finish_step pending
     int64_t num_samples = 0; // KM:1557
@@ -199,6 +202,8 @@ struct sfgpu_ctx {
     char *src_tmp = nullptr; // device scratch of sfgpu_source_uniform (sampled particles, flags, ranks, spline, scan storage)
     size_t src_bytes = 0;
     unsigned long long last_fallback = 0, last_flush = 0;
+    char *hit_slab = nullptr; // surface-hit list of a step: t,u,v,w,mpw [cap] doubles, seg, mesh [cap] ints, alive [cap] bytes
+    size_t hit_cap = 0;
     bool force_sort = false;
     std::string err;
 };
@@ -573,10 +578,11 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaMalloc(&ctx->d_xfer, sizeof(XferDev) * SF_MAX_MESHES));
         CU(cudaMalloc(&ctx->d_args, sizeof(FastStepArgs) * SF_MAX_MESHES));
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
-        CU(cudaFuncSetAttribute(k_fast_step, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_fast_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k_fast_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         int nsm = 0, per_sm = 0;
         CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_step, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_step<false>, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         if (per_sm < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
         ctx->fast_grid = nsm * per_sm;
         if (const char *e = getenv("SFGPU_FAST_GRID")) ctx->fast_grid = atoi(e) > 0 ? atoi(e) : ctx->fast_grid; // occupancy experiments
@@ -636,11 +642,16 @@ extern "C" void sfgpu_destroy(sfgpu_ctx *ctx)
             if (m.nbr[f]) cudaFree(m.nbr[f]);
         }
         if (m.has_seg) cudaFree(m.has_seg);
+        if (m.seg_offs) cudaFree(m.seg_offs);
+        if (m.seg_ids) cudaFree(m.seg_ids);
+        if (m.seg_xy) cudaFree(m.seg_xy);
+        if (m.seg_kind) cudaFree(m.seg_kind);
         if (m.fields) cudaFree(m.fields);
         if (m.node_vol) cudaFree(m.node_vol);
     }
     rec_free(ctx->tmp);
     if (ctx->d_meshes) cudaFree(ctx->d_meshes);
+    if (ctx->hit_slab) cudaFree(ctx->hit_slab);
     if (ctx->d_cnt) cudaFree(ctx->d_cnt);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     if (ctx->d_xfer) cudaFree(ctx->d_xfer);
@@ -728,9 +739,112 @@ extern "C" int sfgpu_mesh_add(sfgpu_ctx *ctx, int32_t ni, int32_t nj, const doub
         CU(cudaMemcpy(m.node_vol, node_vol, plane * sizeof(double), cudaMemcpyHostToDevice));
         d.node_vol = m.node_vol;
     }
+    d.seg_offs = nullptr; d.seg_ids = nullptr; d.seg_xy = nullptr; d.seg_kind = nullptr;
+    d.hits = HitList{};
+    d.id = (int)ctx->meshes.size();
     ctx->meshes.push_back(m);
     ctx->meshes_dirty = true;
     *mesh_id = (int)ctx->meshes.size() - 1;
+    return 0;
+}
+
+// the DIRICHLET / SINK linear segments of node.segments (Mesh.setNodeControlVolumes, MESH:1215-1290) with the
+// outcome Material.performSurfaceInteraction has for this material on each of them; the segment part of ProcessBoundary
+// (KM:482-603) then runs on the device and no particle of this mesh is handed to the host for it.
+extern "C" int sfgpu_mesh_set_segments(sfgpu_ctx *ctx, int32_t mesh_id, int32_t n_seg, const double *x1, const double *y1, const double *x2,
+                                       const double *y2, const int32_t *kind, const int32_t *sink, const int32_t *node_offs, const int32_t *node_ids)
+{
+    CHECK_CTX();
+    CHECK_MESH();
+    MeshHost &m = ctx->meshes[mesh_id];
+    if (n_seg < 0 || (n_seg > 0 && (!x1 || !y1 || !x2 || !y2 || !kind || !node_offs))) return fail(ctx, SFGPU_EINVAL, "sfgpu_mesh_set_segments: null argument");
+    const size_t plane = (size_t)m.dev.ni * m.dev.nj;
+    void *old[] = {m.seg_offs, m.seg_ids, m.seg_xy, m.seg_kind};
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (void *q : old)
+        if (q) CU(cudaFree(q));
+    m.seg_offs = m.seg_ids = nullptr; m.seg_xy = nullptr; m.seg_kind = nullptr;
+    m.dev.seg_offs = m.dev.seg_ids = nullptr; m.dev.seg_xy = nullptr; m.dev.seg_kind = nullptr;
+    ctx->meshes_dirty = true;
+    if (n_seg == 0) return 0;
+    const int n_ids = node_offs[plane];
+    if (node_offs[0] != 0 || n_ids < 0 || (n_ids > 0 && !node_ids)) return fail(ctx, SFGPU_EINVAL, "sfgpu_mesh_set_segments: bad node table");
+    std::vector<uint8_t> hs(plane, 0);
+    for (size_t k = 0; k < plane; k++) {
+        if (node_offs[k + 1] < node_offs[k]) return fail(ctx, SFGPU_EINVAL, "sfgpu_mesh_set_segments: node_offs must not decrease");
+        for (int q = node_offs[k]; q < node_offs[k + 1]; q++)
+            if (node_ids[q] < 0 || node_ids[q] >= n_seg) return fail(ctx, SFGPU_EINVAL, "sfgpu_mesh_set_segments: segment id %d out of range", node_ids[q]);
+        hs[k] = node_offs[k + 1] > node_offs[k];
+    }
+    std::vector<double4> xy(n_seg);
+    std::vector<int2> kd(n_seg);
+    for (int k = 0; k < n_seg; k++) {
+        xy[k] = make_double4(x1[k], y1[k], x2[k], y2[k]);
+        kd[k] = make_int2(kind[k], sink ? sink[k] : 0);
+    }
+    CU(cudaMalloc(&m.seg_offs, sizeof(int) * (plane + 1)));
+    CU(cudaMalloc(&m.seg_ids, sizeof(int) * (n_ids > 0 ? n_ids : 1)));
+    CU(cudaMalloc(&m.seg_xy, sizeof(double4) * n_seg));
+    CU(cudaMalloc(&m.seg_kind, sizeof(int2) * n_seg));
+    CU(cudaMemcpy(m.seg_offs, node_offs, sizeof(int) * (plane + 1), cudaMemcpyHostToDevice));
+    if (n_ids > 0) CU(cudaMemcpy(m.seg_ids, node_ids, sizeof(int) * n_ids, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m.seg_xy, xy.data(), sizeof(double4) * n_seg, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m.seg_kind, kd.data(), sizeof(int2) * n_seg, cudaMemcpyHostToDevice));
+    // the node table defines which nodes own a segment (KM:508-518)
+    if (!m.has_seg) CU(cudaMalloc(&m.has_seg, plane));
+    CU(cudaMemcpy(m.has_seg, hs.data(), plane, cudaMemcpyHostToDevice));
+    m.dev.has_seg = m.has_seg;
+    m.dev.any_seg = n_ids > 0 ? 1 : 0;
+    m.dev.seg_offs = m.seg_offs; m.dev.seg_ids = m.seg_ids; m.dev.seg_xy = m.seg_xy; m.dev.seg_kind = m.seg_kind;
+    // hit list shared by the meshes of the context
+    if (!ctx->hit_cap) {
+        ctx->hit_cap = 1 << 20;
+        CU(cudaMalloc(&ctx->hit_slab, ctx->hit_cap * (2 * sizeof(int) + 5 * sizeof(double) + 1)));
+    }
+    char *hp = ctx->hit_slab;
+    HitList h{};
+    h.t = (double *)hp; h.u = h.t + ctx->hit_cap; h.v = h.u + ctx->hit_cap; h.w = h.v + ctx->hit_cap; h.mpw = h.w + ctx->hit_cap;
+    h.seg = (int *)(h.mpw + ctx->hit_cap); h.mesh = h.seg + ctx->hit_cap;
+    h.alive = (signed char *)(h.mesh + ctx->hit_cap);
+    h.cap = ctx->hit_cap;
+    h.n = &ctx->d_cnt->n_hits;
+    m.dev.hits = h;
+    // CIRCUIT faces still need the host
+    m.needs_slow = false;
+    for (int f = 0; f < 4; f++) {
+        const int len = (f == SFGPU_FACE_RIGHT || f == SFGPU_FACE_LEFT) ? m.dev.nj : m.dev.ni;
+        std::vector<int8_t> b(len);
+        CU(cudaMemcpy(b.data(), m.bc[f], len, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < len; k++)
+            if (b[k] == SFGPU_BC_CIRCUIT) m.needs_slow = true;
+    }
+    return 0;
+}
+
+// surface hits of the last sfgpu_step, KM:586-602 (any order): what addSurfaceMomentum / addSurfaceMassDeposit /
+// boundary_charge need on the host.  Arrays nullable; *n returns the number of hits of the step (copied: min(n, max)).
+extern "C" int sfgpu_take_surface_hits(sfgpu_ctx *ctx, int32_t sp, int64_t max, int32_t *mesh, int32_t *seg, double *t, double *u, double *v,
+                                       double *w, double *mpw, int8_t *alive, int64_t *n, int64_t *n_absorbed)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    Species &s = ctx->species[sp];
+    if (n) *n = s.n_hits;
+    if (n_absorbed) *n_absorbed = s.n_absorbed;
+    int64_t c = s.n_hits < max ? s.n_hits : max;
+    if ((int64_t)ctx->hit_cap < c) c = (int64_t)ctx->hit_cap;
+    if (c <= 0 || !ctx->hit_slab) return 0;
+    const size_t cap = ctx->hit_cap;
+    double *hd = (double *)ctx->hit_slab;
+    int *hi = (int *)(hd + 5 * cap);
+    signed char *ha = (signed char *)(hi + 2 * cap);
+    double *dst[5] = {t, u, v, w, mpw};
+    for (int k = 0; k < 5; k++)
+        if (dst[k]) CU(cudaMemcpyAsync(dst[k], hd + k * cap, c * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (seg) CU(cudaMemcpyAsync(seg, hi, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mesh) CU(cudaMemcpyAsync(mesh, hi + cap, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (alive) CU(cudaMemcpyAsync(alive, ha, c, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -1331,7 +1445,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             int64_t tail_first = 0;
             if (!untiled && f.n_sorted > 0 && f.n_items > 0) {
                 CU(cudaMemcpyAsync(ctx->d_args + m, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
-                k_fast_step<<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                if (a.m.any_seg) k_fast_step<true><<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                else k_fast_step<false><<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
                 CU(cudaGetLastError());
                 { ctx->last_launches++; ctx->launch_total++; }
                 tail_first = f.n_sorted;
@@ -1436,6 +1551,10 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     }
     s.n_exited = (int64_t)ctx->h_cnt->n_exited;
     s.n_removed = (int64_t)ctx->h_cnt->n_removed;
+    s.n_absorbed = (int64_t)ctx->h_cnt->n_absorbed;
+    s.n_hits = (int64_t)ctx->h_cnt->n_hits;
+    if (s.n_hits > (int64_t)ctx->hit_cap && ctx->hit_cap)
+        return fail(ctx, SFGPU_EOVERFLOW, "%lld surface hits in one step, the list holds %zu", (long long)s.n_hits, ctx->hit_cap);
     s.slow_n = (int64_t)ctx->h_cnt->n_slow;
     ctx->last_fallback = ctx->h_cnt->n_fallback;
     // too many particles drifted out of their warp tiles: sort before the next step instead of waiting for the interval
@@ -2000,3 +2119,5 @@ extern "C" int sfgpu_last_step_counters(sfgpu_ctx *ctx, int64_t *n_fallback)
     if (n_fallback) *n_fallback = (int64_t)ctx->last_fallback;
     return 0;
 }
+
+#include "sf_multi.cuh"

@@ -55,6 +55,8 @@ struct StepCounters {
     unsigned long long n_out[16]; // per-mesh survivors appended to the next-step list
     unsigned long long n_exited;  // SF_DEAD
     unsigned long long n_removed; // SF_REMOVED
+    unsigned long long n_absorbed; // SF_ABSORBED
+    unsigned long long n_hits;    // surface-hit list cursor
     unsigned long long n_slow;    // slow-path list length
     unsigned long long n_xfer_copies;
     unsigned long long overflow;  // a list ran out of room

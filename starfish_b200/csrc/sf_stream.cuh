@@ -119,6 +119,8 @@ __device__ __forceinline__ void fast_leave(const FastStepArgs &a, int st, const 
         else atomicAdd(&a.c->overflow, 1ULL);
     } else if (st == SF_DEAD) {
         atomicAdd(&a.c->n_exited, 1ULL);
+    } else if (st == SF_ABSORBED) {
+        atomicAdd(&a.c->n_absorbed, 1ULL);
     } else if (st == SF_REMOVED) {
         atomicAdd(&a.c->n_removed, 1ULL);
     } else if (st == SF_TRANSFER) {
@@ -360,7 +362,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 }
             }
             int fl = 3;
-            if (simple_ok && sf_move_simple(m, a.b.qm, a.b.dt, p)) {
+            if (simple_ok && sf_move_simple<false>(m, a.b.qm, a.b.dt, p)) {
                 st[0 * SFS_ROW + s] = p.x; st[1 * SFS_ROW + s] = p.y; st[2 * SFS_ROW + s] = p.z;
                 st[3 * SFS_ROW + s] = p.u; st[4 * SFS_ROW + s] = p.v; st[5 * SFS_ROW + s] = p.w;
             } else {

@@ -192,3 +192,91 @@ class LinearSpline:
             self.cum_area[k + 1] = self.cum_area[k] + self.area[k]
         self.spline_area = float(self.cum_area[-1])
         self.n_seg = len(length)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# solid boundaries: which nodes own which segments (host-side set-up, stays Java in production)
+# ---------------------------------------------------------------------------------------------------------------------
+def _jint(d):
+    """Java (int)double: toward zero, NaN -> 0, saturating."""
+    if d != d:
+        return 0
+    return int(max(min(d, 2147483647.0), -2147483648.0))
+
+
+def _segment_intersect(x1, y1, x2, y2, p3, p4):
+    """LinearSegment.intersect(p3, p4), LinearSegment.java:113-179 -> (t_segment, t_p3p4) or (-1, -1)."""
+    x3, y3, x4, y4 = p3[0], p3[1], p4[0], p4[1]
+    den = (x1 - x2) * (y3 - y4) - (y1 - y2) * (x3 - x4)
+    if den == 0:
+        return -1.0, -1.0
+    xp0 = ((x1 * y2 - y1 * x2) * (x3 - x4) - (x1 - x2) * (x3 * y4 - y3 * x4)) / den
+    xp1 = ((x1 * y2 - y1 * x2) * (y3 - y4) - (y1 - y2) * (x3 * y4 - y3 * x4)) / den
+    t0 = (xp0 - x1) / (x2 - x1) if abs(x2 - x1) > 1e-6 else (xp1 - y1) / (y2 - y1)
+    if t0 < -FLT_EPS or t0 > 1 + FLT_EPS:
+        return -1.0, -1.0
+    t1 = (xp0 - x3) / (x4 - x3) if abs(x4 - x3) > 1e-6 else (xp1 - y3) / (y4 - y3)
+    if t1 < -FLT_EPS or t1 > 1 + FLT_EPS:
+        return -1.0, -1.0
+    return min(max(t0, 0.0), 1.0), min(max(t1, 0.0), 1.0)
+
+
+class SolidBoundary:
+    """A ``Boundary`` of type DIRICHLET ("solid") or SINK made of linear segments (boundaries.xml ``<path>M .. L ..</path>``),
+    with the outcome ``Material.performSurfaceInteraction`` (Material.java:279-300) has for the species that hits it:
+    ``kind`` 0 = the particle dies (no interaction listed for the pair, or ABSORB), 1 = it lives on unchanged (NONE; SPECULAR
+    as SurfaceInteraction.java:82-125 implements it)."""
+
+    def __init__(self, name, points, kind=0, sink=False):
+        pts = np.asarray(points, np.float64)
+        self.name, self.kind, self.sink = name, int(kind), bool(sink)
+        self.x1, self.y1 = np.ascontiguousarray(pts[:-1, 0]), np.ascontiguousarray(pts[:-1, 1])
+        self.x2, self.y2 = np.ascontiguousarray(pts[1:, 0]), np.ascontiguousarray(pts[1:, 1])
+        self.n_seg = len(self.x1)
+
+
+def set_boundaries(mesh, boundaries):
+    """``Mesh.setNodeControlVolumes`` (Mesh.java:1215-1290) for the DIRICHLET / SINK boundaries: every node whose +-1.01-cell box
+    is touched by a segment owns it (``node.segments``).  Fills ``mesh.has_seg`` (KM:508-518) and the segment tables the device
+    and the oracle take: ``mesh.segments`` = dict(x1,y1,x2,y2,kind,sink) over all segments and the node CSR ``seg_offs``/``seg_ids``."""
+    ni, nj = mesh.ni, mesh.nj
+    owners = [[[] for _ in range(nj)] for _ in range(ni)]
+    seg = dict(x1=[], y1=[], x2=[], y2=[], kind=[], sink=[], boundary=[], index=[])
+    for b_id, b in enumerate(boundaries):
+        for s in range(b.n_seg):
+            sid = len(seg["x1"])
+            x1, y1, x2, y2 = float(b.x1[s]), float(b.y1[s]), float(b.x2[s]), float(b.y2[s])
+            for k, v in zip(("x1", "y1", "x2", "y2", "kind", "sink", "boundary", "index"), (x1, y1, x2, y2, b.kind, int(b.sink), b_id, s)):
+                seg[k].append(v)
+            lo = mesh.XtoL(np.array([min(x1, x2), min(y1, y2)]))  # Segment.getBox + Mesh.XtoI
+            hi = mesh.XtoL(np.array([max(x1, x2), max(y1, y2)]))
+            lcm = [_jint(lo[0]) - 1, _jint(lo[1]) - 1]
+            lcp = [_jint(hi[0]) + 2, _jint(hi[1]) + 2]
+            lcm = [max(lcm[0], 0), max(lcm[1], 0)]
+            lcp = [min(lcp[0], ni - 1), min(lcp[1], nj - 1)]
+            for j in range(lcm[1], lcp[1] + 1):
+                for i in range(lcm[0], lcp[0] + 1):
+                    bsize = 1.01
+                    b1 = mesh.pos(np.array([i - bsize, j - bsize]))
+                    b2 = mesh.pos(np.array([i + bsize, j + bsize]))
+                    inbox = lambda px, py: b1[0] <= px <= b2[0] and b1[1] <= py <= b2[1]
+                    hit = inbox(x1, y1) or inbox(x2, y2)
+                    if not hit:  # Segment.segmentInBox: cuts of the four box faces, Segment.java:246-290
+                        faces = (((b1[0], b1[1]), (b2[0], b1[1])), ((b2[0], b1[1]), (b2[0], b2[1])), ((b2[0], b2[1]), (b1[0], b2[1])),
+                                 ((b1[0], b2[1]), (b1[0], b1[1])))
+                        hit = any(_segment_intersect(x1, y1, x2, y2, f1, f2)[0] >= 0 for f1, f2 in faces)
+                    if hit and sid not in owners[i][j]:
+                        owners[i][j].append(sid)
+    mesh.has_seg = np.zeros((ni, nj), dtype=np.uint8)
+    offs, ids = [0], []
+    for i in range(ni):
+        for j in range(nj):
+            if owners[i][j]:
+                mesh.has_seg[i, j] = 1
+            ids += owners[i][j]
+            offs.append(len(ids))
+    mesh.segments = {k: np.ascontiguousarray(v, np.float64 if k in ("x1", "y1", "x2", "y2") else np.int32) for k, v in seg.items()}
+    mesh.seg_offs = np.ascontiguousarray(offs, np.int32)
+    mesh.seg_ids = np.ascontiguousarray(ids, np.int32)
+    mesh.node_segments = owners
+    return mesh

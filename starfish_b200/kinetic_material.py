@@ -109,7 +109,7 @@ class KineticMaterial:
     """One kinetic species on one GPU.  ``meshes`` is the ordered mesh list (Starfish.getMeshList())."""
 
     def __init__(self, name, charge, mass, meshes, domain_type=DomainType.XY, spwt=1.0, device=0,
-                 capacity_hint=0, step_flags=0):
+                 capacity_hint=0, step_flags=0, device_segments=True):
         self.lib = _lib.load()
         self.name = name
         self.charge, self.mass, self.spwt0 = float(charge), float(mass), float(spwt)
@@ -138,6 +138,13 @@ class KineticMaterial:
                                                 dh.ctypes.data_as(_lib.c_double_p), bc, nbr, _ptr(has_seg), _ptr(node_vol),
                                                 C.byref(mid)))
             assert mid.value == k
+            # deterministic surface hits on the device (domain.set_boundaries built the node -> segment table)
+            sg = getattr(m, "segments", None)
+            if device_segments and sg is not None and len(sg["x1"]):
+                ip = lambda a: np.ascontiguousarray(a, np.int32).ctypes.data_as(_lib.c_int32_p)
+                dp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(_lib.c_double_p)
+                self._check(self.lib.sfgpu_mesh_set_segments(self._ctx, k, len(sg["x1"]), dp(sg["x1"]), dp(sg["y1"]), dp(sg["x2"]), dp(sg["y2"]),
+                                                             ip(sg["kind"]), ip(sg["sink"]), ip(m.seg_offs), ip(m.seg_ids)))
         sp = C.c_int32(-1)
         self._check(self.lib.sfgpu_species_add(self._ctx, self.charge, self.mass, int(capacity_hint), C.byref(sp)))
         self._sp = sp.value
@@ -363,6 +370,21 @@ class KineticMaterial:
         dt = self.dt if dt is None else dt
         self._check(self.lib.sfgpu_restart_load(self._ctx, self._sp, mesh.index, data, len(data), float(dt), C.byref(used), C.byref(added)))
         return used.value, added.value
+
+    def takeSurfaceHits(self):
+        """Surface hits of the last step (KM:586-602): dict of arrays mesh, seg, t, u, v, w, mpw, alive; also sets n_absorbed."""
+        n, na = C.c_int64(), C.c_int64()
+        self._check(self.lib.sfgpu_take_surface_hits(self._ctx, self._sp, 0, None, None, None, None, None, None, None, None, C.byref(n), C.byref(na)))
+        self.n_absorbed = na.value
+        k = n.value
+        out = dict(mesh=np.empty(k, np.int32), seg=np.empty(k, np.int32), t=np.empty(k), u=np.empty(k), v=np.empty(k), w=np.empty(k), mpw=np.empty(k),
+                   alive=np.empty(k, np.int8))
+        if k:
+            d = lambda a: a.ctypes.data_as(_lib.c_double_p)
+            self._check(self.lib.sfgpu_take_surface_hits(self._ctx, self._sp, k, out["mesh"].ctypes.data_as(_lib.c_int32_p), out["seg"].ctypes.data_as(_lib.c_int32_p),
+                                                         d(out["t"]), d(out["u"]), d(out["v"]), d(out["w"]), d(out["mpw"]), out["alive"].ctypes.data_as(C.POINTER(C.c_int8)),
+                                                         C.byref(n), C.byref(na)))
+        return out
 
     def takeSlowPath(self):
         n_slow = C.c_int64()

@@ -137,3 +137,50 @@ def config_multi_domain():
         meshes.append(m)
     set_mesh_neighbors(meshes)
     return meshes, QE, 39.9 * AMU, 5e-8
+
+
+class TutorialStep2:
+    """BASELINE config 1: dat/examples/tutorial/step2 -- O+ ions streaming past a cylinder at -100 V.
+
+    domain.xml: XY, uniform mesh 81x41 nodes, origin (-0.15, 0), spacing 5e-3; LEFT dirichlet, BOTTOM symmetry, others OPEN.
+    boundaries.xml: 20-segment "cylinder" (solid; no surface interaction is loaded for O+ on SS, so Material.java:292-295 removes
+    every ion that hits it) and the virtual "inlet" line x = -0.15, y: 0.20 -> 0.  materials.xml: O+ molwt 16, charge +1, spwt 1e3.
+    starfish.xml: uniform source on the inlet, mdot 3.72e-13 kg/s, v_drift 7000 m/s; dt 1e-7, 400 iterations.
+    The potential solver is outside this path: E is frozen to an analytic sheath, phi = -100 V * exp(-(r - r0) / 1 cm) around
+    the cylinder (the example's plasma, n0 = 1e10 m^-3 and Te = 1.5 eV, shields the wall over about a centimetre), sampled on the nodes
+    and zero inside the cylinder."""
+
+    CYLINDER = ("0.05, 0 0.0475528, -0.0154508 0.0404508, -0.0293893 0.0293893, -0.0404508 0.0154508, -0.0475528 -9.18E-18, -0.05 "
+                "-0.0154508, -0.0475528 -0.0293893, -0.0404508 -0.0404508, -0.0293893 -0.0475528, -0.0154508 -0.05, 6.12E-18 "
+                "-0.0475528, 0.0154508 -0.0404508, 0.0293893 -0.0293893, 0.0404508 -0.0154508, 0.0475528 3.06E-18, 0.05 "
+                "0.0154508, 0.0475528 0.0293893, 0.0404508 0.0404508, 0.0293893 0.0475528, 0.0154508 0.05, 0")
+
+    def __init__(self, spwt=1e3, wall_kind=0, volts=-100.0):
+        from .domain import LinearSpline, SolidBoundary, set_boundaries
+        m = UniformMesh(81, 41, (-0.15, 0.0), (5e-3, 5e-3), DomainType.XY, name="mesh1")
+        m.setMeshBCType(Face.LEFT, DomainBoundaryType.DIRICHLET)
+        m.setMeshBCType(Face.BOTTOM, DomainBoundaryType.SYMMETRY)
+        pts = np.array([float(t) for t in self.CYLINDER.replace(",", " ").split()]).reshape(-1, 2)
+        self.cylinder = SolidBoundary("cylinder", pts, kind=wall_kind)
+        set_boundaries(m, [self.cylinder])
+        self.inlet = LinearSpline(np.array([[-0.15, 0.20], [-0.15, 0.0]]))
+        x = m.x0[0] + np.arange(m.ni) * m.dh[0]
+        y = m.x0[1] + np.arange(m.nj) * m.dh[1]
+        X, Y = np.meshgrid(x, y, indexing="ij")
+        r = np.sqrt(X * X + Y * Y)
+        r0, lam = 0.05, 0.01
+        er = np.where(r >= r0 * 0.999, (volts / lam) * np.exp(-(r - r0) / lam), 0.0)  # -d/dr [V0 exp(-(r - r0)/lam)]
+        m.efi = np.ascontiguousarray(er * X / np.maximum(r, 1e-9))
+        m.efj = np.ascontiguousarray(er * Y / np.maximum(r, 1e-9))
+        self.mesh, self.name = m, "tutorial_step2"
+        self.charge, self.mass, self.spwt = QE, 16 * AMU, float(spwt)
+        self.dt, self.steps = 1e-7, 400
+        self.mdot, self.v_drift = 3.72e-13, 7000.0
+        self.mp_rem = 0.0
+
+    def num_mp(self):
+        """Source.regenerate(), Source.java:121-133: macroparticles of this step, the remainder carried over."""
+        mp = (self.mdot * self.dt) / (self.mass * self.spwt) + self.mp_rem
+        n = int(mp)
+        self.mp_rem = mp - n
+        return n

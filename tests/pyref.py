@@ -170,6 +170,7 @@ class KM:
         self.transfer = [[] for _ in meshes]
         self.slow = []
         self.id_counter = 0
+        self.n_absorbed, self.hits = 0, []
         self.sums = [0.0] * 5
         self.n_exited = 0
 
@@ -229,13 +230,66 @@ class KM:
                     return True
         return False
 
+    def segment_hit(self, mesh, part, old, lc_old, dt0):
+        """Segment part of ProcessBoundary, KM:482-603, for LinearSegments whose surface outcome is deterministic.
+        Returns None (no hit), True (hit, alive) or False (hit, removed)."""
+        def mn(a, b):
+            return float("nan") if (a != a or b != b) else min(a, b)
+
+        def mx(a, b):
+            return float("nan") if (a != a or b != b) else max(a, b)
+        i_min, i_max = jint(mn(part.lc[0], lc_old[0])), jint(mx(part.lc[0], lc_old[0]))
+        j_min, j_max = jint(mn(part.lc[1], lc_old[1])), jint(mx(part.lc[1], lc_old[1]))
+        i_min, j_min = max(i_min, 0), max(j_min, 0)
+        i_max, j_max = min(i_max, mesh.ni - 1), min(j_max, mesh.nj - 1)
+        segments = []  # Set<Segment>, KM:505-518 (insertion order; the order only matters for exact ties)
+        for i in range(i_min, i_max + 1):
+            for j in range(j_min, j_max + 1):
+                for sid in mesh.node_segments[i][j]:
+                    if sid not in segments:
+                        segments.append(sid)
+        tp_min, tsurf_min, seg_min = 2.0, 0.0, None
+        for sid in segments:
+            seg = mesh.segments[sid]
+            t = seg.intersect(old, part.pos)
+            t_part = t[1]
+            if t_part > 0:
+                n = seg.normal
+                acos = (n[0] * part.vel[0] + n[1] * part.vel[1]) / math.sqrt(part.vel[0] * part.vel[0] + part.vel[1] * part.vel[1]) \
+                    if (part.vel[0] != 0 or part.vel[1] != 0) else float("nan")
+                if t_part < FLT_EPS and acos > 0:
+                    continue
+                if t_part < tp_min:
+                    tp_min, tsurf_min, seg_min = t_part, t[0], seg
+        if seg_min is None:
+            return None
+        tp_min *= 0.9999
+        part.pos[0] = old[0] + tp_min * (part.pos[0] - old[0])
+        part.pos[1] = old[1] + tp_min * (part.pos[1] - old[1])
+        part.lc = mesh.XtoL(part.pos)
+        part.dt = dt0 * (1 - tp_min)
+        if part.lc[0] < 0 and part.lc[0] > -FLT_EPS:
+            part.lc[0] = 0.0
+        if part.lc[1] < 0 and part.lc[1] > -FLT_EPS:
+            part.lc[1] = 0.0
+        alive = seg_min.kind != 0  # Material.performSurfaceInteraction: no handler / ABSORB kills, NONE / SPECULAR-as-written keep
+        if seg_min.sink:
+            alive = False
+        self.hits.append((seg_min.sid, tsurf_min, list(part.vel), part.mpw, alive))
+        return alive
+
     def process_boundary(self, m, part, old, lc_old):
-        """KM:471-750 without segments.  Returns 'alive', 'dead', 'slow' or 'transfer'."""
+        """KM:471-750.  Returns 'alive', 'dead', 'slow', 'absorbed' or 'transfer'."""
         mesh = self.meshes[m]
-        if self.bbox_segments(mesh, part.lc, lc_old):
+        near = self.bbox_segments(mesh, part.lc, lc_old)
+        if near and not getattr(mesh, "segments", None):
             return "slow"
         dt0 = part.dt
         part.dt = 0.0
+        if near:
+            if self.segment_hit(mesh, part, old, lc_old, dt0) is False:
+                self.n_absorbed += 1
+                return "absorbed"
         ni, nj = mesh.ni, mesh.nj
         if part.lc[0] < 0 or part.lc[1] < 0 or part.lc[0] >= ni - 1 or part.lc[1] >= nj - 1:
             t_right = t_top = t_left = t_bottom = 99.0
@@ -387,6 +441,7 @@ class KM:
 
     def updateFields(self, dt):  # KM:117-163
         self.slow, self.n_exited = [], 0
+        self.n_absorbed, self.hits = 0, []
         self.sums = [0.0] * 5
         for m in range(len(self.meshes)):
             self.particles[m], s = self.mover(m, self.particles[m], dt, False)
@@ -418,6 +473,47 @@ class KM:
                 if 0 <= ci < mesh.ni and 0 <= cj < mesh.nj:
                     F[7].data[ci][cj] += 1
             self.raw.append([f.data for f in F])
+
+
+class WallSegment:  # boundaries/LinearSegment.java:21-47, :113-179 as ProcessBoundary uses it
+    def __init__(self, sid, x1, y1, x2, y2, kind=0, sink=False):
+        self.sid, self.x1, self.x2 = sid, [x1, y1], [x2, y2]
+        self.kind, self.sink = kind, sink
+        dx, dy = x2 - x1, y2 - y1
+        length = math.sqrt(dx * dx + dy * dy)
+        dx /= length
+        dy /= length
+        self.normal = [-dy, dx, 0.0]
+
+    @staticmethod
+    def infinite_line_intersect(p1, p2, p3, p4):
+        x1, x2, x3, x4 = p1[0], p2[0], p3[0], p4[0]
+        y1, y2, y3, y4 = p1[1], p2[1], p3[1], p4[1]
+        den = (x1 - x2) * (y3 - y4) - (y1 - y2) * (x3 - x4)
+        if den == 0:
+            return None
+        return [((x1 * y2 - y1 * x2) * (x3 - x4) - (x1 - x2) * (x3 * y4 - y3 * x4)) / den,
+                ((x1 * y2 - y1 * x2) * (y3 - y4) - (y1 - y2) * (x3 * y4 - y3 * x4)) / den]
+
+    def intersect(self, p3, p4):
+        p1, p2 = self.x1, self.x2
+        xp = self.infinite_line_intersect(p1, p2, p3, p4)
+        if xp is None:
+            return [-1.0, -1.0]
+        t = [0.0, 0.0]
+        if abs(p2[0] - p1[0]) > 1e-6:
+            t[0] = (xp[0] - p1[0]) / (p2[0] - p1[0])
+        else:
+            t[0] = (xp[1] - p1[1]) / (p2[1] - p1[1])
+        if t[0] < -FLT_EPS or t[0] > (1 + FLT_EPS):
+            return [-1.0, -1.0]
+        if abs(p4[0] - p3[0]) > 1e-6:
+            t[1] = (xp[0] - p3[0]) / (p4[0] - p3[0])
+        else:
+            t[1] = (xp[1] - p3[1]) / (p4[1] - p3[1])
+        if t[1] < -FLT_EPS or t[1] > (1 + FLT_EPS):
+            return [-1.0, -1.0]
+        return [min(max(t[0], 0.0), 1.0), min(max(t[1], 0.0), 1.0)]
 
 
 # ---------------------------------------------------------------------------------------------

@@ -77,3 +77,38 @@ def test_gpus_match_single_population_oracle(tmp_path, world):
     assert np.array_equal(ids[o], full["id"])
     for key in ("x", "y", "u", "v"):
         assert np.array_equal(np.concatenate([x[key] for x in r])[o], full[key]), key
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2, 8])
+def test_single_caller_group_matches_oracle(n_gpus):
+    """sfgpu_multi_*: ONE host thread (Starfish's main loop, Starfish.java:77-121) drives all GPUs; the worker threads of the
+    group run the per-GPU steps and the NCCL all-reduce concurrently.  Same bars as the one-process-per-GPU layout."""
+    import torch
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    from oracle import oracle as O
+    from starfish_b200 import Particles, synthetic as S
+    from starfish_b200.multi import MultiGpuKineticMaterial
+    wl = S.config_b(ni=96, nj=80, bc="open")
+    n = 150001
+    arr = wl.particles(0, n)
+    ok = O.OracleKM(wl.charge, wl.mass, [wl.mesh])
+    ok.addParticles(0, arr, wl.dt)
+    with MultiGpuKineticMaterial("O+", wl.charge, wl.mass, wl.mesh, n_gpus) as km:
+        km.dt = wl.dt
+        assert km.n_gpus == n_gpus
+        assert km.addParticles(Particles(n, **arr)) == n
+        for _ in range(4):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            assert km.np_alive == ok.getNp() and km.n_exited == ok.n_exited
+        dep = km.deposit()
+        scale = np.abs(ok.raw[0]).max(axis=(1, 2), keepdims=True)
+        assert np.all(np.abs(dep - ok.raw[0]) <= 1e-10 * scale) and np.array_equal(dep[7], ok.raw[0][7])
+        assert np.allclose(km.density(), ok.fields[0]["nd"], rtol=1e-10, atol=1e-10 * np.abs(ok.fields[0]["nd"]).max())
+        assert np.allclose(km.sums5, ok.sums5, rtol=1e-10, atol=1e-10 * abs(ok.sums5[4]))
+        p = km.getParticles().sorted_by_id()
+        o = ok.sorted_parts(0)
+        assert np.array_equal(p.id, o["id"])  # ids from one counter: unique over the GPUs, the oracle's numbering
+        for key in ("x", "y", "u", "v", "w", "li", "lj"):
+            assert np.array_equal(getattr(p, key), o[key]), key

@@ -1,0 +1,103 @@
+"""BASELINE config 1 (dat/examples/tutorial/step2: ions streaming past an absorbing 20-segment cylinder) on the GPU.
+
+1. device path: the segment part of ProcessBoundary runs inside the step kernels, nothing is handed to the host;
+2. host path: the device only classifies, the host finishes those particles with the unchanged reference logic
+   (here: the pure-Python restatement tests/pyref.py standing in for the Java ProcessBoundary).
+Both against the oracle: particle state and counts bit exact, surface hits identical as a set, deposit within 1e-10."""
+import numpy as np
+import pytest
+
+import pyref
+from oracle import oracle as O
+from starfish_b200 import KineticMaterial, Particles, _lib, synthetic as S
+from test_gpu_parity import compare_fields, compare_state
+from test_segments import py_mesh
+
+pytestmark = pytest.mark.gpu
+
+PATHS = [pytest.param(_lib.STEP_GENERIC, id="generic"), pytest.param(_lib.STEP_INPLACE, id="tiled"), pytest.param(_lib.STEP_STREAM, id="stream")]
+
+
+def _hit_key(h):
+    o = np.lexsort((h["mpw"], h["v"], h["u"], h["t"], h["seg"]))
+    return [(int(h["seg"][q]), float(h["t"][q]), float(h["u"][q]), float(h["v"][q]), float(h["w"][q]), float(h["mpw"][q]), int(h["alive"][q])) for q in o]
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("wall_kind", [0, 1], ids=["absorb", "keep"])
+def test_tutorial_step2_device_segments_match_oracle(flags, wall_kind):
+    cfg = S.TutorialStep2(wall_kind=wall_kind)
+    m = cfg.mesh
+    ok = O.OracleKM(cfg.charge, cfg.mass, [m])
+    steps = cfg.steps if wall_kind == 0 else 250
+    with KineticMaterial("O+", cfg.charge, cfg.mass, [m], m.domain_type, spwt=cfg.spwt, step_flags=flags) as km:
+        km.dt = cfg.dt
+        state_o = state_g = O.java_seed(0)
+        absorbed = hits = 0
+        for it in range(steps):
+            n_mp = cfg.num_mp()
+            no, state_o = ok.sampleUniformSource(cfg.inlet, cfg.v_drift, n_mp, cfg.dt, state_o, cfg.spwt, born_it=it)
+            ng, state_g = km.sampleUniformSource(cfg.inlet, cfg.v_drift, n_mp, state_g, born_it=it)
+            assert (ng, state_g) == (no, state_o)
+            km.updateFields()
+            ok.updateFields(cfg.dt)
+            h = km.takeSurfaceHits()
+            assert km.n_slow == 0 and not ok.slow  # nothing goes back to the host
+            assert km.n_absorbed == ok.n_absorbed and km.n_exited == ok.n_exited and km.getNp() == ok.getNp(), it
+            assert _hit_key(h) == _hit_key(ok.hits[0]), it
+            absorbed += km.n_absorbed
+            hits += len(h["seg"])
+            if it % 100 == 99 or it == steps - 1:
+                compare_state(km, ok)
+                compare_fields(km, ok)
+        assert hits > 1000 and (absorbed == hits if wall_kind == 0 else absorbed == 0)
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_tutorial_step2_host_slow_path_matches_oracle(flags):
+    """Without the segment table the device hands every particle whose sub-step touches a segment node back UNMOVED; the host runs
+    ProcessBoundary + the remaining sub-steps and re-injects the survivors into the still-open step."""
+    cfg = S.TutorialStep2(spwt=4e3)
+    m = cfg.mesh
+    ok = O.OracleKM(cfg.charge, cfg.mass, [m])
+    host = pyref.KM(cfg.charge, cfg.mass, [py_mesh(m)])  # the "unchanged Java": only its process_boundary / finish_slow are used
+    absorbed = {"n": 0}
+
+    def handler(km, slow, extra):
+        keep = []
+        absorbed["slow"] = absorbed.get("slow", 0) + slow.n
+        host.n_absorbed, host.n_exited, host.hits = 0, 0, []
+        for q in range(slow.n):
+            part = pyref.Particle([slow.x[q], slow.y[q], slow.z[q]], [slow.u[q], slow.v[q], slow.w[q]], slow.mpw[q], int(slow.id[q]))
+            part.lc, part.dt, part.born_it = [slow.li[q], slow.lj[q]], float(slow.dt[q]), int(slow.born_it[q])
+            if host.finish_slow(int(extra["mesh"][q]), part, [extra["old_x"][q], extra["old_y"][q]], [extra["old_li"][q], extra["old_lj"][q]], int(extra["bounces"][q])):
+                keep.append(part)
+        absorbed["n"] = host.n_absorbed
+        absorbed["exited"] = host.n_exited
+        arr = dict(x=[p.pos[0] for p in keep], y=[p.pos[1] for p in keep], z=[p.pos[2] for p in keep], u=[p.vel[0] for p in keep], v=[p.vel[1] for p in keep],
+                   w=[p.vel[2] for p in keep], mpw=[p.mpw for p in keep], li=[p.lc[0] for p in keep], lj=[p.lc[1] for p in keep], dt=[p.dt for p in keep])
+        yield 0, Particles(len(keep), **{k: np.array(v, dtype=np.float64) for k, v in arr.items()}, id=np.array([p.id for p in keep], np.int32),
+                           born_it=np.array([p.born_it for p in keep], np.int32))
+
+    with KineticMaterial("O+", cfg.charge, cfg.mass, [m], m.domain_type, spwt=cfg.spwt, step_flags=flags, device_segments=False) as km:
+        km.dt = cfg.dt
+        km.slow_path_handler = handler
+        state_o = state_g = O.java_seed(0)
+        total_abs = 0
+        for it in range(300):
+            n_mp = cfg.num_mp()
+            no, state_o = ok.sampleUniformSource(cfg.inlet, cfg.v_drift, n_mp, cfg.dt, state_o, cfg.spwt, born_it=it)
+            ng, state_g = km.sampleUniformSource(cfg.inlet, cfg.v_drift, n_mp, state_g, born_it=it)
+            assert (ng, state_g) == (no, state_o)
+            absorbed["n"] = absorbed["exited"] = 0
+            km.updateFields()
+            ok.updateFields(cfg.dt)
+            total_abs += absorbed["n"]
+            assert absorbed["n"] == ok.n_absorbed and km.getNp() == ok.getNp(), it
+            assert km.n_exited + absorbed["exited"] == ok.n_exited
+        assert absorbed["slow"] > 1000 and total_abs > 100
+        compare_state(km, ok)
+        for f in range(7):
+            scale = np.abs(ok.raw[0][f]).max()
+            assert np.allclose(km.last_deposit[0][f], ok.raw[0][f], rtol=1e-10, atol=1e-10 * scale), f
+        assert np.array_equal(km.last_deposit[0][7], ok.raw[0][7])

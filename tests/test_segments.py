@@ -1,0 +1,94 @@
+"""Surface hits on linear segments (SURVEY 8 a10 second half, f-4; BASELINE config 1 = dat/examples/tutorial/step2):
+LinearSegment.intersect (LinearSegment.java:113-179), the nearest-hit search with the start-of-step exclusion and the 0.9999
+back-off (KM:519-603), ABSORB / keep outcomes.  CPU part: known answers, and the C oracle against the independent Python
+restatement on the tutorial geometry.  GPU part (tests/test_gpu_segments.py) compares the CUDA path with the oracle."""
+import numpy as np
+import pytest
+
+import pyref
+from oracle import oracle as O
+from starfish_b200 import synthetic as S
+from starfish_b200.domain import DomainType, SolidBoundary, UniformMesh, set_boundaries
+
+
+def py_mesh(m):
+    pm = pyref.Mesh(m.ni, m.nj, m.x0, m.dh, int(m.domain_type))
+    for f in range(4):
+        pm.bc[f] = [int(v) for v in m.bc[f]]
+    pm.Efi = pyref.Field(pm, m.efi)
+    pm.Efj = pyref.Field(pm, m.efj)
+    pm.has_seg = [[int(v) for v in row] for row in m.has_seg]
+    sg = m.segments
+    pm.segments = [pyref.WallSegment(q, float(sg["x1"][q]), float(sg["y1"][q]), float(sg["x2"][q]), float(sg["y2"][q]), int(sg["kind"][q]), bool(sg["sink"][q]))
+                   for q in range(len(sg["x1"]))]
+    pm.node_segments = m.node_segments
+    return pm
+
+
+def test_kat_segment_intersect():
+    lib = O.load()
+    import ctypes as C
+    lib.sfo_segment_intersect.restype = None
+    seg = O._Segment(0.0, 0.0, 1.0, 0.0, 0, 0)  # along +x
+    t = (C.c_double * 2)()
+
+    def hit(p3, p4):
+        lib.sfo_segment_intersect(C.byref(seg), (C.c_double * 2)(*p3), (C.c_double * 2)(*p4), t)
+        ws = pyref.WallSegment(0, 0.0, 0.0, 1.0, 0.0).intersect(list(p3), list(p4))
+        assert [t[0], t[1]] == ws  # C oracle == Python restatement, bit for bit
+        return t[0], t[1]
+    assert hit((0.25, 1.0), (0.25, -1.0)) == (0.25, 0.5)          # crossing at the quarter point, half way along the path
+    assert hit((0.25, 1.0), (0.25, 0.5)) == (-1.0, -1.0)          # stops short
+    assert hit((2.0, 1.0), (2.0, -1.0)) == (-1.0, -1.0)           # beside the segment
+    assert hit((0.0, 1.0), (1.0, 1.0)) == (-1.0, -1.0)            # parallel: den == 0
+    t0, t1 = hit((0.5, 1.0), (0.5, 0.0))                           # ends ON the segment: t_part = 1
+    assert (t0, t1) == (0.5, 1.0)
+    t0, t1 = hit((1.0 + 5e-8, 1.0), (1.0 + 5e-8, -1.0))            # within FLT_EPS of the end point: clamped to 1
+    assert t0 == 1.0 and t1 == 0.5
+
+
+def test_tutorial_geometry_node_ownership():
+    cfg = S.TutorialStep2()
+    m = cfg.mesh
+    assert len(m.segments["x1"]) == 20 and m.has_seg.sum() > 60
+    # every node within one cell of the circle r = 0.05 owns a segment, nodes two cells away from the polygon do not
+    x = m.x0[0] + np.arange(m.ni)[:, None] * m.dh[0]
+    y = m.x0[1] + np.arange(m.nj)[None, :] * m.dh[1]
+    r = np.hypot(x, y)
+    assert m.has_seg[(np.abs(r - 0.05) < 0.6 * m.dh[0])].all()
+    assert not m.has_seg[np.abs(r - 0.05) > 3.1 * m.dh[0]].any()
+
+
+@pytest.mark.parametrize("wall_kind", [0, 1], ids=["absorb", "keep"])
+def test_oracle_matches_python_restatement_on_tutorial_step2(wall_kind):
+    """dat/examples/tutorial/step2 at a coarser specific weight: the inlet source (java.util.Random draws), the frozen sheath
+    field, the absorbing cylinder.  Absorbing walls draw no random numbers, so the two restatements must agree bit for bit."""
+    cfg = S.TutorialStep2(spwt=2e4, wall_kind=wall_kind)
+    m = cfg.mesh
+    ok = O.OracleKM(cfg.charge, cfg.mass, [m])
+    km = pyref.KM(cfg.charge, cfg.mass, [py_mesh(m)])
+    rnd = pyref.JavaRandom(0)
+    spl = pyref.Spline(np.array([[-0.15, 0.20], [-0.15, 0.0]]))
+    state = O.java_seed(0)
+    absorbed = hits = 0
+    for it in range(200):
+        n_mp = cfg.num_mp()
+        n, state = ok.sampleUniformSource(cfg.inlet, cfg.v_drift, n_mp, cfg.dt, state, cfg.spwt, born_it=it)
+        assert n == pyref.uniform_source_sample(km, spl, cfg.v_drift, n_mp, cfg.dt, rnd, cfg.spwt, born_it=it)
+        ok.updateFields(cfg.dt)
+        km.updateFields(cfg.dt)
+        assert ok.n_absorbed == km.n_absorbed and ok.n_exited == km.n_exited and not ok.slow and not km.slow
+        h = ok.hits[0]
+        assert len(h["seg"]) == len(km.hits)
+        for q, (sid, ts, vel, mpw, alive) in enumerate(km.hits):  # same hits in the same order (single mover thread)
+            assert (int(h["seg"][q]), float(h["t"][q]), float(h["u"][q]), float(h["v"][q]), float(h["mpw"][q]), bool(h["alive"][q])) == (sid, ts, vel[0], vel[1], mpw, alive)
+        absorbed += ok.n_absorbed
+        hits += len(km.hits)
+    assert hits > 20 and (absorbed == hits if wall_kind == 0 else absorbed == 0)
+    p = ok.sorted_parts(0)
+    q = sorted(km.particles[0], key=lambda a: a.id)
+    assert len(q) == len(p["x"]) > 1000
+    for key, get in (("x", lambda a: a.pos[0]), ("y", lambda a: a.pos[1]), ("u", lambda a: a.vel[0]), ("v", lambda a: a.vel[1]), ("li", lambda a: a.lc[0]),
+                     ("lj", lambda a: a.lc[1]), ("dt", lambda a: a.dt)):
+        assert np.array_equal(p[key], np.array([get(a) for a in q])), key
+    assert state == rnd.state
