@@ -20,7 +20,7 @@
 #include "sf_generic.cuh"
 
 #ifndef SF_FAST_WARPS
-#define SF_FAST_WARPS 4 // warps per CTA of the tiled kernel
+#define SF_FAST_WARPS 5 // warps per CTA of the tiled kernel (3 CTAs of 5 warps fit the 227 KB of shared memory: 15 warps / SM)
 #endif
 #ifndef SF_PPT
 #define SF_PPT 1        // particles per lane and batch (independent instruction streams hide FP64 latency)
@@ -31,7 +31,7 @@
 #define SF_WROW (32 * SF_PPT + 2) // padded row of the per-warp scratch (doubles): conflict-free 128-bit reads
 #define SF_TILE_DOUBLES (SFGPU_NFIELDS * SF_NT * SF_NT)
 #ifndef SF_STAGE
-#define SF_STAGE 1 // 1: cp.async prefetch of the next batch through shared memory; 0: plain loads, 3.5 KB less per warp
+#define SF_STAGE 0 // 1: cp.async prefetch of the next batch through shared memory; 0: plain loads, 3.5 KB less per warp
 #endif
 #define SF_EXTRA 6 // per-warp sums next to the tile: energy, fallback N/Px/Py/Pz/E (the fallback count rides in the tag of E)
 #define SF_SCRATCH_DOUBLES (SF_EXTRA + 12 * SF_WROW + 16 * SF_PPT + 2 + SF_STAGE * 2 * 7 * 32 * SF_PPT)
@@ -64,7 +64,10 @@ struct FastStepArgs {
     SlowPtrs slow;
     double *dep;
     StepCounters *c;
+    unsigned *defer;          // slots k_fast_step leaves to k_fast_deferred: bit 31 clear = re-run the particle through sf_move() from its
+    unsigned defer_cap;       // stored state; bit 31 set = already pushed and stored, only its deposit (it left the warp tile) is due
 };
+#define SF_DEFER_DEPOSIT_ONLY 0x80000000u
 
 // what happens to a particle of the fast store after sf_move(); shared by the tiled and the tail kernel
 __device__ __forceinline__ void fast_epilogue(const FastStepArgs &a, const MeshDev &m, size_t q, int st, bool exact,
@@ -142,35 +145,6 @@ __device__ __forceinline__ bool fast_load_move(const FastStepArgs &a, const Mesh
     const GlobalFieldGather fg;
     st = sf_move(m, a.meshes, a.qm, a.charge, a.dt, false, p, aux, exact, fg);
     return true;
-}
-
-// everything that is not the common case (boundaries, B field, segments, removal), out of line so that its
-// register needs do not inflate the hot loop.  Returns true when the particle still deposits in this step.
-__device__ __noinline__ bool fast_general(const FastStepArgs *__restrict__ ga, unsigned long long q, PState *pp, double z0, long long w0bits)
-{
-    const FastStepArgs &a = *ga;
-    MoveAux aux;
-    bool exact = true, deposit = false;
-    const GlobalFieldGather fg;
-    PState p = *pp;
-    const int st = sf_move(a.m, a.meshes, a.qm, a.charge, a.dt, false, p, aux, exact, fg);
-    fast_epilogue(a, a.m, q, st, exact, p, aux, z0, w0bits, make_int2(0, 0), deposit);
-    *pp = p;
-    return deposit;
-}
-
-// a particle that deposits outside the warp tile (drifted since the last sort): global FP64 REDs for the fields,
-// and its mover sums (KM:406-413) into the warp's shared-memory slots (CAS atomics: only lanes of this warp contend)
-__device__ __noinline__ void fast_fallback(const MeshDev *mp, const PState *pp, double *dep, double *extra, int *nfall)
-{
-    const PState &p = *pp;
-    deposit_global(*mp, p, dep);
-    atomicAdd(extra + 1, p.mpw);
-    atomicAdd(extra + 2, p.mpw * p.u);
-    atomicAdd(extra + 3, p.mpw * p.v);
-    atomicAdd(extra + 4, p.mpw * p.w);
-    atomicAdd(extra + 5, p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w));
-    atomicAdd(nfall, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -269,7 +243,9 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     double *sW = tile + SF_TILE_DOUBLES + SF_EXTRA; // tile, extra sums of the warp (energy, fallback N/P/E), then [4][SF_WROW] weights, [9][SF_WROW] values
     double *sV = sW + 4 * SF_WROW;
     int *sKey = reinterpret_cast<int *>(sV + 8 * SF_WROW); // [32 * SF_PPT] tile-local cell of each row, then the fallback count
+#if SF_STAGE
     double *sIn = reinterpret_cast<double *>(sKey + 32 * SF_PPT + 4); // [2 stages][7][32 * SF_PPT] prefetched particle state
+#endif
     const MeshDev &m = a.m;
     const size_t plane = (size_t)m.ni * m.nj;
     const bool simple_ok = !m.has_b && a.dt > 0 && (SEG || !m.any_seg);
@@ -360,10 +336,9 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                     a.fs.v[q] = p[j].v;
                     if (__double_as_longlong(p[j].w) != w0bits[j]) a.fs.w[q] = p[j].w;
                     deposit = true;
-                } else if (present[j]) { // general path (boundaries, B field, segments, removal)
-                    PState t = p[j]; // only the copy has its address taken: p[] stays in registers
-                    deposit = fast_general(ga, q, &t, z0[j], w0bits[j]);
-                    p[j] = t;
+                } else if (present[j]) { // anything else (boundaries, segments, removal ...): k_fast_deferred re-runs it from the stored state
+                    const unsigned long long s_ = atomicAdd(&a.c->n_defer[a.mesh_id], 1ULL);
+                    if (s_ < a.defer_cap) a.defer[s_] = (unsigned)q;
                 }
                 // ---- deposit: weights and the tile-local cell of this particle ----
                 key[j] = -1;
@@ -372,9 +347,9 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                     const int li_ = dw[j].i - ti0, lj_ = dw[j].j - tj0;
                     if (in && li_ >= 0 && lj_ >= 0 && li_ < SF_NT - 1 && lj_ < SF_NT - 1) {
                         key[j] = li_ * SF_NT + lj_;
-                    } else {
-                        const PState t = p[j];
-                        fast_fallback(&ga->m, &t, a.dep, tile + SF_TILE_DOUBLES, sKey + 32 * SF_PPT);
+                    } else { // pushed and stored, but its deposit misses the warp tile: left to k_fast_deferred
+                        const unsigned long long s_ = atomicAdd(&a.c->n_defer[a.mesh_id], 1ULL);
+                        if (s_ < a.defer_cap) a.defer[s_] = (unsigned)q | SF_DEFER_DEPOSIT_ONLY;
                     }
                 }
             }
@@ -481,15 +456,11 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
         if (lane == 0) {
             double *ex = tile + SF_TILE_DOUBLES;
-            const int nf = sKey[32 * SF_PPT];
-            if (s0 != 0 || nf != 0) {
-                atomicAdd(&a.c->sums[0], s0 + ex[1]); atomicAdd(&a.c->sums[1], s1 + ex[2]); atomicAdd(&a.c->sums[2], s2 + ex[3]);
-                atomicAdd(&a.c->sums[3], s3 + ex[4]); atomicAdd(&a.c->sums[4], ex[0] + ex[5]);
-                if (nf != 0) atomicAdd(&a.c->n_fallback, (unsigned long long)nf);
+            if (s0 != 0 || ex[0] != 0) {
+                atomicAdd(&a.c->sums[0], s0); atomicAdd(&a.c->sums[1], s1); atomicAdd(&a.c->sums[2], s2);
+                atomicAdd(&a.c->sums[3], s3); atomicAdd(&a.c->sums[4], ex[0]);
             }
-#pragma unroll
-            for (int k = 0; k < SF_EXTRA; k++) ex[k] = 0.0;
-            sKey[32 * SF_PPT] = 0;
+            ex[0] = 0.0;
         }
         __syncwarp();
     }
@@ -528,6 +499,57 @@ k_fast_tail(const __grid_constant__ FastStepArgs a, unsigned long long first, un
         atomicAdd(&a.c->sums[0], sN); atomicAdd(&a.c->sums[1], sPx); atomicAdd(&a.c->sums[2], sPy);
         atomicAdd(&a.c->sums[3], sPz); atomicAdd(&a.c->sums[4], sE);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// deferred kernel: the few particles k_fast_step did not finish -- everything that is not the common case goes through
+// sf_move() here, so that the hot kernel holds no call and no rare-path registers
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fast_deferred(const __grid_constant__ FastStepArgs a)
+{
+    const MeshDev &m = a.m;
+    double sN = 0, sPx = 0, sPy = 0, sPz = 0, sE = 0;
+    unsigned long long nd = a.c->n_defer[a.mesh_id];
+    if (nd > a.defer_cap) nd = a.defer_cap;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned nfall = 0;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += stride) {
+        const unsigned e = a.defer[k];
+        const size_t q = e & ~SF_DEFER_DEPOSIT_ONLY;
+        PState p;
+        bool deposit = false;
+        if (e & SF_DEFER_DEPOSIT_ONLY) {
+            p.x = a.fs.x[q]; p.y = a.fs.y[q]; p.z = a.fs.z[q]; p.u = a.fs.u[q]; p.v = a.fs.v[q]; p.w = a.fs.w[q]; p.mpw = a.fs.mpw[q];
+            p.li = (p.x - m.x0) / m.dhx;
+            p.lj = (p.y - m.y0) / m.dhy;
+            p.dt = 0;
+            deposit = true;
+            nfall++;
+        } else {
+            MoveAux aux;
+            int st = SF_REMOVED;
+            bool exact = true;
+            double z0 = 0;
+            long long w0bits = 0;
+            if (!fast_load_move(a, m, q, p, aux, st, exact, z0, w0bits)) continue;
+            fast_epilogue(a, m, q, st, exact, p, aux, z0, w0bits, make_int2(0, 0), deposit);
+        }
+        if (deposit) {
+            deposit_global(m, p, a.dep);
+            sN += p.mpw;
+            sPx += p.mpw * p.u;
+            sPy += p.mpw * p.v;
+            sPz += p.mpw * p.w;
+            sE += p.mpw * sqrt(p.u * p.u + p.v * p.v + p.w * p.w);
+        }
+    }
+    sN = warp_sum(sN); sPx = warp_sum(sPx); sPy = warp_sum(sPy); sPz = warp_sum(sPz); sE = warp_sum(sE);
+    if ((threadIdx.x & 31) == 0 && sN != 0) {
+        atomicAdd(&a.c->sums[0], sN); atomicAdd(&a.c->sums[1], sPx); atomicAdd(&a.c->sums[2], sPy);
+        atomicAdd(&a.c->sums[3], sPz); atomicAdd(&a.c->sums[4], sE);
+    }
+    if (nfall) atomicAdd(&a.c->n_fallback, (unsigned long long)nfall);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -116,6 +116,8 @@ struct FastStore { // cell-sorted SoA store of the normal particles of one speci
     bool stream_ok = false; // hist counts every live particle of p[0,n) and offs describes p[0,n_sorted)
     bool items_ok = false;  // items / d_nitems are the work items of k_fast_step for the current slab (not the streaming kernel's chunks)
     WorkItem *items = nullptr;
+    unsigned *defer = nullptr; // slots the tiled kernel leaves to k_fast_deferred
+    int64_t defer_cap = 0;
     unsigned *d_nitems = nullptr;
     unsigned max_items = 0, n_items = 0;
     void *cub_tmp = nullptr;
@@ -296,7 +298,7 @@ static int fast_reserve(sfgpu_ctx *ctx, FastStore &f, int64_t need)
 
 static void fast_free(FastStore &f)
 {
-    void *ptrs[] = {f.slab, f.alt_slab, f.keys, f.ranks, f.hist, f.offs, f.items, f.d_nitems, f.cub_tmp, f.hist_next, f.offs_out, f.cursor};
+    void *ptrs[] = {f.slab, f.alt_slab, f.keys, f.ranks, f.hist, f.offs, f.items, f.d_nitems, f.cub_tmp, f.hist_next, f.offs_out, f.cursor, f.defer};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     f = FastStore();
@@ -489,6 +491,7 @@ static FastStepArgs fast_args(sfgpu_ctx *ctx, Species &s, int m, double dt, cons
     a.fs = pop.fast.p; a.items = pop.fast.items; a.n_items = pop.fast.d_nitems; a.ntj = pop.fast.ntj;
     a.exc = pop.nxt.p; a.exc_cap = (unsigned long long)pop.nxt.cap;
     a.xfer = ctx->d_xfer; a.slow = slow; a.dep = pop.dep; a.c = ctx->d_cnt;
+    a.defer = pop.fast.defer; a.defer_cap = (unsigned)(pop.fast.defer_cap > 0x7fffffff ? 0x7fffffff : pop.fast.defer_cap);
     return a;
 }
 
@@ -1441,14 +1444,25 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                 }
             }
         } else if (f.n > 0) {
-            const FastStepArgs a = fast_args(ctx, s, m, dt, slow);
+            FastStepArgs a = fast_args(ctx, s, m, dt, slow);
             int64_t tail_first = 0;
-            if (!untiled && f.n_sorted > 0 && f.n_items > 0) {
+            // the tiled kernel carries only the common case (no B field, dt > 0); everything else goes through sf_move() in the tail kernel
+            const bool tiled = !untiled && f.n_sorted > 0 && f.n_items > 0 && !a.m.has_b && dt > 0 && f.n_sorted < 0x7fffffff;
+            if (tiled) {
+                if (f.defer_cap < f.n_sorted) {
+                    if (f.defer) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(f.defer)); }
+                    f.defer = nullptr; f.defer_cap = 0;
+                    CU(cudaMalloc(&f.defer, (size_t)f.cap * sizeof(unsigned)));
+                    f.defer_cap = f.cap;
+                    a.defer = f.defer; a.defer_cap = (unsigned)(f.defer_cap > 0x7fffffff ? 0x7fffffff : f.defer_cap);
+                }
                 CU(cudaMemcpyAsync(ctx->d_args + m, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
                 if (a.m.any_seg) k_fast_step<true><<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
                 else k_fast_step<false><<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
                 CU(cudaGetLastError());
-                { ctx->last_launches++; ctx->launch_total++; }
+                k_fast_deferred<<<148 * 4, 256, 0, ctx->stream>>>(a); // boundary crossers, tile misses, removals: a fraction of a percent
+                CU(cudaGetLastError());
+                { ctx->last_launches += 2; ctx->launch_total += 2; }
                 tail_first = f.n_sorted;
             }
             if (f.n > tail_first) {
@@ -1518,6 +1532,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     }
     if (ctx->h_cnt->overflow)
         return fail(ctx, SFGPU_EOVERFLOW, "%llu particles did not fit an internal list (records / slow path / mesh hand-off)", ctx->h_cnt->overflow);
+    for (int m = 0; m < nmesh; m++)
+        if ((int64_t)ctx->h_cnt->n_defer[m] > s.pops[m].fast.defer_cap) return fail(ctx, SFGPU_EOVERFLOW, "internal: deferred list overflow");
     for (int m = 0; m < nmesh; m++) {
         Pop &pop = s.pops[m];
         FastStore &f = pop.fast;

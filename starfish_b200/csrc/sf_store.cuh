@@ -66,6 +66,7 @@ struct StepCounters {
     unsigned long long fast_n[16]; // per-mesh: fast-store length cursor (records that became normal are appended)
     unsigned long long n_fallback; // deposits that missed the warp tile and went to global atomics
     unsigned long long n_flush;    // segment flushes of the tiled kernel (diagnostic)
+    unsigned long long n_defer[16]; // per mesh: particles k_fast_step left to k_fast_deferred
     long long fast_delta[16];      // per-mesh change of the number of live fast-store particles
     unsigned int queue[16];        // per-mesh work-item queue head of the tiled kernel
 };
