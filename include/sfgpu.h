@@ -233,6 +233,11 @@ int sfgpu_restart_load(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const void *
 
 /* explicit cell sort + compaction (sortParticlesToCells, KM:1150-1179: order only, no result change) */
 int sfgpu_sort(sfgpu_ctx *ctx, int32_t sp);
+/* SURVEY 8f-2, per-cell particle lists for consumers that bin by cell (collisions/DSMC.java:194-252, MCC.java:167-216; the reference's own
+ * sortParticlesToCells, KM:1150-1179): cell-sorts the store of one mesh and returns, for every CELL c = i*(nj-1) + j, the index of its first particle in
+ * sfgpu_download / sfgpu_upload order (cell_first, (ni-1)*(nj-1) entries) and its population (cell_count).  Indices [0, *n_sorted) are covered; the few
+ * exceptional records (stale lc after a boundary clamp, residual dt) follow unsorted at [*n_sorted, np).  Valid until the next call that moves particles. */
+int sfgpu_cell_lists(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t *cell_first, int32_t *cell_count, int64_t *n_sorted);
 /* sfgpu_step re-sorts the store by cell every `steps` steps (default 3, env SFGPU_SORT_EVERY).
  * KineticMaterial.mergeParticles (KM:1008-1143, particle_merge_skip > 0) is NOT offered: materials that merge keep type="kinetic". */
 int sfgpu_set_sort_interval(sfgpu_ctx *ctx, int32_t steps);

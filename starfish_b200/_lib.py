@@ -68,6 +68,7 @@ EXPORTS = {
     "sfgpu_multi_get_samples": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),
     "sfgpu_multi_clear_samples": (C.c_int, [C.c_void_p, C.c_int32]),
     "sfgpu_multi_get_sums": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_int64_p, c_int64_p, c_int64_p]),
+    "sfgpu_cell_lists": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_int64_p, c_int32_p, c_int64_p]),
     "sfgpu_set_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfgpu_species_add": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int64, c_int32_p]),
     "sfgpu_inject": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Particles), C.c_double, C.c_uint32, c_int64_p]),

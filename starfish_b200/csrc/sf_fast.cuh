@@ -34,7 +34,7 @@
 #define SF_STAGE 0 // 1: cp.async prefetch of the next batch through shared memory; 0: plain loads, 3.5 KB less per warp
 #endif
 #define SF_EXTRA 6 // per-warp sums next to the tile: energy, fallback N/Px/Py/Pz/E (the fallback count rides in the tag of E)
-#define SF_SCRATCH_DOUBLES (SF_EXTRA + 12 * SF_WROW + 16 * SF_PPT + 2 + SF_STAGE * 2 * 7 * 32 * SF_PPT)
+#define SF_SCRATCH_DOUBLES (SF_EXTRA + 13 * SF_WROW + 16 + 16 * SF_PPT + 2 + SF_STAGE * 2 * 7 * 32 * SF_PPT)
 #define SF_WARP_SMEM_BYTES ((SF_TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8)
 
 __device__ __forceinline__ double sf_vacant() { return __longlong_as_double(0x7ff8000000000001LL); }
@@ -239,10 +239,12 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *tile = reinterpret_cast<double *>(smem_raw + (size_t)wid * SF_WARP_SMEM_BYTES);
-    __shared__ __align__(16) double sOnes[32 * SF_PPT]; // weight and value of the counting lane
     double *sW = tile + SF_TILE_DOUBLES + SF_EXTRA; // tile, extra sums of the warp (energy, fallback N/P/E), then [4][SF_WROW] weights, [9][SF_WROW] values
     double *sV = sW + 4 * SF_WROW;
-    int *sKey = reinterpret_cast<int *>(sV + 8 * SF_WROW); // [32 * SF_PPT] tile-local cell of each row, then the fallback count
+    // weight and value of the counting lanes (f == 7): a row of ones placed on the bank group of value row 7 (rows are 272 bytes apart, i.e. 4 banks
+    // further per row: the eight lanes of a quarter warp then read eight different bank groups and the 128-bit operand loads stay conflict free)
+    double *sOnes = sV + 8 * SF_WROW + ((7 * SF_WROW - 8 * SF_WROW) % 16 + 16) % 16;
+    int *sKey = reinterpret_cast<int *>(sV + 9 * SF_WROW + 16); // [32 * SF_PPT] tile-local cell of each row, then the fallback count
 #if SF_STAGE
     double *sIn = reinterpret_cast<double *>(sKey + 32 * SF_PPT + 4); // [2 stages][7][32 * SF_PPT] prefetched particle state
 #endif
@@ -252,8 +254,8 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
 
     for (int k = lane; k < SF_TILE_DOUBLES + SF_EXTRA; k += 32) tile[k] = 0.0;
     if (lane == 0) sKey[32 * SF_PPT] = 0;
-    for (int k = threadIdx.x; k < 32 * SF_PPT; k += blockDim.x) sOnes[k] = 1.0;
-    __syncthreads();
+    for (int k = lane; k < 32 * SF_PPT; k += 32) sOnes[k] = 1.0;
+    __syncwarp();
 
     // role of this lane in the reduction: node n (w00,w10,w11,w01) x field f (7 moments; f == 7: n == 0 counts the
     // particles of the cell (mpc), n == 1 sums mpw*|vel| of the whole work item (energy sum, KM:412))
@@ -277,6 +279,21 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
         const int tj0 = (wi.tile % a.ntj) * SF_TILE - SF_HALO;
 #if SF_STAGE
         sf_prefetch_batch(a.fs, sIn, (size_t)wi.begin, 0, wi.count, lane);
+#else
+        // the state of the NEXT batch is fetched into registers while the current one is processed (the kernel has registers to spare
+        // since the rare paths left it): the first use of a batch no longer waits for HBM
+        double nx[SF_PPT][7];
+#pragma unroll
+        for (int j = 0; j < SF_PPT; j++) {
+            const int o = j * 32 + lane;
+            nx[j][6] = sf_vacant();
+            if (o < wi.count) {
+                const size_t q = (size_t)wi.begin + o;
+                nx[j][0] = a.fs.x[q]; nx[j][1] = a.fs.y[q]; nx[j][2] = a.fs.z[q];
+                nx[j][3] = a.fs.u[q]; nx[j][4] = a.fs.v[q]; nx[j][5] = a.fs.w[q];
+                nx[j][6] = a.fs.mpw[q];
+            }
+        }
 #endif
         for (int b = 0; b < wi.count; b += 32 * SF_PPT) {
             PState p[SF_PPT];
@@ -304,12 +321,20 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                     p[j].u = in[3 * 32 * SF_PPT]; p[j].v = in[4 * 32 * SF_PPT]; p[j].w = in[5 * 32 * SF_PPT];
                     p[j].mpw = in[6 * 32 * SF_PPT];
 #else
-                    const size_t q = (size_t)wi.begin + o;
-                    p[j].x = a.fs.x[q]; p[j].y = a.fs.y[q]; p[j].z = a.fs.z[q];
-                    p[j].u = a.fs.u[q]; p[j].v = a.fs.v[q]; p[j].w = a.fs.w[q];
-                    p[j].mpw = a.fs.mpw[q];
+                    p[j].x = nx[j][0]; p[j].y = nx[j][1]; p[j].z = nx[j][2];
+                    p[j].u = nx[j][3]; p[j].v = nx[j][4]; p[j].w = nx[j][5];
+                    p[j].mpw = nx[j][6];
 #endif
                 }
+#if !SF_STAGE
+                nx[j][6] = sf_vacant();
+                if (o + 32 * SF_PPT < wi.count) {
+                    const size_t q = (size_t)wi.begin + o + 32 * SF_PPT;
+                    nx[j][0] = a.fs.x[q]; nx[j][1] = a.fs.y[q]; nx[j][2] = a.fs.z[q];
+                    nx[j][3] = a.fs.u[q]; nx[j][4] = a.fs.v[q]; nx[j][5] = a.fs.w[q];
+                    nx[j][6] = a.fs.mpw[q];
+                }
+#endif
             }
             // ---- common case, branch free ----
 #pragma unroll

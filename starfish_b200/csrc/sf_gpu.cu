@@ -2023,6 +2023,39 @@ extern "C" int sfgpu_sort(sfgpu_ctx *ctx, int32_t sp)
     return 0;
 }
 
+// per-cell particle lists for the consumers that bin particles by cell themselves (DSMC.java:194-252, MCC.java:167-216,
+// KineticMaterial.sortParticlesToCells KM:1150-1179): cell-sorts the store and returns, for every cell c = i*(nj-1) + j, the index of its first
+// particle in sfgpu_download / sfgpu_upload order and its population.  Particles [0, *n_sorted) are covered; the few exceptional records
+// (stale lc, residual dt) follow at [*n_sorted, np) unsorted.
+extern "C" int sfgpu_cell_lists(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t *cell_first, int32_t *cell_count, int64_t *n_sorted)
+{
+    CHECK_CTX();
+    CHECK_SP();
+    CHECK_MESH();
+    if (!cell_first || !cell_count) return fail(ctx, SFGPU_EINVAL, "sfgpu_cell_lists: null output");
+    int rc = sync_meshes(ctx);
+    if (rc) return rc;
+    FastStore &f = ctx->species[sp].pops[mesh_id].fast;
+    rc = fast_sort(ctx, mesh_id, f);
+    if (rc) return rc;
+    const MeshDev &m = ctx->meshes[mesh_id].dev;
+    const int nci = m.ni - 1, ncj = m.nj - 1;
+    for (int64_t c = 0; c < (int64_t)nci * ncj; c++) { cell_first[c] = 0; cell_count[c] = 0; }
+    if (n_sorted) *n_sorted = f.n_sorted;
+    if (f.n == 0) return 0;
+    std::vector<unsigned> offs((size_t)f.nkeys + 1);
+    CU(cudaMemcpyAsync(offs.data(), f.offs, offs.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (unsigned key = 0; key < f.nkeys; key++) {
+        const int tile = (int)(key / (SF_TILE * SF_TILE)), cell = (int)(key % (SF_TILE * SF_TILE));
+        const int ci = (tile / f.ntj) * SF_TILE + cell / SF_TILE, cj = (tile % f.ntj) * SF_TILE + cell % SF_TILE;
+        if (ci >= nci || cj >= ncj) continue;
+        cell_first[(int64_t)ci * ncj + cj] = offs[key];
+        cell_count[(int64_t)ci * ncj + cj] = (int32_t)(offs[key + 1] - offs[key]);
+    }
+    return 0;
+}
+
 extern "C" int sfgpu_set_sort_interval(sfgpu_ctx *ctx, int32_t steps)
 {
     CHECK_CTX();

@@ -371,6 +371,16 @@ class KineticMaterial:
         self._check(self.lib.sfgpu_restart_load(self._ctx, self._sp, mesh.index, data, len(data), float(dt), C.byref(used), C.byref(added)))
         return used.value, added.value
 
+    def cellLists(self, mesh):
+        """Per-cell particle lists (what DSMC.java:194-252 / KM:1150-1179 build on the host): after this call
+        ``getParticles(mesh)`` is in cell order and particles ``first[i, j] .. first[i, j] + count[i, j]`` are the ones of cell (i, j).
+        Returns (first, count, n_sorted); the exceptional records follow at [n_sorted, np)."""
+        first = np.zeros((mesh.ni - 1, mesh.nj - 1), np.int64)
+        count = np.zeros((mesh.ni - 1, mesh.nj - 1), np.int32)
+        ns = C.c_int64()
+        self._check(self.lib.sfgpu_cell_lists(self._ctx, self._sp, mesh.index, first.ctypes.data_as(_lib.c_int64_p), count.ctypes.data_as(_lib.c_int32_p), C.byref(ns)))
+        return first, count, ns.value
+
     def takeSurfaceHits(self):
         """Surface hits of the last step (KM:586-602): dict of arrays mesh, seg, t, u, v, w, mpw, alive; also sets n_absorbed."""
         n, na = C.c_int64(), C.c_int64()

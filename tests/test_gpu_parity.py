@@ -539,3 +539,29 @@ def test_config_c_beam_with_injection_and_exits_matches_oracle(flags):
     beam injection every step; the rotation, the Ruyten weights, the symmetry axis and compaction at full mesh size."""
     exited = _full_size_vs_oracle(S.config_c(), 1 << 24, 4, flags, inject_every=1)
     assert exited > 0
+
+
+def test_cell_lists_for_collision_consumers():
+    """sfgpu_cell_lists sorts the store and tells where every cell's particles sit in download order."""
+    m = S.make_mesh(37, 29, DomainType.XY, 1e-3, "symmetry")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 9, vth_cells=0.8, kick_frac=0.1)
+    with KineticMaterial("ion", wl.charge, wl.mass, [m], m.domain_type) as km:
+        km.dt = wl.dt
+        km.addParticles(m, to_particles(wl.particles(0, 40000)), wl.dt)
+        for _ in range(4):
+            km.updateFields()
+        first, count, n_sorted = km.cellLists(m)
+        p = km.getParticles(m)
+        assert count.sum() == n_sorted <= p.n == km.getNp()
+        ci, cj = p.li.astype(np.int64), p.lj.astype(np.int64)
+        for i, j in [(0, 0), (5, 7), (35, 27), (17, 0), (20, 13)]:
+            sl = slice(first[i, j], first[i, j] + count[i, j])
+            assert count[i, j] == np.sum((ci[:n_sorted] == i) & (cj[:n_sorted] == j))
+            assert np.all(ci[sl] == i) and np.all(cj[sl] == j)
+        # the lists do not disturb the physics: one more step still matches the oracle
+        ok = O.OracleKM(wl.charge, wl.mass, [m])
+        ok.addParticles(0, wl.particles(0, 40000), wl.dt)
+        for _ in range(5):
+            ok.updateFields(wl.dt)
+        km.updateFields()
+        compare_state(km, ok)

@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--so", default="starfish_b200/libstarfish_gpu.so")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--sass", action="store_true", help="also list the hottest SASS instructions")
+    ap.add_argument("--sym", default=None, help="substring of the mangled symbol in the cubin when KERNEL (a regex on the demangled name) is ambiguous there")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "-k", "regex:" + a.kernel], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -56,7 +57,7 @@ def main():
         if len(r) < len(hdr) or not r[0].startswith("0x"):
             break
         sass.append(r)
-    lt = line_table(a.so, a.kernel)
+    lt = line_table(a.so, a.sym or a.kernel)
     if len(lt) != len(sass):
         print("warning: %d SASS rows in the report, %d in the cubin (rebuilt since the capture?)" % (len(sass), len(lt)))
     n = min(len(lt), len(sass))
@@ -72,7 +73,7 @@ def main():
         c["inst"] += inst
         c["samples"] += samp
         c["shared_wf"] += int(float(r[col["L1 Wavefronts Shared"]] or 0))
-        c["local_sectors"] += int(float(r[col["L2 Theoretical Sectors Local"]] or 0))
+        c["local_sectors"] += int(float(r[col["L2 Theoretical Sectors Local"]] or 0)) if "L2 Theoretical Sectors Local" in col else 0
         for h in stall_cols:
             v = int(float(r[col[h]] or 0))
             if v:
