@@ -20,7 +20,7 @@
 #include "sf_generic.cuh"
 
 #ifndef SF_FAST_WARPS
-#define SF_FAST_WARPS 5 // warps per CTA of the tiled kernel (3 CTAs of 5 warps fit the 227 KB of shared memory: 15 warps / SM)
+#define SF_FAST_WARPS 4 // warps per CTA of the tiled kernel (3 CTAs of 4 warps x 17.4 KB fit the 227 KB of shared memory: 12 warps / SM)
 #endif
 #ifndef SF_PPT
 #define SF_PPT 1        // particles per lane and batch (independent instruction streams hide FP64 latency)
@@ -33,8 +33,16 @@
 #ifndef SF_STAGE
 #define SF_STAGE 0 // 1: cp.async prefetch of the next batch through shared memory; 0: plain loads, 3.5 KB less per warp
 #endif
+#ifndef SF_ETILE
+#define SF_ETILE 1 // 1: the E field of the work item's tile (+ SF_EHALO cells) is staged in shared memory, the gathers of the common path read it
+#endif
+#ifndef SF_EHALO
+#define SF_EHALO 2
+#endif
+#define SF_ENT (SF_TILE + 2 * SF_EHALO + 1) // nodes per edge of the staged E tile
+#define SF_ETILE_DOUBLES (SF_ETILE * (2 * SF_ENT * SF_ENT + (2 * SF_ENT * SF_ENT) % 2))
 #define SF_EXTRA 6 // per-warp sums next to the tile: energy, fallback N/Px/Py/Pz/E (the fallback count rides in the tag of E)
-#define SF_SCRATCH_DOUBLES (SF_EXTRA + 13 * SF_WROW + 16 + 16 * SF_PPT + 2 + SF_STAGE * 2 * 7 * 32 * SF_PPT)
+#define SF_SCRATCH_DOUBLES (SF_EXTRA + 13 * SF_WROW + 16 + 16 * SF_PPT + 2 + SF_ETILE_DOUBLES + SF_STAGE * 2 * 7 * 32 * SF_PPT)
 #define SF_WARP_SMEM_BYTES ((SF_TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8)
 
 __device__ __forceinline__ double sf_vacant() { return __longlong_as_double(0x7ff8000000000001LL); }
@@ -154,25 +162,50 @@ __device__ __forceinline__ bool fast_load_move(const FastStepArgs &a, const Mesh
 // paths are bit-identical; `ok` false means "not the common case": the caller re-runs the particle through
 // sf_move() from its original state.
 // ---------------------------------------------------------------------------------------------------------
-template <bool SEG> // SEG: the mesh has segment nodes; a sub-step whose node box touches one is not the common case
-__device__ __forceinline__ bool sf_move_simple(const MeshDev &m, double qm, double dt, PState &p)
+// where the common path finds the four E nodes of a cell: global memory (L1 / L2), or the tile staged in shared memory
+struct EGlobal {
+    __device__ __forceinline__ bool corners(const MeshDev &m, int i, int j, bool ok, double (&e)[8]) const
+    {
+        const int ic = min(max(i, 0), m.ni - 2), jc = min(max(j, 0), m.nj - 2); // safe addresses when !ok
+        const size_t n00 = (size_t)ic * m.nj + jc;
+        const double *fi = m.efi + n00, *fj = m.efj + n00;
+        e[0] = __ldg(fi); e[1] = __ldg(fi + m.nj); e[2] = __ldg(fi + m.nj + 1); e[3] = __ldg(fi + 1);
+        e[4] = __ldg(fj); e[5] = __ldg(fj + m.nj); e[6] = __ldg(fj + m.nj + 1); e[7] = __ldg(fj + 1);
+        return ok;
+    }
+};
+struct ETile { // efi, efj over SF_ENT x SF_ENT nodes starting at node (i0, j0); a particle outside the tile is not the common case
+    const double *e;
+    int i0, j0;
+    __device__ __forceinline__ bool corners(const MeshDev &m, int i, int j, bool ok, double (&c)[8]) const
+    {
+        const int ti = i - i0, tj = j - j0;
+        ok = ok && (unsigned)ti < (unsigned)(SF_ENT - 1) && (unsigned)tj < (unsigned)(SF_ENT - 1);
+        const double *b = e + (ok ? ti * SF_ENT + tj : 0);
+        c[0] = b[0]; c[1] = b[SF_ENT]; c[2] = b[SF_ENT + 1]; c[3] = b[1];
+        c[4] = b[SF_ENT * SF_ENT]; c[5] = b[SF_ENT * SF_ENT + SF_ENT]; c[6] = b[SF_ENT * SF_ENT + SF_ENT + 1]; c[7] = b[SF_ENT * SF_ENT + 1];
+        return ok;
+    }
+};
+
+template <bool SEG, class EField> // SEG: the mesh has segment nodes; a sub-step whose node box touches one is not the common case
+__device__ __forceinline__ bool sf_move_simple(const MeshDev &m, double qm, double dt, PState &p, const EField &ef)
 {
     const int ni = m.ni, nj = m.nj;
     const int i = sf_j2i(p.li), j = sf_j2i(p.lj);
     bool ok = (p.mpw > 0) && i >= 0 && j >= 0 && i < ni - 1 && j < nj - 1;
-    const int ic = min(max(i, 0), ni - 2), jc = min(max(j, 0), nj - 2); // safe addresses when !ok
     const double di = p.li - i, dj = p.lj - j;
-    const size_t n00 = (size_t)ic * nj + jc;
-    const double *fi = m.efi + n00, *fj = m.efj + n00;
+    double e[8];
+    ok = ef.corners(m, i, j, ok, e);
     const double w00 = (1 - di) * (1 - dj), w10 = di * (1 - dj), w11 = di * dj, w01 = (1 - di) * dj; // F2D:345-348
-    double ex = w00 * __ldg(fi);
-    ex += w10 * __ldg(fi + nj);
-    ex += w11 * __ldg(fi + nj + 1);
-    ex += w01 * __ldg(fi + 1);
-    double ey = w00 * __ldg(fj);
-    ey += w10 * __ldg(fj + nj);
-    ey += w11 * __ldg(fj + nj + 1);
-    ey += w01 * __ldg(fj + 1);
+    double ex = w00 * e[0];
+    ex += w10 * e[1];
+    ex += w11 * e[2];
+    ex += w01 * e[3];
+    double ey = w00 * e[4];
+    ey += w10 * e[5];
+    ey += w11 * e[6];
+    ey += w01 * e[7];
     const double u = p.u + qm * ex * dt; // KM:345-346 with part.dt = 0 + dt
     const double v = p.v + qm * ey * dt;
     double x = p.x + u * dt; // KM:369-370
@@ -245,8 +278,11 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     // further per row: the eight lanes of a quarter warp then read eight different bank groups and the 128-bit operand loads stay conflict free)
     double *sOnes = sV + 8 * SF_WROW + ((7 * SF_WROW - 8 * SF_WROW) % 16 + 16) % 16;
     int *sKey = reinterpret_cast<int *>(sV + 9 * SF_WROW + 16); // [32 * SF_PPT] tile-local cell of each row, then the fallback count
+#if SF_ETILE
+    double *sE = reinterpret_cast<double *>(sKey + 32 * SF_PPT + 4); // [2][SF_ENT][SF_ENT] efi, efj around the tile
+#endif
 #if SF_STAGE
-    double *sIn = reinterpret_cast<double *>(sKey + 32 * SF_PPT + 4); // [2 stages][7][32 * SF_PPT] prefetched particle state
+    double *sIn = reinterpret_cast<double *>(sKey + 32 * SF_PPT + 4) + SF_ETILE_DOUBLES; // [2 stages][7][32 * SF_PPT] prefetched particle state
 #endif
     const MeshDev &m = a.m;
     const size_t plane = (size_t)m.ni * m.nj;
@@ -277,6 +313,25 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
         const WorkItem wi = a.items[it];
         const int ti0 = (wi.tile / a.ntj) * SF_TILE - SF_HALO; // first node row / column held by the tile
         const int tj0 = (wi.tile % a.ntj) * SF_TILE - SF_HALO;
+#if SF_ETILE
+        // E field of the tile's neighbourhood (F2D:300-350 reads four nodes per field and particle): staged once per work item
+        ETile etile;
+        etile.e = sE;
+        etile.i0 = ti0 + SF_HALO - SF_EHALO;
+        etile.j0 = tj0 + SF_HALO - SF_EHALO;
+        __syncwarp();
+        for (int k = lane; k < SF_ENT * SF_ENT; k += 32) {
+            const int gi = etile.i0 + k / SF_ENT, gj = etile.j0 + k % SF_ENT;
+            double fi = 0.0, fj = 0.0;
+            if (gi >= 0 && gj >= 0 && gi < m.ni && gj < m.nj) {
+                fi = __ldg(m.efi + (size_t)gi * m.nj + gj);
+                fj = __ldg(m.efj + (size_t)gi * m.nj + gj);
+            }
+            sE[k] = fi;
+            sE[SF_ENT * SF_ENT + k] = fj;
+        }
+        __syncwarp();
+#endif
 #if SF_STAGE
         sf_prefetch_batch(a.fs, sIn, (size_t)wi.begin, 0, wi.count, lane);
 #else
@@ -345,7 +400,11 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                 p[j].li = sf_div_exact(p[j].x - m.x0, m.dhx, m.rdhx, m.fastdiv); // the stored lc of a normal particle is exactly XtoL(pos)
                 p[j].lj = sf_div_exact(p[j].y - m.y0, m.dhy, m.rdhy, m.fastdiv);
                 p[j].dt = 0;
-                done[j] = present[j] && simple_ok && sf_move_simple<SEG>(m, a.qm, a.dt, p[j]);
+#if SF_ETILE
+                done[j] = present[j] && simple_ok && sf_move_simple<SEG>(m, a.qm, a.dt, p[j], etile);
+#else
+                done[j] = present[j] && simple_ok && sf_move_simple<SEG>(m, a.qm, a.dt, p[j], EGlobal());
+#endif
             }
             int key[SF_PPT];
             DepW dw[SF_PPT];

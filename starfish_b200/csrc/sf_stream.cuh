@@ -362,7 +362,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
                 }
             }
             int fl = 3;
-            if (simple_ok && sf_move_simple<false>(m, a.b.qm, a.b.dt, p)) {
+            if (simple_ok && sf_move_simple<false>(m, a.b.qm, a.b.dt, p, EGlobal())) {
                 st[0 * SFS_ROW + s] = p.x; st[1 * SFS_ROW + s] = p.y; st[2 * SFS_ROW + s] = p.z;
                 st[3 * SFS_ROW + s] = p.u; st[4 * SFS_ROW + s] = p.v; st[5 * SFS_ROW + s] = p.w;
             } else {
