@@ -682,6 +682,32 @@ k_sort_scatter(FastPtrs in, FastPtrs out, unsigned long long n, const unsigned *
     out.tag[d] = in.tag[q];
 }
 
+// pass 3 in two halves (default): 3a writes only the inverse permutation (4 bytes per particle, scattered), 3b lets thread d of the
+// OUTPUT gather its particle: the eight 8-byte streams are then read scattered (the input is still roughly in cell order, so the
+// sectors are shared by neighbouring lanes through L1) and written fully coalesced, instead of written scattered
+__global__ void __launch_bounds__(256)
+k_sort_invert(unsigned long long n, const unsigned *__restrict__ offs, const unsigned *__restrict__ keys, const unsigned *__restrict__ ranks,
+              unsigned *__restrict__ inv)
+{
+    const unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const unsigned key = keys[q];
+    if (key == SF_KEY_NONE) return;
+    inv[offs[key] + ranks[q]] = (unsigned)q;
+}
+
+__global__ void __launch_bounds__(256)
+k_sort_gather(FastPtrs in, FastPtrs out, unsigned long long n_out, const unsigned *__restrict__ inv)
+{
+    const unsigned long long d = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_out) return;
+    const size_t q = inv[d];
+    out.x[d] = in.x[q]; out.y[d] = in.y[q]; out.z[d] = in.z[q];
+    out.u[d] = in.u[q]; out.v[d] = in.v[q]; out.w[d] = in.w[q];
+    out.mpw[d] = in.mpw[q];
+    out.tag[d] = in.tag[q];
+}
+
 // work items: each tile's run [offs[tile*64], offs[(tile+1)*64]) cut into pieces of <= SF_ITEM_MAX particles
 __global__ void k_build_items(const unsigned *__restrict__ offs, int n_tiles, WorkItem *__restrict__ items, unsigned *__restrict__ n_items,
                               unsigned max_items)

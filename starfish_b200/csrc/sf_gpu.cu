@@ -108,7 +108,7 @@ struct FastStore { // cell-sorted SoA store of the normal particles of one speci
     int64_t alive = 0;    // live particles
     bool dirty = false;   // has vacant slots
     int steps_since_sort = 0;
-    unsigned *keys = nullptr, *ranks = nullptr; // per particle, sort scratch
+    unsigned *keys = nullptr, *ranks = nullptr, *inv = nullptr; // per particle, sort scratch (key, rank in its cell, inverse permutation)
     int64_t kr_cap = 0;
     unsigned *hist = nullptr, *offs = nullptr;  // per cell key (+1): live particles per key; segment offsets of the sorted prefix
     // streaming step (sf_stream.cuh): histogram accumulated for the next launch, output segment offsets, output cursors
@@ -197,6 +197,7 @@ struct sfgpu_ctx {
     bool hybrid = false;     // tiled path: run the step in which a re-sort is due with the streaming kernel instead of sorting separately
     unsigned *h_cnt2 = nullptr; // pinned: per-mesh work-item counts read back with the step counters
     int last_kernel = 0;     // step kernel of the last sfgpu_step: 0 tiled, 1 streaming, 2 generic
+    bool sort_gather = true; // cell sort: inverse permutation + gather with coalesced stores (false: one scatter pass; env SFGPU_SORT_GATHER=0)
     bool stream_sort = false; // periodic re-sort of the tiled path: 1 = streaming pass (k_stream_sort), 0 = generic counting sort (equal speed measured)
     bool stream_check = false; // debug: verify the output cursors after every streaming launch
     unsigned long long *d_bad = nullptr;
@@ -298,7 +299,7 @@ static int fast_reserve(sfgpu_ctx *ctx, FastStore &f, int64_t need)
 
 static void fast_free(FastStore &f)
 {
-    void *ptrs[] = {f.slab, f.alt_slab, f.keys, f.ranks, f.hist, f.offs, f.items, f.d_nitems, f.cub_tmp, f.hist_next, f.offs_out, f.cursor, f.defer};
+    void *ptrs[] = {f.slab, f.alt_slab, f.keys, f.ranks, f.hist, f.offs, f.items, f.d_nitems, f.cub_tmp, f.hist_next, f.offs_out, f.cursor, f.defer, f.inv};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     f = FastStore();
@@ -350,6 +351,9 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
         f.keys = f.ranks = nullptr; f.kr_cap = 0;
         CU(cudaMalloc(&f.keys, (size_t)f.cap * sizeof(unsigned)));
         CU(cudaMalloc(&f.ranks, (size_t)f.cap * sizeof(unsigned)));
+        if (f.inv) CU(cudaFree(f.inv));
+        f.inv = nullptr;
+        CU(cudaMalloc(&f.inv, (size_t)f.cap * sizeof(unsigned)));
         f.kr_cap = f.cap;
     }
     const unsigned want_items = (unsigned)(f.n / SF_ITEM_MAX + (int64_t)f.nti * f.ntj + 1);
@@ -364,7 +368,16 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     k_sort_count<<<grid, 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, (unsigned long long)f.n, f.ntj, f.hist, f.keys, f.ranks);
     CU(cudaGetLastError());
     CU(cub::DeviceScan::ExclusiveSum(f.cub_tmp, f.cub_bytes, f.hist, f.offs, (int)(f.nkeys + 1), ctx->stream));
-    k_sort_scatter<<<grid, 256, 0, ctx->stream>>>(f.p, f.alt, (unsigned long long)f.n, f.offs, f.keys, f.ranks);
+    if (ctx->sort_gather) { // inverse permutation first (the keys array is reused for it after the fact: ranks -> inv), then a gather with coalesced stores
+        k_sort_invert<<<grid, 256, 0, ctx->stream>>>((unsigned long long)f.n, f.offs, f.keys, f.ranks, f.inv);
+        CU(cudaGetLastError());
+        const unsigned ggrid = (unsigned)((f.alive + 255) / 256);
+        if (ggrid) k_sort_gather<<<ggrid, 256, 0, ctx->stream>>>(f.p, f.alt, (unsigned long long)f.alive, f.inv);
+        ctx->launch_total++;
+        ctx->last_launches++;
+    } else {
+        k_sort_scatter<<<grid, 256, 0, ctx->stream>>>(f.p, f.alt, (unsigned long long)f.n, f.offs, f.keys, f.ranks);
+    }
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
     const int n_tiles = f.nti * f.ntj;
@@ -580,6 +593,7 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         if (const char *e = getenv("SFGPU_STREAM_SORT")) ctx->stream_sort = atoi(e) != 0;
         CU(cudaMalloc(&ctx->d_xfer, sizeof(XferDev) * SF_MAX_MESHES));
         CU(cudaMalloc(&ctx->d_args, sizeof(FastStepArgs) * SF_MAX_MESHES));
+        if (const char *e = getenv("SFGPU_SORT_GATHER")) ctx->sort_gather = atoi(e) != 0;
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
         CU(cudaFuncSetAttribute(k_fast_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         CU(cudaFuncSetAttribute(k_fast_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
