@@ -236,14 +236,14 @@ def main():
     km.timerStart()
     for _ in range(args.steps):
         one_step()
-        pushes += km.getNp() + km.n_exited_last()
-        _tot, ker, _n = km.lastStepTiming()
+        np_alive, n_exit, ker, kind, nfall = km.stepStats()
+        pushes += np_alive + n_exit
         ker_ms += ker
-        rec = by_kind.setdefault(km.lastStepKernel(), [0, 0.0, 0])
+        rec = by_kind.setdefault(kind, [0, 0.0, 0])
         rec[0] += 1
         rec[1] += ker
-        rec[2] += km.getNp() + km.n_exited_last()
-        fallback += km.lastStepFallback()
+        rec[2] += np_alive + n_exit
+        fallback += nfall
     dev_ms = km.timerStop()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)

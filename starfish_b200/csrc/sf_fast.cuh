@@ -652,7 +652,7 @@ k_sort_count(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs fs, unsig
     unsigned key = SF_KEY_NONE;
     if (q < n) {
         const double mpw = fs.mpw[q];
-        if (mpw == mpw) key = sf_cell_key(m, (fs.x[q] - m.x0) / m.dhx, (fs.y[q] - m.y0) / m.dhy, ntj);
+        if (mpw == mpw) key = sf_cell_key(m, sf_div_exact(fs.x[q] - m.x0, m.dhx, m.rdhx, m.fastdiv), sf_div_exact(fs.y[q] - m.y0, m.dhy, m.rdhy, m.fastdiv), ntj);
     }
     const unsigned act = __ballot_sync(0xffffffffu, key != SF_KEY_NONE);
     if (key != SF_KEY_NONE) {

@@ -1470,7 +1470,6 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                     f.defer_cap = f.cap;
                     a.defer = f.defer; a.defer_cap = (unsigned)(f.defer_cap > 0x7fffffff ? 0x7fffffff : f.defer_cap);
                 }
-                CU(cudaMemcpyAsync(ctx->d_args + m, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before return
                 if (a.m.any_seg) k_fast_step<true><<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
                 else k_fast_step<false><<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
                 CU(cudaGetLastError());

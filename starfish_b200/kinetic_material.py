@@ -437,6 +437,17 @@ class KineticMaterial:
         self._check(self.lib.sfgpu_last_step_timing(self._ctx, C.byref(tot), C.byref(ker), C.byref(n)))
         return tot.value, ker.value, n.value
 
+    def stepStats(self):
+        """(particles alive, particles that left through open faces in the last step, step-kernel ms, step kernel kind, out-of-tile
+        deposits) of the last step with as few library calls as possible (bench.py calls this inside its timed loop)."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.sfgpu_get_sums(self._ctx, self._sp, None, C.byref(a), C.byref(b), None))
+        ker, k, f = C.c_float(), C.c_int32(), C.c_int64()
+        self._check(self.lib.sfgpu_last_step_timing(self._ctx, None, C.byref(ker), None))
+        self._check(self.lib.sfgpu_last_step_kernel(self._ctx, C.byref(k)))
+        self._check(self.lib.sfgpu_last_step_counters(self._ctx, C.byref(f)))
+        return a.value, b.value, ker.value, k.value, f.value
+
     def lastStepKernel(self):
         """Which step kernel ran last: 0 tiled in-place, 1 streaming (moves, deposits and re-sorts), 2 generic."""
         k = C.c_int32()
