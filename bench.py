@@ -319,7 +319,7 @@ def main():
             import hashlib
             h = hashlib.sha1()
             for fn in sorted(os.listdir(os.path.join(ROOT, "starfish_b200", "csrc"))):
-                if fn.endswith((".cu", ".cuh")):
+                if fn.endswith(".cuh"):  # the kernels (sf_gpu.cu is host code)
                     h.update(open(os.path.join(ROOT, "starfish_b200", "csrc", fn), "rb").read())
             if tj.get("csrc_sha1") == h.hexdigest():
                 traffic = tj.get(wname)

@@ -72,7 +72,9 @@ extern "C" {
 #define SFGPU_STEP_GENERIC 1u  /* cross-check mode: no cell sort, no warp tiles; every particle gathers
                                   and deposits straight from / to global memory (FP64 REDs)         */
 #define SFGPU_STEP_DEFER_FINISH 2u /* do not close the step: the host still has slow-path survivors to
-                                      re-inject (SFGPU_INJECT_DEPOSIT_NOW); it calls sfgpu_finish_step */
+                                      re-inject (SFGPU_INJECT_DEPOSIT_NOW); it calls sfgpu_finish_step.  One deferred
+                                      step per context at a time: stepping or injecting into ANOTHER species before
+                                      sfgpu_finish_step is refused (the step counters are per context) */
 #define SFGPU_STEP_INPLACE 4u  /* force the in-place tiled step kernel + periodic cell sort (sf_fast.cuh)            */
 #define SFGPU_STEP_STREAM 8u   /* force the streaming step kernel that re-sorts the store as it writes (sf_stream.cuh).
                                   Without either flag the context default applies (env SFGPU_PATH=tiled|stream).    */

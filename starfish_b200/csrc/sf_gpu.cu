@@ -1105,6 +1105,9 @@ extern "C" int sfgpu_inject(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, const s
     if ((p->li == nullptr) != (p->lj == nullptr)) return fail(ctx, SFGPU_EINVAL, "sfgpu_inject: give both li and lj or neither");
     if ((flags & SFGPU_INJECT_TRANSFER) && (flags & (SFGPU_INJECT_REWIND | SFGPU_INJECT_DEPOSIT_NOW)))
         return fail(ctx, SFGPU_EINVAL, "sfgpu_inject: TRANSFER excludes REWIND and DEPOSIT_NOW");
+    for (size_t k = 0; k < ctx->species.size(); k++) // (injection kernels use the context's step counters too)
+        if ((int)k != sp && ctx->species[k].step_open)
+            return fail(ctx, SFGPU_ESTATE, "species %d has a deferred step open: call sfgpu_finish_step(%d) before injecting into species %d", (int)k, (int)k, (int)sp);
     int rc = sync_meshes(ctx);
     if (rc) return rc;
     Species &s = ctx->species[sp];
@@ -1298,6 +1301,8 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     const int nmesh = (int)ctx->meshes.size();
     if (s.slow_n) return fail(ctx, SFGPU_ESTATE, "take the slow-path particles of the previous step first");
     if (s.step_open) return fail(ctx, SFGPU_ESTATE, "previous step was deferred: call sfgpu_finish_step first");
+    for (size_t k = 0; k < ctx->species.size(); k++) // the step counters (mover sums included) are per context: one open step at a time
+        if (ctx->species[k].step_open) return fail(ctx, SFGPU_ESTATE, "species %d has a deferred step open: call sfgpu_finish_step(%d) first", (int)k, (int)k);
     const bool untiled = (flags & SFGPU_STEP_GENERIC) != 0;
     ctx->last_launches = 0;
     int64_t n_total = 0;

@@ -565,3 +565,76 @@ def test_cell_lists_for_collision_consumers():
             ok.updateFields(wl.dt)
         km.updateFields()
         compare_state(km, ok)
+
+
+def test_one_deferred_step_per_context():
+    """The step counters (mover sums included) belong to the context: while one species has a deferred step open, stepping or
+    injecting into another species of the same context is refused instead of silently clobbering them (round-1 advisor finding)."""
+    import ctypes as C
+    from starfish_b200.kinetic_material import SfgpuError
+    m = S.make_mesh(20, 20, DomainType.XY, 1e-3, "open")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 3, vth_cells=0.3)
+    with KineticMaterial("a", wl.charge, wl.mass, [m], m.domain_type) as km:
+        km.dt = wl.dt
+        sp2 = C.c_int32(-1)
+        km._check(km.lib.sfgpu_species_add(km._ctx, wl.charge, 2 * wl.mass, 0, C.byref(sp2)))
+        km.addParticles(m, to_particles(wl.particles(0, 500)), wl.dt)
+        km._check(km.lib.sfgpu_step(km._ctx, km._sp, wl.dt, _lib.STEP_DEFER_FINISH))
+        rc = km.lib.sfgpu_step(km._ctx, sp2.value, wl.dt, 0)
+        assert rc == -6 and b"deferred step open" in km.lib.sfgpu_last_error(km._ctx)
+        km._check(km.lib.sfgpu_finish_step(km._ctx, km._sp))
+        km._check(km.lib.sfgpu_step(km._ctx, sp2.value, wl.dt, 0))
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_differential_cuda_vs_oracle_random_cases(flags):
+    """hypothesis-drawn meshes (size, spacing, origin), per-face boundary types (OPEN / SYMMETRY / PERIODIC / DIRICHLET), time steps,
+    charge sign, field amplitudes, thermal speeds from 0.05 to 2.5 cells per step, particles exactly on nodes / faces / the plus
+    edge and with zero or negative weight: the CUDA path must match the oracle (state bit exact, deposit 1e-10) after every step."""
+    pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    bcs = [int(BC.OPEN), int(BC.SYMMETRY), int(BC.PERIODIC), int(BC.DIRICHLET)]
+
+    @settings(max_examples=16, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(dom=st.sampled_from([DomainType.XY, DomainType.RZ, DomainType.ZR]), ni=st.integers(3, 40), nj=st.integers(3, 40),
+           dhx=st.sampled_from([1e-3, 0.5e-3, 3.3e-4, 0.1]), dhy=st.sampled_from([1e-3, 2e-3, 7e-4, 0.25]),
+           x0=st.sampled_from([0.0, -0.15, 0.013]), faces=st.lists(st.sampled_from(bcs), min_size=4, max_size=4),
+           dt=st.sampled_from([1e-7, 3e-8, 1e-6]), neg=st.booleans(), seed=st.integers(0, 10**6), e_amp=st.sampled_from([0.0, 1e2, 1e5]),
+           vth=st.sampled_from([0.05, 0.6, 2.5]))
+    def run(dom, ni, nj, dhx, dhy, x0, faces, dt, neg, seed, e_amp, vth):
+        ox = x0 if dom != DomainType.RZ else abs(x0)
+        m = UniformMesh(ni, nj, (ox, 0.0), (dhx, dhy), dom)
+        for f, t in zip(Face, faces):
+            if t == int(BC.PERIODIC) and dom != DomainType.XY:
+                t = int(BC.OPEN)
+            m.setMeshBCType(f, BC(t))
+        rng = np.random.default_rng(seed)
+        m.efi = e_amp * rng.standard_normal((ni, nj))
+        m.efj = e_amp * rng.standard_normal((ni, nj))
+        n = 3000
+        li, lj = rng.uniform(0, ni - 1, n), rng.uniform(0, nj - 1, n)
+        li[:6] = np.array([0.0, ni - 1.0, 1.0, float(ni // 2), 0.0, ni - 1.0])
+        lj[:6] = np.array([0.0, nj - 1.0, float(nj // 2), 1.0, nj - 1.0, 0.0])
+        x, y = ox + li * dhx, lj * dhy
+        if dom == DomainType.RZ:
+            x = np.maximum(x, ox + 1e-9 * dhx)
+        if dom == DomainType.ZR:
+            y = np.maximum(y, 1e-9 * dhy)
+        mpw = np.full(n, 1e3)
+        mpw[6], mpw[7] = 0.0, -1.0
+        arr = dict(x=x, y=y, z=np.zeros(n), u=vth * dhx / dt * rng.standard_normal(n), v=vth * dhy / dt * rng.standard_normal(n),
+                   w=vth * dhx / dt * rng.standard_normal(n), mpw=mpw)
+
+        class W:
+            charge, mass = (-S.QE if neg else S.QE), 16 * S.AMU
+        W.dt = dt
+        km, ok = make_pair([m], W, [arr], flags)
+        with km:
+            km.setSortInterval(2)
+            for _ in range(4):
+                km.updateFields()
+                ok.updateFields(dt)
+                compare_state(km, ok)
+                compare_fields(km, ok)
+
+    run()

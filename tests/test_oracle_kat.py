@@ -269,7 +269,10 @@ def _compare(km, pk, nmesh):
                 assert g == w_ or (g != g and w_ != w_), (k, a, got, want)
         raw = np.array(pk.raw[k])
         # same arithmetic, but the oracle walks particles in store order and the Python lists in theirs
-        assert np.allclose(km.raw[k], raw, rtol=1e-12, atol=0)
+        finite = np.isfinite(raw)
+        assert np.array_equal(finite, np.isfinite(km.raw[k]))  # a NaN weight poisons the same nodes in both
+        scale = np.abs(np.where(finite, raw, 0)).max(axis=(1, 2), keepdims=True)
+        assert np.allclose(np.where(finite, km.raw[k], 0), np.where(finite, raw, 0), rtol=1e-12, atol=1e-12 * scale)
         assert np.array_equal(km.raw[k][7], raw[7])
 
 
@@ -289,7 +292,7 @@ def _run_pair(meshes, charge, mass, dt, arrays_per_mesh, steps, check_sums=True)
         _compare(km, pk, len(meshes))
         assert km.n_exited == pk.n_exited
         if check_sums and len(meshes) == 1:
-            assert list(km.sums5) == pk.sums
+            assert all(a == b or (a != a and b != b) for a, b in zip(km.sums5, pk.sums)), (list(km.sums5), pk.sums)
         assert sum(len(s[1]["x"]) for s in km.slow) == len(pk.slow)
     return km, pk
 
@@ -412,3 +415,50 @@ def test_oracle_uniform_source_matches_python_restatement(cold, v_drift):
     assert km.getNp(0) > 0 and km.getNp(1) > 0
     wz = km.sorted_parts(0)["w"]
     assert np.all(np.signbit(wz) == (v_drift < 0 and not cold))  # the one observable difference between the two sources
+
+
+# ---------------------------------------------------------------- (3) property-based differential test of the two restatements
+def test_differential_oracle_vs_python_restatement_random_cases():
+    """hypothesis draws mesh sizes, spacings, origins, per-face boundary types, time steps, charge sign, field amplitudes and
+    particle sets that sit exactly ON nodes / faces / the plus edge or carry zero, negative and NaN weights; the C oracle and the
+    independent Python restatement must agree bit for bit (particle state, exits, mover sums) after every step."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    bcs = [int(BC.OPEN), int(BC.SYMMETRY), int(BC.PERIODIC), int(BC.DIRICHLET)]
+
+    @settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(dom=st.sampled_from([DomainType.XY, DomainType.RZ, DomainType.ZR]), ni=st.integers(3, 9), nj=st.integers(3, 9),
+           dhx=st.sampled_from([1e-3, 0.5e-3, 3.3e-4, 0.1]), dhy=st.sampled_from([1e-3, 2e-3, 7e-4, 0.25]),
+           x0=st.sampled_from([0.0, -0.15, 0.013]), faces=st.lists(st.sampled_from(bcs), min_size=4, max_size=4),
+           dt=st.sampled_from([1e-7, 3e-8, 1e-6]), neg=st.booleans(), seed=st.integers(0, 10**6), e_amp=st.sampled_from([0.0, 1e2, 1e5]),
+           vth=st.sampled_from([0.05, 0.6, 2.5]))
+    def run(dom, ni, nj, dhx, dhy, x0, faces, dt, neg, seed, e_amp, vth):
+        ox = x0 if dom != DomainType.RZ else abs(x0)  # keep the radial axis non-negative
+        oy = 0.0
+        m = UniformMesh(ni, nj, (ox, oy), (dhx, dhy), dom)
+        for f, t in zip(Face, faces):
+            if t == int(BC.PERIODIC) and dom != DomainType.XY:
+                t = int(BC.OPEN)
+            m.setMeshBCType(f, BC(t))
+        rng = np.random.default_rng(seed)
+        m.efi = e_amp * rng.standard_normal((ni, nj))
+        m.efj = e_amp * rng.standard_normal((ni, nj))
+        n = 40
+        li = rng.uniform(0, ni - 1, n)
+        lj = rng.uniform(0, nj - 1, n)
+        li[:6] = np.array([0.0, ni - 1.0, 1.0, float(ni // 2), 0.0, ni - 1.0])  # on faces, nodes and the plus edge
+        lj[:6] = np.array([0.0, nj - 1.0, float(nj // 2), 1.0, nj - 1.0, 0.0])
+        x = ox + li * dhx
+        y = oy + lj * dhy
+        if dom == DomainType.RZ:
+            x = np.maximum(x, ox + 1e-9 * dhx)
+        if dom == DomainType.ZR:
+            y = np.maximum(y, oy + 1e-9 * dhy)
+        mpw = np.full(n, 1e3)
+        mpw[6], mpw[7], mpw[8] = 0.0, -1.0, np.nan
+        arr = dict(x=x, y=y, z=np.zeros(n), u=vth * dhx / dt * rng.standard_normal(n), v=vth * dhy / dt * rng.standard_normal(n),
+                   w=vth * dhx / dt * rng.standard_normal(n), mpw=mpw)
+        _run_pair([m], -S.QE if neg else S.QE, 16 * S.AMU, dt, [arr], 3)
+
+    run()

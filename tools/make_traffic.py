@@ -19,7 +19,7 @@ def csrc_sha1():
     h = hashlib.sha1()
     d = os.path.join(ROOT, "starfish_b200", "csrc")
     for fn in sorted(os.listdir(d)):
-        if fn.endswith((".cu", ".cuh")):
+        if fn.endswith(".cuh"):  # the kernels (sf_gpu.cu is host code)
             h.update(open(os.path.join(d, fn), "rb").read())
     return h.hexdigest()
 
