@@ -642,28 +642,47 @@ k_fast_deferred(const __grid_constant__ FastStepArgs a)
 #define SF_KEY_NONE 0xffffffffu
 
 // pass 1: key and rank of every particle; hist[key] = particles per cell.  Vacant slots get SF_KEY_NONE.
+// Four particles per thread (blockDim apart, so every load stays coalesced): the twelve loads and then the four
+// histogram atomics of a thread are in flight together instead of one dependent chain per particle.
+#define SF_COUNT_ILP 4
 __global__ void __launch_bounds__(256)
 k_sort_count(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs fs, unsigned long long n, int ntj, unsigned *__restrict__ hist,
              unsigned *__restrict__ keys, unsigned *__restrict__ ranks)
 {
     const MeshDev m = meshes[mesh_id];
-    const unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long q0 = (unsigned long long)blockIdx.x * (blockDim.x * SF_COUNT_ILP) + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    unsigned key = SF_KEY_NONE;
-    if (q < n) {
-        const double mpw = fs.mpw[q];
-        if (mpw == mpw) key = sf_cell_key(m, sf_div_exact(fs.x[q] - m.x0, m.dhx, m.rdhx, m.fastdiv), sf_div_exact(fs.y[q] - m.y0, m.dhy, m.rdhy, m.fastdiv), ntj);
+    double mpw[SF_COUNT_ILP], x[SF_COUNT_ILP], y[SF_COUNT_ILP];
+#pragma unroll
+    for (int k = 0; k < SF_COUNT_ILP; k++) {
+        const unsigned long long q = q0 + (unsigned long long)k * blockDim.x;
+        mpw[k] = sf_vacant();
+        x[k] = y[k] = 0.0;
+        if (q < n) { mpw[k] = fs.mpw[q]; x[k] = fs.x[q]; y[k] = fs.y[q]; }
     }
-    const unsigned act = __ballot_sync(0xffffffffu, key != SF_KEY_NONE);
-    if (key != SF_KEY_NONE) {
-        const unsigned grp = __match_any_sync(act, key);
-        const int leader = __ffs(grp) - 1;
-        unsigned base = 0;
-        if (lane == leader) base = atomicAdd(&hist[key], (unsigned)__popc(grp));
-        base = __shfl_sync(grp, base, leader);
-        ranks[q] = base + __popc(grp & ((1u << lane) - 1u));
+    unsigned key[SF_COUNT_ILP], grp[SF_COUNT_ILP], base[SF_COUNT_ILP];
+#pragma unroll
+    for (int k = 0; k < SF_COUNT_ILP; k++) {
+        key[k] = SF_KEY_NONE;
+        if (mpw[k] == mpw[k])
+            key[k] = sf_cell_key(m, sf_div_exact(x[k] - m.x0, m.dhx, m.rdhx, m.fastdiv), sf_div_exact(y[k] - m.y0, m.dhy, m.rdhy, m.fastdiv), ntj);
+        const unsigned act = __ballot_sync(0xffffffffu, key[k] != SF_KEY_NONE);
+        grp[k] = 0;
+        base[k] = 0;
+        if (key[k] != SF_KEY_NONE) {
+            grp[k] = __match_any_sync(act, key[k]);
+            if (lane == __ffs(grp[k]) - 1) base[k] = atomicAdd(&hist[key[k]], (unsigned)__popc(grp[k]));
+        }
     }
-    if (q < n) keys[q] = key;
+#pragma unroll
+    for (int k = 0; k < SF_COUNT_ILP; k++) {
+        const unsigned long long q = q0 + (unsigned long long)k * blockDim.x;
+        if (key[k] != SF_KEY_NONE) {
+            const unsigned b = __shfl_sync(grp[k], base[k], __ffs(grp[k]) - 1);
+            ranks[q] = b + __popc(grp[k] & ((1u << lane) - 1u));
+        }
+        if (q < n) keys[q] = key[k];
+    }
 }
 
 // pass 3: scatter to the sorted position
@@ -685,27 +704,53 @@ k_sort_scatter(FastPtrs in, FastPtrs out, unsigned long long n, const unsigned *
 // pass 3 in two halves (default): 3a writes only the inverse permutation (4 bytes per particle, scattered), 3b lets thread d of the
 // OUTPUT gather its particle: the eight 8-byte streams are then read scattered (the input is still roughly in cell order, so the
 // sectors are shared by neighbouring lanes through L1) and written fully coalesced, instead of written scattered
+#define SF_SORT_ILP 4
 __global__ void __launch_bounds__(256)
 k_sort_invert(unsigned long long n, const unsigned *__restrict__ offs, const unsigned *__restrict__ keys, const unsigned *__restrict__ ranks,
               unsigned *__restrict__ inv)
 {
-    const unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const unsigned key = keys[q];
-    if (key == SF_KEY_NONE) return;
-    inv[offs[key] + ranks[q]] = (unsigned)q;
+    const unsigned long long q0 = (unsigned long long)blockIdx.x * (blockDim.x * SF_SORT_ILP) + threadIdx.x;
+    unsigned key[SF_SORT_ILP], rank[SF_SORT_ILP], off[SF_SORT_ILP];
+#pragma unroll
+    for (int k = 0; k < SF_SORT_ILP; k++) {
+        const unsigned long long q = q0 + (unsigned long long)k * blockDim.x;
+        key[k] = q < n ? keys[q] : SF_KEY_NONE;
+        rank[k] = (key[k] != SF_KEY_NONE) ? ranks[q] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < SF_SORT_ILP; k++) off[k] = (key[k] != SF_KEY_NONE) ? offs[key[k]] : 0u;
+#pragma unroll
+    for (int k = 0; k < SF_SORT_ILP; k++)
+        if (key[k] != SF_KEY_NONE) inv[off[k] + rank[k]] = (unsigned)(q0 + (unsigned long long)k * blockDim.x);
 }
 
 __global__ void __launch_bounds__(256)
 k_sort_gather(FastPtrs in, FastPtrs out, unsigned long long n_out, const unsigned *__restrict__ inv)
 {
-    const unsigned long long d = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_out) return;
-    const size_t q = inv[d];
-    out.x[d] = in.x[q]; out.y[d] = in.y[q]; out.z[d] = in.z[q];
-    out.u[d] = in.u[q]; out.v[d] = in.v[q]; out.w[d] = in.w[q];
-    out.mpw[d] = in.mpw[q];
-    out.tag[d] = in.tag[q];
+    const unsigned long long d0 = (unsigned long long)blockIdx.x * (blockDim.x * SF_SORT_ILP) + threadIdx.x;
+    size_t q[SF_SORT_ILP];
+#pragma unroll
+    for (int k = 0; k < SF_SORT_ILP; k++) {
+        const unsigned long long d = d0 + (unsigned long long)k * blockDim.x;
+        q[k] = d < n_out ? inv[d] : 0;
+    }
+    double v[SF_SORT_ILP][7];
+    int2 tag[SF_SORT_ILP];
+#pragma unroll
+    for (int k = 0; k < SF_SORT_ILP; k++) { // all gathers of the thread in flight together
+        v[k][0] = in.x[q[k]]; v[k][1] = in.y[q[k]]; v[k][2] = in.z[q[k]]; v[k][3] = in.u[q[k]];
+        v[k][4] = in.v[q[k]]; v[k][5] = in.w[q[k]]; v[k][6] = in.mpw[q[k]];
+        tag[k] = in.tag[q[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < SF_SORT_ILP; k++) {
+        const unsigned long long d = d0 + (unsigned long long)k * blockDim.x;
+        if (d < n_out) {
+            out.x[d] = v[k][0]; out.y[d] = v[k][1]; out.z[d] = v[k][2]; out.u[d] = v[k][3];
+            out.v[d] = v[k][4]; out.w[d] = v[k][5]; out.mpw[d] = v[k][6];
+            out.tag[d] = tag[k];
+        }
+    }
 }
 
 // work items: each tile's run [offs[tile*64], offs[(tile+1)*64]) cut into pieces of <= SF_ITEM_MAX particles

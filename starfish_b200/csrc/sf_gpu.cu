@@ -365,13 +365,13 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     }
     const unsigned grid = (unsigned)((f.n + 255) / 256);
     CU(cudaMemsetAsync(f.hist, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
-    k_sort_count<<<grid, 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, (unsigned long long)f.n, f.ntj, f.hist, f.keys, f.ranks);
+    k_sort_count<<<(unsigned)((f.n + 256 * SF_COUNT_ILP - 1) / (256 * SF_COUNT_ILP)), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, (unsigned long long)f.n, f.ntj, f.hist, f.keys, f.ranks);
     CU(cudaGetLastError());
     CU(cub::DeviceScan::ExclusiveSum(f.cub_tmp, f.cub_bytes, f.hist, f.offs, (int)(f.nkeys + 1), ctx->stream));
     if (ctx->sort_gather) { // inverse permutation first (the keys array is reused for it after the fact: ranks -> inv), then a gather with coalesced stores
-        k_sort_invert<<<grid, 256, 0, ctx->stream>>>((unsigned long long)f.n, f.offs, f.keys, f.ranks, f.inv);
+        k_sort_invert<<<(unsigned)((f.n + 256 * SF_SORT_ILP - 1) / (256 * SF_SORT_ILP)), 256, 0, ctx->stream>>>((unsigned long long)f.n, f.offs, f.keys, f.ranks, f.inv);
         CU(cudaGetLastError());
-        const unsigned ggrid = (unsigned)((f.alive + 255) / 256);
+        const unsigned ggrid = (unsigned)((f.alive + 256 * SF_SORT_ILP - 1) / (256 * SF_SORT_ILP));
         if (ggrid) k_sort_gather<<<ggrid, 256, 0, ctx->stream>>>(f.p, f.alt, (unsigned long long)f.alive, f.inv);
         ctx->launch_total++;
         ctx->last_launches++;
