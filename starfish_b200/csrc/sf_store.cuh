@@ -33,7 +33,9 @@ struct WorkItem {
 #define SF_HALO 2       // extra cells kept around the tile in the warp-private accumulation tile
 #endif
 #define SF_NT (SF_TILE + 2 * SF_HALO + 1) // nodes per edge of the accumulation tile
+#ifndef SF_ITEM_MAX
 #define SF_ITEM_MAX 2048 // particles per work item
+#endif
 
 // slow-path hand-over list: record + ProcessBoundary arguments
 struct SlowPtrs {
