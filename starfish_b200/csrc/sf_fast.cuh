@@ -647,8 +647,11 @@ k_fast_deferred(const __grid_constant__ FastStepArgs a)
 #define SF_COUNT_ILP 4
 __global__ void __launch_bounds__(256)
 k_sort_count(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs fs, unsigned long long n, int ntj, unsigned *__restrict__ hist,
-             unsigned *__restrict__ keys, unsigned *__restrict__ ranks)
+             unsigned *__restrict__ keys, unsigned *__restrict__ ranks, double dt_pred)
 {
+    // dt_pred != 0: the key is the cell of pos + vel*dt_pred, i.e. (up to the field kick) the cell the particle will be deposited into by the
+    // step that follows this sort: that step then finds its batches grouped by NEW cell, and every later step sees an order one step fresher.
+    // Order only: no result depends on it.
     const MeshDev m = meshes[mesh_id];
     const unsigned long long q0 = (unsigned long long)blockIdx.x * (blockDim.x * SF_COUNT_ILP) + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -658,7 +661,10 @@ k_sort_count(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs fs, unsig
         const unsigned long long q = q0 + (unsigned long long)k * blockDim.x;
         mpw[k] = sf_vacant();
         x[k] = y[k] = 0.0;
-        if (q < n) { mpw[k] = fs.mpw[q]; x[k] = fs.x[q]; y[k] = fs.y[q]; }
+        if (q < n) {
+            mpw[k] = fs.mpw[q]; x[k] = fs.x[q]; y[k] = fs.y[q];
+            if (dt_pred != 0) { x[k] += fs.u[q] * dt_pred; y[k] += fs.v[q] * dt_pred; }
+        }
     }
     unsigned key[SF_COUNT_ILP], grp[SF_COUNT_ILP], base[SF_COUNT_ILP];
 #pragma unroll

@@ -197,6 +197,10 @@ struct sfgpu_ctx {
     bool hybrid = false;     // tiled path: run the step in which a re-sort is due with the streaming kernel instead of sorting separately
     unsigned *h_cnt2 = nullptr; // pinned: per-mesh work-item counts read back with the step counters
     int last_kernel = 0;     // step kernel of the last sfgpu_step: 0 tiled, 1 streaming, 2 generic
+    // the periodic sort of the tiled path keys every particle by the cell of pos + vel*dt*h, i.e. (up to the field kick) the cell it will be deposited
+    // into h steps later: the steps between two sorts then see an order that is at most one or two steps away from "grouped by new cell" in EITHER
+    // direction (ages 1,0,1 for 3 steps and h = 2) instead of growing stale (ages 1,2,3).  < 0: h = min(2, (sort_every+1)/2); env SFGPU_SORT_PREDICT=h, 0 = current cell
+    double sort_predict = -1.0;
     bool sort_gather = true; // cell sort: inverse permutation + gather with coalesced stores (false: one scatter pass; env SFGPU_SORT_GATHER=0)
     bool stream_sort = false; // periodic re-sort of the tiled path: 1 = streaming pass (k_stream_sort), 0 = generic counting sort (equal speed measured)
     bool stream_check = false; // debug: verify the output cursors after every streaming launch
@@ -326,7 +330,7 @@ static int fast_init_geometry(sfgpu_ctx *ctx, FastStore &f, const MeshDev &m)
 // K3: counting sort of the fast store by cell key (tile-major) + compaction of vacant slots, out of place;
 // rebuilds the work items of the tiled kernel.  sortParticlesToCells (KM:1150-1179) is the closest reference
 // member: order only, no result changes beyond summation order.
-static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
+static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f, double dt_pred = 0.0)
 {
     f.steps_since_sort = 0;
     if (f.n == 0) {
@@ -365,7 +369,7 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
     }
     const unsigned grid = (unsigned)((f.n + 255) / 256);
     CU(cudaMemsetAsync(f.hist, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
-    k_sort_count<<<(unsigned)((f.n + 256 * SF_COUNT_ILP - 1) / (256 * SF_COUNT_ILP)), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, (unsigned long long)f.n, f.ntj, f.hist, f.keys, f.ranks);
+    k_sort_count<<<(unsigned)((f.n + 256 * SF_COUNT_ILP - 1) / (256 * SF_COUNT_ILP)), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, (unsigned long long)f.n, f.ntj, f.hist, f.keys, f.ranks, dt_pred * (ctx->sort_predict >= 0 ? ctx->sort_predict : std::min(2.0, 0.5 * (ctx->sort_every + 1))));
     CU(cudaGetLastError());
     CU(cub::DeviceScan::ExclusiveSum(f.cub_tmp, f.cub_bytes, f.hist, f.offs, (int)(f.nkeys + 1), ctx->stream));
     if (ctx->sort_gather) { // inverse permutation first (the keys array is reused for it after the fact: ranks -> inv), then a gather with coalesced stores
@@ -422,9 +426,9 @@ static int fast_reserve_alt(sfgpu_ctx *ctx, FastStore &f);
 // K3 for a store that is still roughly in cell order: histogram of the current cells, exclusive scan, one streaming pass
 // (k_stream_sort) that writes every particle into its cell's segment of the second slab.  Falls back to the generic counting
 // sort for a store that was never sorted or whose unsorted tail is large.
-static int fast_resort(sfgpu_ctx *ctx, int mesh_id, FastStore &f)
+static int fast_resort(sfgpu_ctx *ctx, int mesh_id, FastStore &f, double dt_pred = 0.0)
 {
-    if (!ctx->stream_sort || f.n == 0 || f.n_sorted == 0 || (f.n - f.n_sorted) * 16 > f.n) return fast_sort(ctx, mesh_id, f);
+    if (!ctx->stream_sort || f.n == 0 || f.n_sorted == 0 || (f.n - f.n_sorted) * 16 > f.n) return fast_sort(ctx, mesh_id, f, dt_pred);
     if ((uint64_t)f.n >= 0xfffffff0ull) return fail(ctx, SFGPU_EINVAL, "more than 2^32 particles of one species on one GPU mesh are not supported");
     int rc = fast_rehist(ctx, mesh_id, f);
     if (rc) return rc;
@@ -594,6 +598,7 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaMalloc(&ctx->d_xfer, sizeof(XferDev) * SF_MAX_MESHES));
         CU(cudaMalloc(&ctx->d_args, sizeof(FastStepArgs) * SF_MAX_MESHES));
         if (const char *e = getenv("SFGPU_SORT_GATHER")) ctx->sort_gather = atoi(e) != 0;
+        if (const char *e = getenv("SFGPU_SORT_PREDICT")) ctx->sort_predict = atof(e);
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
         CU(cudaFuncSetAttribute(k_fast_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
         CU(cudaFuncSetAttribute(k_fast_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
@@ -1356,7 +1361,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         if (f.n == 0) continue;
         const int64_t tail = f.n - f.n_sorted;
         if (f.n_sorted == 0 || !f.items_ok || f.steps_since_sort >= ctx->sort_every || tail * 16 > f.n || ctx->force_sort) {
-            rc = fast_resort(ctx, m, f); // streaming re-sort when the store is still roughly ordered, counting sort otherwise
+            rc = fast_resort(ctx, m, f, dt); // counting sort keyed by the cell each particle is about to move into (streaming re-sort pass: SFGPU_STREAM_SORT=1)
             if (rc) return rc;
             f.stream_ok = false;
         }
