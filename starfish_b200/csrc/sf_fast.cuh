@@ -42,7 +42,7 @@
 #define SF_ENT (SF_TILE + 2 * SF_EHALO + 1) // nodes per edge of the staged E tile
 #define SF_ETILE_DOUBLES (SF_ETILE * (2 * SF_ENT * SF_ENT + (2 * SF_ENT * SF_ENT) % 2))
 #define SF_EXTRA 6 // per-warp sums next to the tile: energy, fallback N/Px/Py/Pz/E (the fallback count rides in the tag of E)
-#define SF_SCRATCH_DOUBLES (SF_EXTRA + 13 * SF_WROW + 16 + 16 * SF_PPT + 2 + SF_ETILE_DOUBLES + SF_STAGE * 2 * 7 * 32 * SF_PPT)
+#define SF_SCRATCH_DOUBLES (SF_EXTRA + 13 * SF_WROW + 16 + 32 * SF_PPT + 16 + 16 * SF_PPT + 2 + SF_ETILE_DOUBLES + SF_STAGE * 2 * 7 * 32 * SF_PPT)
 #define SF_WARP_SMEM_BYTES ((SF_TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8)
 
 __device__ __forceinline__ double sf_vacant() { return __longlong_as_double(0x7ff8000000000001LL); }
@@ -277,7 +277,10 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     // weight and value of the counting lanes (f == 7): a row of ones placed on the bank group of value row 7 (rows are 272 bytes apart, i.e. 4 banks
     // further per row: the eight lanes of a quarter warp then read eight different bank groups and the 128-bit operand loads stay conflict free)
     double *sOnes = sV + 8 * SF_WROW + ((7 * SF_WROW - 8 * SF_WROW) % 16 + 16) % 16;
-    int *sKey = reinterpret_cast<int *>(sV + 9 * SF_WROW + 16); // [32 * SF_PPT] tile-local cell of each row, then the fallback count
+    // ... and a second row of ones for the WEIGHT operand of the counting lanes, on the bank group of value row 0 = weight row 4: none of the
+    // four weight rows a quarter warp reads (the first one collided with weight row 3)
+    double *sOnesW = sV + 9 * SF_WROW + 16 + ((0 * SF_WROW - (9 * SF_WROW + 16)) % 16 + 16) % 16;
+    int *sKey = reinterpret_cast<int *>(sV + 9 * SF_WROW + 16 + 32 * SF_PPT + 16); // [32 * SF_PPT] tile-local cell of each row, then the fallback count
 #if SF_ETILE
     double *sE = reinterpret_cast<double *>(sKey + 32 * SF_PPT + 4); // [2][SF_ENT][SF_ENT] efi, efj around the tile
 #endif
@@ -290,14 +293,14 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
 
     for (int k = lane; k < SF_TILE_DOUBLES + SF_EXTRA; k += 32) tile[k] = 0.0;
     if (lane == 0) sKey[32 * SF_PPT] = 0;
-    for (int k = lane; k < 32 * SF_PPT; k += 32) sOnes[k] = 1.0;
+    for (int k = lane; k < 32 * SF_PPT; k += 32) sOnes[k] = sOnesW[k] = 1.0;
     __syncwarp();
 
     // role of this lane in the reduction: node n (w00,w10,w11,w01) x field f (7 moments; f == 7: n == 0 counts the
     // particles of the cell (mpc), n == 1 sums mpw*|vel| of the whole work item (energy sum, KM:412))
     const int rn = lane >> 3, rf = lane & 7;
     const int noff = (rn == 0) ? 0 : (rn == 1) ? SF_NT : (rn == 2) ? SF_NT + 1 : 1;
-    const double *rw = (rf == 7) ? sOnes : (sW + rn * SF_WROW); // f == 7 lanes: weight 1.0
+    const double *rw = (rf == 7) ? sOnesW : (sW + rn * SF_WROW); // f == 7 lanes: weight 1.0
     const double *rv = (rf == 7 && rn != 1) ? sOnes : (sV + rf * SF_WROW); // row 7 of sV = mpw*|vel|
     const bool renergy = rf == 7 && rn == 1;
     double *racc = renergy ? (tile + SF_TILE_DOUBLES) : (tile + rf * (SF_NT * SF_NT) + ((rf == 7) ? 0 : noff));
