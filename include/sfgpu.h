@@ -66,7 +66,12 @@ extern "C" {
 #define SFGPU_INJECT_DEPOSIT_NOW 2u /* particle was already moved this step (slow-path survivor):
                                        add it to this step's deposit, move it from the next step on */
 #define SFGPU_INJECT_TRANSFER 4u    /* particle enters a mesh's transfer list (KM:1377-1380): it is
-                                       moved by the transfer sweeps of the next sfgpu_step          */
+                                       moved by the transfer sweeps of the next sfgpu_step.
+                                       Known difference: a slow-path survivor that crosses a MESH face while the HOST
+                                       finishes its sub-steps comes back this way and so finishes its residual dt (and
+                                       deposits) one step later than the reference, which sweeps it in the same
+                                       updateFields() (KM:131-142).  Only multi-mesh cases whose surface models stay on the
+                                       host are affected; segments registered with sfgpu_mesh_set_segments are not. */
 
 /* sfgpu_step flags */
 #define SFGPU_STEP_GENERIC 1u  /* cross-check mode: no cell sort, no warp tiles; every particle gathers

@@ -448,13 +448,22 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                 const int leader = __ffs(grp) - 1;
                 const int rank = __popc(grp & ((1u << lane) - 1u));
                 const bool isl = lane == leader;
-                int x = isl ? __popc(grp) : 0; // inclusive scan of the group sizes over the leaders, lane order
+                // first row of this lane's group = number of particles whose group leader is a lower lane: five ballots over the bits of the
+                // leader (a radix rank) instead of a five-step shuffle scan over the group sizes: no dependent shuffle chain
+                int off = 0;
+                {
+                    unsigned eq = 0xffffffffu; // lanes whose leader agrees with mine on the bits seen so far
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int y = __shfl_up_sync(0xffffffffu, x, d);
-                    if (lane >= d) x += y;
+                    for (int b = 4; b >= 0; b--) {
+                        const unsigned bal = __ballot_sync(0xffffffffu, (leader >> b) & 1);
+                        if ((leader >> b) & 1) {
+                            off += __popc(eq & ~bal);
+                            eq &= bal;
+                        } else {
+                            eq &= ~bal;
+                        }
+                    }
                 }
-                const int off = __shfl_sync(0xffffffffu, x, leader) - __popc(grp);
                 const int row = j * 32 + off + rank;
                 bmask[j] = __reduce_or_sync(0xffffffffu, isl ? (1u << off) : 0u);
                 sKey[row] = key[j];
