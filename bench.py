@@ -335,7 +335,7 @@ def main():
             "wall_ms_per_step": wall_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": "pushes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": int(launches), "untiled_deposit_fraction": fallback / max(pushes, 1),
+            "gpu_launches": int(launches), "untiled_deposit_fraction": fallback / max(pushes, 1), "tile_halo": km.tileHalo()[0],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": names[dom], "kernel_ms_per_launch": d_ms / d_steps,
                          "algorithmic_bytes_per_push": ALGO_BYTES_PER_PUSH, "kernel_ms_per_step": ker_ms / args.steps,

@@ -91,6 +91,8 @@ EXPORTS = {
     "sfgpu_restart_load": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_double, c_int64_p, c_int64_p]),
     "sfgpu_sort": (C.c_int, [C.c_void_p, C.c_int32]),
     "sfgpu_set_sort_interval": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sfgpu_set_tile_halo": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sfgpu_get_tile_halo": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "sfgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
     "sfgpu_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "sfgpu_deposit_device_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),

@@ -44,6 +44,17 @@
 #define SF_EXTRA 6 // per-warp sums next to the tile: energy, fallback N/Px/Py/Pz/E (the fallback count rides in the tag of E)
 #define SF_SCRATCH_DOUBLES (SF_EXTRA + 13 * SF_WROW + 16 + 32 * SF_PPT + 16 + 16 * SF_PPT + 2 + SF_ETILE_DOUBLES + SF_STAGE * 2 * 7 * 32 * SF_PPT)
 #define SF_WARP_SMEM_BYTES ((SF_TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8)
+// geometry of the tiled kernel per halo width.  A halo of one cell is enough while the deposits of a particle stay within one cell of the
+// cell it was sorted into (the sort key is the PREDICTED cell, so that is one step of thermal spread either way): the smaller tile lets
+// 15 warps share an SM instead of 12.  Populations that move further per step fall back to the two-cell halo (sfgpu_step picks, SFGPU_HALO)
+template <int HALO> struct FastGeom {
+    static constexpr int NT = SF_TILE + 2 * HALO + 1;              // nodes per edge of the accumulation tile
+    static constexpr int TILE_DOUBLES = SFGPU_NFIELDS * NT * NT;
+    static constexpr int WARP_BYTES = (TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8;
+    static constexpr int WARPS = (HALO == 1) ? 5 : SF_FAST_WARPS;   // warps per CTA; SF_FAST_MIN_CTAS CTAs per SM
+    static_assert(WARP_BYTES % 16 == 0 && (TILE_DOUBLES + SF_EXTRA) % 2 == 0, "128-bit shared-memory operands");
+    static_assert(SF_FAST_MIN_CTAS * WARPS * WARP_BYTES <= 227 * 1024, "shared memory of an SM");
+};
 
 __device__ __forceinline__ double sf_vacant() { return __longlong_as_double(0x7ff8000000000001LL); }
 
@@ -265,14 +276,15 @@ __device__ __forceinline__ void sf_prefetch_batch(const FastPtrs &fs, double *st
 // ---------------------------------------------------------------------------------------------------------
 // tiled kernel: persistent warps pull work items from a queue; every lane carries SF_PPT particles per batch
 // ---------------------------------------------------------------------------------------------------------
-template <bool SEG>
-__global__ void __launch_bounds__(SF_FAST_WARPS * 32, SF_FAST_MIN_CTAS)
+template <bool SEG, int HALO> // HALO: cells kept around the 8 x 8 tile in the warp-private accumulation tile (1: 15 warps / SM, 2: 12)
+__global__ void __launch_bounds__(FastGeom<HALO>::WARPS * 32, SF_FAST_MIN_CTAS)
 k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restrict__ ga)
 {
+    constexpr int NT = FastGeom<HALO>::NT, TD = FastGeom<HALO>::TILE_DOUBLES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double *tile = reinterpret_cast<double *>(smem_raw + (size_t)wid * SF_WARP_SMEM_BYTES);
-    double *sW = tile + SF_TILE_DOUBLES + SF_EXTRA; // tile, extra sums of the warp (energy, fallback N/P/E), then [4][SF_WROW] weights, [9][SF_WROW] values
+    double *tile = reinterpret_cast<double *>(smem_raw + (size_t)wid * FastGeom<HALO>::WARP_BYTES);
+    double *sW = tile + TD + SF_EXTRA; // tile, extra sums of the warp (energy, fallback N/P/E), then [4][SF_WROW] weights, [9][SF_WROW] values
     double *sV = sW + 4 * SF_WROW;
     // weight and value of the counting lanes (f == 7): a row of ones placed on the bank group of value row 7 (rows are 272 bytes apart, i.e. 4 banks
     // further per row: the eight lanes of a quarter warp then read eight different bank groups and the 128-bit operand loads stay conflict free)
@@ -291,7 +303,7 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     const size_t plane = (size_t)m.ni * m.nj;
     const bool simple_ok = !m.has_b && a.dt > 0 && (SEG || !m.any_seg);
 
-    for (int k = lane; k < SF_TILE_DOUBLES + SF_EXTRA; k += 32) tile[k] = 0.0;
+    for (int k = lane; k < TD + SF_EXTRA; k += 32) tile[k] = 0.0;
     if (lane == 0) sKey[32 * SF_PPT] = 0;
     for (int k = lane; k < 32 * SF_PPT; k += 32) sOnes[k] = sOnesW[k] = 1.0;
     __syncwarp();
@@ -299,11 +311,11 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
     // role of this lane in the reduction: node n (w00,w10,w11,w01) x field f (7 moments; f == 7: n == 0 counts the
     // particles of the cell (mpc), n == 1 sums mpw*|vel| of the whole work item (energy sum, KM:412))
     const int rn = lane >> 3, rf = lane & 7;
-    const int noff = (rn == 0) ? 0 : (rn == 1) ? SF_NT : (rn == 2) ? SF_NT + 1 : 1;
+    const int noff = (rn == 0) ? 0 : (rn == 1) ? NT : (rn == 2) ? NT + 1 : 1;
     const double *rw = (rf == 7) ? sOnesW : (sW + rn * SF_WROW); // f == 7 lanes: weight 1.0
     const double *rv = (rf == 7 && rn != 1) ? sOnes : (sV + rf * SF_WROW); // row 7 of sV = mpw*|vel|
     const bool renergy = rf == 7 && rn == 1;
-    double *racc = renergy ? (tile + SF_TILE_DOUBLES) : (tile + rf * (SF_NT * SF_NT) + ((rf == 7) ? 0 : noff));
+    double *racc = renergy ? (tile + TD) : (tile + rf * (NT * NT) + ((rf == 7) ? 0 : noff));
     const int rmul = renergy ? 0 : 1;
     const bool rflush = (rf < 7) || (rn <= 1);
 
@@ -314,14 +326,14 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= n_items) break;
         const WorkItem wi = a.items[it];
-        const int ti0 = (wi.tile / a.ntj) * SF_TILE - SF_HALO; // first node row / column held by the tile
-        const int tj0 = (wi.tile % a.ntj) * SF_TILE - SF_HALO;
+        const int ti0 = (wi.tile / a.ntj) * SF_TILE - HALO; // first node row / column held by the tile
+        const int tj0 = (wi.tile % a.ntj) * SF_TILE - HALO;
 #if SF_ETILE
         // E field of the tile's neighbourhood (F2D:300-350 reads four nodes per field and particle): staged once per work item
         ETile etile;
         etile.e = sE;
-        etile.i0 = ti0 + SF_HALO - SF_EHALO;
-        etile.j0 = tj0 + SF_HALO - SF_EHALO;
+        etile.i0 = ti0 + HALO - SF_EHALO;
+        etile.j0 = tj0 + HALO - SF_EHALO;
         __syncwarp();
         for (int k = lane; k < SF_ENT * SF_ENT; k += 32) {
             const int gi = etile.i0 + k / SF_ENT, gj = etile.j0 + k % SF_ENT;
@@ -432,8 +444,8 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                 if (deposit) {
                     const bool in = sf_deposit_weights(m, p[j].li, p[j].lj, dw[j]);
                     const int li_ = dw[j].i - ti0, lj_ = dw[j].j - tj0;
-                    if (in && li_ >= 0 && lj_ >= 0 && li_ < SF_NT - 1 && lj_ < SF_NT - 1) {
-                        key[j] = li_ * SF_NT + lj_;
+                    if (in && li_ >= 0 && lj_ >= 0 && li_ < NT - 1 && lj_ < NT - 1) {
+                        key[j] = li_ * NT + lj_;
                     } else { // pushed and stored, but its deposit misses the warp tile: left to k_fast_deferred
                         const unsigned long long s_ = atomicAdd(&a.c->n_defer[a.mesh_id], 1ULL);
                         if (s_ < a.defer_cap) a.defer[s_] = (unsigned)q | SF_DEFER_DEPOSIT_ONLY;
@@ -536,11 +548,11 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
         // ---- add the warp tile to the global deposit and clear it; the mover sums N, Px, Py, Pz (KM:406-411) of the
         //      particles that went through the tile are the tile totals of Den, U, V, W (bilinear weights sum to 1) ----
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        for (int k = lane; k < SF_TILE_DOUBLES; k += 32) {
+        for (int k = lane; k < TD; k += 32) {
             const double v = tile[k];
             if (v != 0.0) {
-                const int f = k / (SF_NT * SF_NT), r = k % (SF_NT * SF_NT);
-                const int gi = ti0 + r / SF_NT, gj = tj0 + r % SF_NT;
+                const int f = k / (NT * NT), r = k % (NT * NT);
+                const int gi = ti0 + r / NT, gj = tj0 + r % NT;
                 if (gi >= 0 && gj >= 0 && gi < m.ni && gj < m.nj) atomicAdd(a.dep + f * plane + (size_t)gi * m.nj + gj, v);
                 tile[k] = 0.0;
                 if (f == 0) s0 += v;
@@ -551,7 +563,7 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
         }
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
         if (lane == 0) {
-            double *ex = tile + SF_TILE_DOUBLES;
+            double *ex = tile + TD;
             if (s0 != 0 || ex[0] != 0) {
                 atomicAdd(&a.c->sums[0], s0); atomicAdd(&a.c->sums[1], s1); atomicAdd(&a.c->sums[2], s2);
                 atomicAdd(&a.c->sums[3], s3); atomicAdd(&a.c->sums[4], ex[0]);

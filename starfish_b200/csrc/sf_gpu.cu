@@ -191,7 +191,9 @@ struct sfgpu_ctx {
     int last_launches = 0;
     bool timing_valid = false;
     int sort_every = 3;      // steps between cell sorts of the fast store (2..5 give the same step time on config B; 3 keeps the kernel on a fresher order)
-    int fast_grid = 0;       // CTAs of the tiled kernel (persistent)
+    int fast_grid[3] = {0, 0, 0}; // CTAs of the tiled kernel (persistent), by halo width
+    int fast_halo = 1;       // halo of the accumulation tile the next tiled step runs with (FastGeom): 1 = 15 warps / SM, 2 = 12 warps / SM
+    bool fast_halo_auto = true; // a step that left more than 0.5 % of its deposits to k_fast_deferred switches the context to the wide halo
     int path = 0;            // default step kernel: 0 = tiled in-place step + periodic sort (sf_fast.cuh), 1 = streaming step (sf_stream.cuh)
     int stream_grid = 0;     // CTAs of the streaming kernel (persistent)
     bool hybrid = false;     // tiled path: run the step in which a re-sort is due with the streaming kernel instead of sorting separately
@@ -600,14 +602,22 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         if (const char *e = getenv("SFGPU_SORT_GATHER")) ctx->sort_gather = atoi(e) != 0;
         if (const char *e = getenv("SFGPU_SORT_PREDICT")) ctx->sort_predict = atof(e);
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
-        CU(cudaFuncSetAttribute(k_fast_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
-        CU(cudaFuncSetAttribute(k_fast_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
-        int nsm = 0, per_sm = 0;
+        CU(cudaFuncSetAttribute(k_fast_step<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FastGeom<1>::WARPS * FastGeom<1>::WARP_BYTES));
+        CU(cudaFuncSetAttribute(k_fast_step<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FastGeom<1>::WARPS * FastGeom<1>::WARP_BYTES));
+        CU(cudaFuncSetAttribute(k_fast_step<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FastGeom<2>::WARPS * FastGeom<2>::WARP_BYTES));
+        CU(cudaFuncSetAttribute(k_fast_step<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FastGeom<2>::WARPS * FastGeom<2>::WARP_BYTES));
+        int nsm = 0, per_sm[3] = {0, 0, 0};
         CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_step<false>, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES));
-        if (per_sm < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
-        ctx->fast_grid = nsm * per_sm;
-        if (const char *e = getenv("SFGPU_FAST_GRID")) ctx->fast_grid = atoi(e) > 0 ? atoi(e) : ctx->fast_grid; // occupancy experiments
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fast_step<false, 1>, FastGeom<1>::WARPS * 32, FastGeom<1>::WARPS * FastGeom<1>::WARP_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_fast_step<false, 2>, FastGeom<2>::WARPS * 32, FastGeom<2>::WARPS * FastGeom<2>::WARP_BYTES));
+        if (per_sm[1] < 1 || per_sm[2] < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
+        for (int h = 1; h <= 2; h++) {
+            ctx->fast_grid[h] = nsm * per_sm[h];
+            if (const char *e = getenv("SFGPU_FAST_GRID")) ctx->fast_grid[h] = atoi(e) > 0 ? atoi(e) : ctx->fast_grid[h]; // occupancy experiments
+        }
+        if (const char *e = getenv("SFGPU_HALO")) { // 1 | 2: fixed; anything else: start narrow, widen when deposits miss the tile
+            if (atoi(e) == 1 || atoi(e) == 2) { ctx->fast_halo = atoi(e); ctx->fast_halo_auto = false; }
+        }
         CU(cudaFuncSetAttribute(k_stream_step, cudaFuncAttributeMaxDynamicSharedMemorySize, SFS_SMEM_BYTES));
         int per_sm_s = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_stream_step, SFS_THREADS, SFS_SMEM_BYTES));
@@ -618,7 +628,10 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         ctx->stream_check = getenv("SFGPU_STREAM_CHECK") != nullptr;
         CU(cudaMalloc(&ctx->d_bad, sizeof(unsigned long long)));
         if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_stream_step %d CTAs/SM x %d threads, %d B dynamic smem per CTA, grid %d, path %s\n", per_sm_s, SFS_THREADS, (int)SFS_SMEM_BYTES, ctx->stream_grid, ctx->path ? "stream" : "tiled");
-        if (getenv("SFGPU_DEBUG")) fprintf(stderr, "sfgpu: k_fast_step %d CTAs/SM x %d warps, %d B dynamic smem per CTA, grid %d\n", per_sm, SF_FAST_WARPS, (int)(SF_FAST_WARPS * SF_WARP_SMEM_BYTES), ctx->fast_grid);
+        if (getenv("SFGPU_DEBUG"))
+            fprintf(stderr, "sfgpu: k_fast_step halo 1: %d CTAs/SM x %d warps, %d B dynamic smem per CTA, grid %d; halo 2: %d CTAs/SM x %d warps, %d B, grid %d; halo %d%s\n",
+                    per_sm[1], FastGeom<1>::WARPS, FastGeom<1>::WARPS * FastGeom<1>::WARP_BYTES, ctx->fast_grid[1], per_sm[2], FastGeom<2>::WARPS,
+                    FastGeom<2>::WARPS * FastGeom<2>::WARP_BYTES, ctx->fast_grid[2], ctx->fast_halo, ctx->fast_halo_auto ? " (auto)" : "");
         // bit-parity self test: a*b+c must round twice
         double *d = nullptr, h = 0;
         CU(cudaMalloc(&d, sizeof(double)));
@@ -1480,8 +1493,15 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                     f.defer_cap = f.cap;
                     a.defer = f.defer; a.defer_cap = (unsigned)(f.defer_cap > 0x7fffffff ? 0x7fffffff : f.defer_cap);
                 }
-                if (a.m.any_seg) k_fast_step<true><<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
-                else k_fast_step<false><<<ctx->fast_grid, SF_FAST_WARPS * 32, SF_FAST_WARPS * SF_WARP_SMEM_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                if (ctx->fast_halo == 1) {
+                    typedef FastGeom<1> G;
+                    if (a.m.any_seg) k_fast_step<true, 1><<<ctx->fast_grid[1], G::WARPS * 32, G::WARPS * G::WARP_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                    else k_fast_step<false, 1><<<ctx->fast_grid[1], G::WARPS * 32, G::WARPS * G::WARP_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                } else {
+                    typedef FastGeom<2> G;
+                    if (a.m.any_seg) k_fast_step<true, 2><<<ctx->fast_grid[2], G::WARPS * 32, G::WARPS * G::WARP_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                    else k_fast_step<false, 2><<<ctx->fast_grid[2], G::WARPS * 32, G::WARPS * G::WARP_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                }
                 CU(cudaGetLastError());
                 k_fast_deferred<<<148 * 4, 256, 0, ctx->stream>>>(a); // boundary crossers, tile misses, removals: a fraction of a percent
                 CU(cudaGetLastError());
@@ -1596,6 +1616,11 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
         return fail(ctx, SFGPU_EOVERFLOW, "%lld surface hits in one step, the list holds %zu", (long long)s.n_hits, ctx->hit_cap);
     s.slow_n = (int64_t)ctx->h_cnt->n_slow;
     ctx->last_fallback = ctx->h_cnt->n_fallback;
+    if (ctx->fast_halo_auto && ctx->fast_halo == 1) { // deposits further than one cell from the sorted cell: this population wants the wide tile
+        int64_t nfast = 0;
+        for (int m = 0; m < nmesh; m++) nfast += s.pops[m].fast.n;
+        if ((int64_t)ctx->last_fallback * 200 > nfast) ctx->fast_halo = 2;
+    }
     // too many particles drifted out of their warp tiles: sort before the next step instead of waiting for the interval
     ctx->force_sort = !untiled && !stream && (int64_t)ctx->last_fallback * 64 > n_total;
     ctx->last_kernel = untiled ? 2 : (stream ? 1 : 0);
@@ -2084,6 +2109,23 @@ extern "C" int sfgpu_set_sort_interval(sfgpu_ctx *ctx, int32_t steps)
     CHECK_CTX();
     if (steps < 1) return fail(ctx, SFGPU_EINVAL, "sort interval must be >= 1");
     ctx->sort_every = steps;
+    return 0;
+}
+
+extern "C" int sfgpu_set_tile_halo(sfgpu_ctx *ctx, int32_t halo)
+{
+    CHECK_CTX();
+    if (halo < 0 || halo > 2) return fail(ctx, SFGPU_EINVAL, "tile halo must be 0 (automatic), 1 or 2");
+    ctx->fast_halo_auto = halo == 0;
+    ctx->fast_halo = halo == 0 ? 1 : halo;
+    return 0;
+}
+
+extern "C" int sfgpu_get_tile_halo(sfgpu_ctx *ctx, int32_t *halo, int32_t *automatic)
+{
+    CHECK_CTX();
+    if (halo) *halo = ctx->fast_halo;
+    if (automatic) *automatic = ctx->fast_halo_auto ? 1 : 0;
     return 0;
 }
 

@@ -475,6 +475,16 @@ class KineticMaterial:
     def setSortInterval(self, steps):
         self._check(self.lib.sfgpu_set_sort_interval(self._ctx, int(steps)))
 
+    def setTileHalo(self, halo):
+        """0: automatic (narrow tile until deposits miss it), 1 / 2: fixed halo of the tiled kernel's accumulation tile (sfgpu_set_tile_halo)."""
+        self._check(self.lib.sfgpu_set_tile_halo(self._ctx, int(halo)))
+
+    def tileHalo(self):
+        """(halo the next tiled step runs with, automatic?)"""
+        h, a = C.c_int32(), C.c_int32()
+        self._check(self.lib.sfgpu_get_tile_halo(self._ctx, C.byref(h), C.byref(a)))
+        return h.value, bool(a.value)
+
     def timerStart(self):
         self._check(self.lib.sfgpu_timer_start(self._ctx))
 

@@ -353,6 +353,32 @@ def test_sort_interval_does_not_change_results(every, flags):
         compare_fields(km, ok)
 
 
+@pytest.mark.parametrize("halo,vth", [(1, 0.15), (1, 0.9), (2, 0.15), (2, 0.9), (0, 0.15), (0, 0.9)])
+def test_tile_halo_is_a_speed_choice_only(halo, vth):
+    """sfgpu_set_tile_halo: deposits that miss the narrow accumulation tile are made by the deferred kernel -- same results for either
+    halo and any thermal spread; the automatic mode widens the tile for good once a step leaves > 0.5 % of its deposits to it."""
+    m = S.make_mesh(90, 75, DomainType.XY, 1e-3, "periodic")
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 11, vth_cells=vth, kick_frac=0.1)
+    arr = wl.particles(0, 60000)
+    km, ok = make_pair([m], wl, [arr], _lib.STEP_INPLACE)
+    with km:
+        km.setTileHalo(halo)
+        assert km.tileHalo() == (halo if halo else 1, halo == 0)
+        missed = 0
+        for _ in range(7):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            missed = max(missed, km.lastStepFallback())
+            compare_state(km, ok)
+            compare_fields(km, ok)
+        if halo:
+            assert km.tileHalo() == (halo, False)
+        elif vth > 0.5:
+            assert km.tileHalo() == (2, True) and missed * 200 > 60000
+        else:
+            assert km.tileHalo() == (1, True) and missed * 200 <= 60000
+
+
 @pytest.mark.parametrize("cold,v_drift", [(False, 7000.0), (True, -7000.0)])
 @pytest.mark.parametrize("flags", PATHS)
 def test_device_side_uniform_source(flags, cold, v_drift):
