@@ -248,9 +248,9 @@ int sfgpu_cell_lists(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t *cell_
 /* sfgpu_step re-sorts the store by cell every `steps` steps (default 3, env SFGPU_SORT_EVERY).
  * KineticMaterial.mergeParticles (KM:1008-1143, particle_merge_skip > 0) is NOT offered: materials that merge keep type="kinetic". */
 int sfgpu_set_sort_interval(sfgpu_ctx *ctx, int32_t steps);
-/* halo of the tiled kernel's warp-private accumulation tile, in cells around the 8 x 8 tile a work item covers.  1: the deposits of a particle must land
- * within one cell of the cell it was sorted into (true while |v| dt < ~0.3 cells; the sort key is the predicted cell) -- smaller tile, 15 warps per SM;
- * 2: two cells, 12 warps per SM.  A deposit outside the tile is still made (k_fast_deferred, global atomics), only slower: results never depend on it.
+/* halo of the tiled kernel's warp-private accumulation tile, in cells around the 4 x 4-cell tile a work item covers.  1: the deposits of a particle must land
+ * within one cell of the cell it was sorted into (true while |v| dt < ~0.3 cells; the sort key is the predicted cell) -- smaller tile, cheaper flush;
+ * 2: two cells.  A deposit outside the tile is still made (k_fast_deferred, global atomics), only slower: results never depend on it.
  * 0 (default, env SFGPU_HALO): start with 1 and switch to 2 for good once a step leaves more than 0.5 % of its deposits to the deferred kernel. */
 int sfgpu_set_tile_halo(sfgpu_ctx *ctx, int32_t halo);
 int sfgpu_get_tile_halo(sfgpu_ctx *ctx, int32_t *halo, int32_t *automatic);

@@ -1,6 +1,6 @@
 // sf_fast.cuh -- the B200 fast path: fused gather / push / locate / deposit over the cell-sorted fast store.
 //
-// Layout (DESIGN.md "Data layout"): structure of arrays x,y,z,u,v,w,mpw (+tag), sorted by cell inside 8x8-cell
+// Layout (DESIGN.md "Data layout"): structure of arrays x,y,z,u,v,w,mpw (+tag), sorted by cell inside SF_TILE x SF_TILE-cell (4 x 4)
 // tiles.  A warp owns one work item = a run of <= SF_ITEM_MAX particles of one tile.  Per 32-particle batch:
 //   1. coalesced loads of the 7 state doubles, lc = XtoL(pos) recomputed (true division, bit exact),
 //   2. sf_move(): E/B gather (L1-cached global loads: cell-sorted lanes hit the same 4 nodes), kick, substeps,
@@ -20,13 +20,16 @@
 #include "sf_generic.cuh"
 
 #ifndef SF_FAST_WARPS
-#define SF_FAST_WARPS 4 // warps per CTA of the tiled kernel (3 CTAs of 4 warps x 17.4 KB fit the 227 KB of shared memory: 12 warps / SM)
+#define SF_FAST_WARPS 5 // warps per CTA of the tiled kernel, two-cell halo (4 CTAs of 5 warps x 10.5 KB of shared memory: 20 warps / SM, 96 registers)
 #endif
 #ifndef SF_PPT
 #define SF_PPT 1        // particles per lane and batch (independent instruction streams hide FP64 latency)
 #endif
+#ifndef SF_FAST_WARPS_H1
+#define SF_FAST_WARPS_H1 5 // ... and of its one-cell-halo instance (5 warps x 8.5 KB; 20 warps / SM is the register limit either way)
+#endif
 #ifndef SF_FAST_MIN_CTAS
-#define SF_FAST_MIN_CTAS 3
+#define SF_FAST_MIN_CTAS 4
 #endif
 #define SF_WROW (32 * SF_PPT + 2) // padded row of the per-warp scratch (doubles): conflict-free 128-bit reads
 #define SF_TILE_DOUBLES (SFGPU_NFIELDS * SF_NT * SF_NT)
@@ -51,7 +54,7 @@ template <int HALO> struct FastGeom {
     static constexpr int NT = SF_TILE + 2 * HALO + 1;              // nodes per edge of the accumulation tile
     static constexpr int TILE_DOUBLES = SFGPU_NFIELDS * NT * NT;
     static constexpr int WARP_BYTES = (TILE_DOUBLES + SF_SCRATCH_DOUBLES) * 8;
-    static constexpr int WARPS = (HALO == 1) ? 5 : SF_FAST_WARPS;   // warps per CTA; SF_FAST_MIN_CTAS CTAs per SM
+    static constexpr int WARPS = (HALO == 1) ? SF_FAST_WARPS_H1 : SF_FAST_WARPS;   // warps per CTA; SF_FAST_MIN_CTAS CTAs per SM
     static_assert(WARP_BYTES % 16 == 0 && (TILE_DOUBLES + SF_EXTRA) % 2 == 0, "128-bit shared-memory operands");
     static_assert(SF_FAST_MIN_CTAS * WARPS * WARP_BYTES <= 227 * 1024, "shared memory of an SM");
 };
@@ -276,7 +279,7 @@ __device__ __forceinline__ void sf_prefetch_batch(const FastPtrs &fs, double *st
 // ---------------------------------------------------------------------------------------------------------
 // tiled kernel: persistent warps pull work items from a queue; every lane carries SF_PPT particles per batch
 // ---------------------------------------------------------------------------------------------------------
-template <bool SEG, int HALO> // HALO: cells kept around the 8 x 8 tile in the warp-private accumulation tile (1: 15 warps / SM, 2: 12)
+template <bool SEG, int HALO> // HALO: cells kept around the SF_TILE x SF_TILE tile in the warp-private accumulation tile
 __global__ void __launch_bounds__(FastGeom<HALO>::WARPS * 32, SF_FAST_MIN_CTAS)
 k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restrict__ ga)
 {
@@ -783,7 +786,7 @@ k_sort_gather(FastPtrs in, FastPtrs out, unsigned long long n_out, const unsigne
     }
 }
 
-// work items: each tile's run [offs[tile*64], offs[(tile+1)*64]) cut into pieces of <= SF_ITEM_MAX particles
+// work items: each tile's run [offs[tile*SF_TILE^2], offs[(tile+1)*SF_TILE^2]) cut into pieces of <= SF_ITEM_MAX particles
 __global__ void k_build_items(const unsigned *__restrict__ offs, int n_tiles, WorkItem *__restrict__ items, unsigned *__restrict__ n_items,
                               unsigned max_items)
 {

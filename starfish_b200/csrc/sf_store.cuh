@@ -27,7 +27,8 @@ struct WorkItem {
 };
 
 #ifndef SF_TILE
-#define SF_TILE 8       // cells per tile edge
+#define SF_TILE 4       // cells per tile edge.  Measured on config B (kernel ms): 8 -> 0.68 (15 warps / SM fit), 6 -> 0.64 (18), 4 -> 0.62 (20, the
+                        // register limit), 2 -> 0.91 (the per-item tile flush dominates); 5 makes the node rows 8 doubles long: bank conflicts, 0.78
 #endif
 #ifndef SF_HALO
 #define SF_HALO 2       // extra cells kept around the tile in the warp-private accumulation tile

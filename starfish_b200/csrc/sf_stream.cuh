@@ -2,7 +2,7 @@
 //
 // One launch does the move (KM:298-422), the deposit (KM:168-197, :1570-1595) and the cell sort + compaction (K3):
 //   * the input store is cell-sorted as of the PREVIOUS step; a CTA takes a chunk of <= SFS_CHUNK particles of one
-//     8x8-cell tile, fetched by TMA bulk copies (cp.async.bulk + mbarrier) one chunk ahead of the arithmetic;
+//     SF_TILE x SF_TILE-cell tile, fetched by TMA bulk copies (cp.async.bulk + mbarrier) one chunk ahead of the arithmetic;
 //   * phase 1 (thread per particle): lc = XtoL(pos), E gather, kick, move, locate, boundaries -- the same expressions as
 //     sf_move(), so results are bit-identical to the generic kernel;
 //   * the particle is written OUT OF PLACE into the second slab at the segment of the cell it occupied BEFORE this push
@@ -621,7 +621,7 @@ k_stream_step(const __grid_constant__ StreamArgs a, const FastStepArgs *__restri
 }
 
 
-// chunks of the streaming kernel: each tile's run [offs[tile*64], offs[(tile+1)*64]) cut into <= SFS_CHUNK particles
+// chunks of the streaming kernel: each tile's run [offs[tile*SF_TILE^2], offs[(tile+1)*SF_TILE^2]) cut into <= SFS_CHUNK particles
 __global__ void k_build_chunks(const unsigned *__restrict__ offs, int n_tiles, WorkItem *__restrict__ items, unsigned *__restrict__ n_items,
                                unsigned max_items, unsigned chunk)
 {
