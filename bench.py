@@ -118,10 +118,33 @@ def run_reference(args, rank, world, wname):
         "e2e": {"value": value, "unit": "pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE line, the result: file descriptor 1 is pointed at stderr for everything else (NCCL prints its version banner on stdout
+    when NCCL_DEBUG is set in the environment, torch.distributed warns there too), the result line goes to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 340 for config B, 40 for the 2^30-particle config E)")
@@ -365,7 +388,7 @@ def main():
             v, t = cpu_reference_run(wl, n_sample, 3, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": "pushes/s", "cores": threads, "kind": "port",
                                     "sample": f"{n_sample} particles x 3 steps of the same workload, {threads} mover threads + serial deposit"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     km.close()
     if world > 1:
         dist.destroy_process_group()
