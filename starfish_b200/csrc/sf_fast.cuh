@@ -88,8 +88,13 @@ struct FastStepArgs {
     StepCounters *c;
     unsigned *defer;          // slots k_fast_step leaves to k_fast_deferred: bit 31 clear = re-run the particle through sf_move() from its
     unsigned defer_cap;       // stored state; bit 31 set = already pushed and stored, only its deposit (it left the warp tile) is due
+    // the step before a cell sort does the sort's counting pass on the way (k_fast_step<.., PREP = true>): key of the cell each particle is predicted to
+    // occupy sort_dt from now, its rank inside that cell, and the histogram -- k_sort_count's outputs without its pass over the particles
+    unsigned *sort_keys, *sort_ranks, *sort_hist;
+    double sort_dt;
 };
 #define SF_DEFER_DEPOSIT_ONLY 0x80000000u
+#define SF_KEY_NONE 0xffffffffu // sort key of a vacant slot
 
 // what happens to a particle of the fast store after sf_move(); shared by the tiled and the tail kernel
 __device__ __forceinline__ void fast_epilogue(const FastStepArgs &a, const MeshDev &m, size_t q, int st, bool exact,
@@ -279,7 +284,7 @@ __device__ __forceinline__ void sf_prefetch_batch(const FastPtrs &fs, double *st
 // ---------------------------------------------------------------------------------------------------------
 // tiled kernel: persistent warps pull work items from a queue; every lane carries SF_PPT particles per batch
 // ---------------------------------------------------------------------------------------------------------
-template <bool SEG, int HALO> // HALO: cells kept around the SF_TILE x SF_TILE tile in the warp-private accumulation tile
+template <bool SEG, int HALO, bool PREP> // PREP: also writes the counting pass of the cell sort that follows this step (FastStepArgs::sort_*); HALO: cells kept around the SF_TILE x SF_TILE tile in the warp-private accumulation tile
 __global__ void __launch_bounds__(FastGeom<HALO>::WARPS * 32, SF_FAST_MIN_CTAS)
 k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restrict__ ga)
 {
@@ -453,6 +458,29 @@ k_fast_step(const __grid_constant__ FastStepArgs a, const FastStepArgs *__restri
                         const unsigned long long s_ = atomicAdd(&a.c->n_defer[a.mesh_id], 1ULL);
                         if (s_ < a.defer_cap) a.defer[s_] = (unsigned)q | SF_DEFER_DEPOSIT_ONLY;
                     }
+                }
+            }
+            if (PREP) { // counting pass of the next sort: same key arithmetic as k_sort_count, on the state this step just stored
+#pragma unroll
+                for (int j = 0; j < SF_PPT; j++) {
+                    const int o = b + j * 32 + lane;
+                    const size_t q = (size_t)wi.begin + o;
+                    unsigned skey = SF_KEY_NONE;
+                    if (done[j]) {
+                        double xs = p[j].x, ys = p[j].y;
+                        if (a.sort_dt != 0) { xs += p[j].u * a.sort_dt; ys += p[j].v * a.sort_dt; }
+                        skey = sf_cell_key(m, sf_div_exact(xs - m.x0, m.dhx, m.rdhx, m.fastdiv), sf_div_exact(ys - m.y0, m.dhy, m.rdhy, m.fastdiv), a.ntj);
+                    }
+                    const unsigned act = __ballot_sync(0xffffffffu, skey != SF_KEY_NONE);
+                    if (skey != SF_KEY_NONE) {
+                        const unsigned sg = __match_any_sync(act, skey);
+                        const int sl = __ffs(sg) - 1;
+                        unsigned sbase = 0;
+                        if (lane == sl) sbase = atomicAdd(&a.sort_hist[skey], (unsigned)__popc(sg));
+                        sbase = __shfl_sync(sg, sbase, sl);
+                        a.sort_ranks[q] = sbase + __popc(sg & ((1u << lane) - 1u));
+                    }
+                    if (o < wi.count) a.sort_keys[q] = skey; // vacant slots and deferred particles: none (k_sort_count_fix keys the deferred ones once they are finished)
                 }
             }
             // ---- group the 32 particles of each set by cell inside the warp: row = position in cell order ----
@@ -666,7 +694,6 @@ k_fast_deferred(const __grid_constant__ FastStepArgs a)
 // ---------------------------------------------------------------------------------------------------------
 // cell sort + compaction (K3): counting sort by cell key, out of place
 // ---------------------------------------------------------------------------------------------------------
-#define SF_KEY_NONE 0xffffffffu
 
 // pass 1: key and rank of every particle; hist[key] = particles per cell.  Vacant slots get SF_KEY_NONE.
 // Four particles per thread (blockDim apart, so every load stays coalesced): the twelve loads and then the four
@@ -716,6 +743,35 @@ k_sort_count(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs fs, unsig
         }
         if (q < n) keys[q] = key[k];
     }
+}
+
+// pass 1 for the particles k_fast_step<.., PREP> could not key itself: the ones it left to k_fast_deferred (keyed from the state that kernel stored, or
+// vacant by now) and the unsorted tail behind the sorted prefix (injection, records that became normal particles again).  Same outputs as k_sort_count.
+__global__ void __launch_bounds__(256)
+k_sort_count_fix(const MeshDev *__restrict__ meshes, int mesh_id, FastPtrs fs, const unsigned *__restrict__ defer, unsigned long long n_defer,
+                 unsigned long long tail_first, unsigned long long n, int ntj, unsigned *__restrict__ hist, unsigned *__restrict__ keys,
+                 unsigned *__restrict__ ranks, double dt_pred)
+{
+    const MeshDev m = meshes[mesh_id];
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long q;
+    if (t < n_defer) {
+        const unsigned e = defer[t];
+        if (e & SF_DEFER_DEPOSIT_ONLY) return; // pushed, stored and keyed by the step kernel; only its deposit was deferred
+        q = e;
+    } else {
+        q = tail_first + (t - n_defer);
+        if (q >= n) return;
+    }
+    const double mpw = fs.mpw[q];
+    unsigned key = SF_KEY_NONE;
+    if (mpw == mpw) {
+        double x = fs.x[q], y = fs.y[q];
+        if (dt_pred != 0) { x += fs.u[q] * dt_pred; y += fs.v[q] * dt_pred; }
+        key = sf_cell_key(m, sf_div_exact(x - m.x0, m.dhx, m.rdhx, m.fastdiv), sf_div_exact(y - m.y0, m.dhy, m.rdhy, m.fastdiv), ntj);
+        ranks[q] = atomicAdd(&hist[key], 1u);
+    }
+    keys[q] = key;
 }
 
 // pass 3: scatter to the sorted position

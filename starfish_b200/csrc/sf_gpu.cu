@@ -110,6 +110,11 @@ struct FastStore { // cell-sorted SoA store of the normal particles of one speci
     int steps_since_sort = 0;
     unsigned *keys = nullptr, *ranks = nullptr, *inv = nullptr; // per particle, sort scratch (key, rank in its cell, inverse permutation)
     int64_t kr_cap = 0;
+    // counting pass of the next sort done by the last tiled step (k_fast_step<.., PREP>): keys / ranks / hist describe p[0, keys_n_sorted) except the
+    // keys_ndefer slots on the deferred list; valid until anything else edits the store in place
+    bool keys_ok = false;
+    double keys_pred = 0.0;
+    int64_t keys_n_sorted = 0, keys_ndefer = 0;
     unsigned *hist = nullptr, *offs = nullptr;  // per cell key (+1): live particles per key; segment offsets of the sorted prefix
     // streaming step (sf_stream.cuh): histogram accumulated for the next launch, output segment offsets, output cursors
     unsigned *hist_next = nullptr, *offs_out = nullptr, *cursor = nullptr;
@@ -193,6 +198,8 @@ struct sfgpu_ctx {
     int sort_every = 3;      // steps between cell sorts of the fast store (2..5 give the same step time on config B; 3 keeps the kernel on a fresher order)
     int fast_grid[3] = {0, 0, 0}; // CTAs of the tiled kernel (persistent), by halo width
     int fast_halo = 1;       // halo of the accumulation tile the next tiled step runs with (FastGeom): 1 = 15 warps / SM, 2 = 12 warps / SM
+    bool fuse_count = false; // SFGPU_FUSE_COUNT=1: the tiled step before a cell sort also does the sort's counting pass (k_fast_step<.., PREP>).  Parity green; measured
+                             // on config B: step 0.872 vs 0.887 ms, but that launch costs +0.10-0.17 ms against 0.16 ms for k_sort_count, config C 6.21 vs 6.16 ms: not default
     bool fast_halo_auto = true; // a step that left more than 0.5 % of its deposits to k_fast_deferred switches the context to the wide halo
     int path = 0;            // default step kernel: 0 = tiled in-place step + periodic sort (sf_fast.cuh), 1 = streaming step (sf_stream.cuh)
     int stream_grid = 0;     // CTAs of the streaming kernel (persistent)
@@ -329,6 +336,26 @@ static int fast_init_geometry(sfgpu_ctx *ctx, FastStore &f, const MeshDev &m)
     return 0;
 }
 
+// per-particle sort scratch (key, rank, inverse permutation); re-allocating it drops a counting pass a step may have left there
+static int fast_reserve_keys(sfgpu_ctx *ctx, FastStore &f)
+{
+    if (f.kr_cap >= f.n && f.kr_cap > 0) return 0;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (f.keys) CU(cudaFree(f.keys));
+    if (f.ranks) CU(cudaFree(f.ranks));
+    if (f.inv) CU(cudaFree(f.inv));
+    f.keys = f.ranks = f.inv = nullptr; f.kr_cap = 0;
+    f.keys_ok = false;
+    CU(cudaMalloc(&f.keys, (size_t)f.cap * sizeof(unsigned)));
+    CU(cudaMalloc(&f.ranks, (size_t)f.cap * sizeof(unsigned)));
+    CU(cudaMalloc(&f.inv, (size_t)f.cap * sizeof(unsigned)));
+    f.kr_cap = f.cap;
+    return 0;
+}
+
+// steps ahead the sort key looks (see k_sort_count)
+static double sort_horizon(const sfgpu_ctx *ctx) { return ctx->sort_predict >= 0 ? ctx->sort_predict : std::min(2.0, 0.5 * (ctx->sort_every + 1)); }
+
 // K3: counting sort of the fast store by cell key (tile-major) + compaction of vacant slots, out of place;
 // rebuilds the work items of the tiled kernel.  sortParticlesToCells (KM:1150-1179) is the closest reference
 // member: order only, no result changes beyond summation order.
@@ -336,6 +363,7 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f, double dt_pred =
 {
     f.steps_since_sort = 0;
     if (f.n == 0) {
+        f.keys_ok = false;
         f.n_sorted = 0; f.n_items = 0; f.dirty = false;
         CU(cudaMemsetAsync(f.d_nitems, 0, sizeof(unsigned), ctx->stream));
         CU(cudaMemsetAsync(f.hist, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
@@ -351,16 +379,9 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f, double dt_pred =
         f.alt_cap = f.cap;
         fast_bind(f.alt, f.alt_slab, f.alt_cap);
     }
-    if (f.kr_cap < f.n) {
-        if (f.keys) CU(cudaFree(f.keys));
-        if (f.ranks) CU(cudaFree(f.ranks));
-        f.keys = f.ranks = nullptr; f.kr_cap = 0;
-        CU(cudaMalloc(&f.keys, (size_t)f.cap * sizeof(unsigned)));
-        CU(cudaMalloc(&f.ranks, (size_t)f.cap * sizeof(unsigned)));
-        if (f.inv) CU(cudaFree(f.inv));
-        f.inv = nullptr;
-        CU(cudaMalloc(&f.inv, (size_t)f.cap * sizeof(unsigned)));
-        f.kr_cap = f.cap;
+    {
+        const int rc = fast_reserve_keys(ctx, f);
+        if (rc) return rc;
     }
     const unsigned want_items = (unsigned)(f.n / SF_ITEM_MAX + (int64_t)f.nti * f.ntj + 1);
     if (f.max_items < want_items) { // (the streaming step re-sizes the list for its own, smaller chunks)
@@ -370,9 +391,24 @@ static int fast_sort(sfgpu_ctx *ctx, int mesh_id, FastStore &f, double dt_pred =
         f.max_items = want_items;
     }
     const unsigned grid = (unsigned)((f.n + 255) / 256);
-    CU(cudaMemsetAsync(f.hist, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
-    k_sort_count<<<(unsigned)((f.n + 256 * SF_COUNT_ILP - 1) / (256 * SF_COUNT_ILP)), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, (unsigned long long)f.n, f.ntj, f.hist, f.keys, f.ranks, dt_pred * (ctx->sort_predict >= 0 ? ctx->sort_predict : std::min(2.0, 0.5 * (ctx->sort_every + 1))));
-    CU(cudaGetLastError());
+    const double pred = dt_pred * sort_horizon(ctx);
+    if (f.keys_ok && ctx->sort_gather && pred == f.keys_pred && pred != 0 && f.keys_n_sorted <= f.n) {
+        // the last tiled step keyed and counted the particles it finished itself; what is left: its deferred particles and the unsorted tail
+        const unsigned long long rest = (unsigned long long)f.keys_ndefer + (unsigned long long)(f.n - f.keys_n_sorted);
+        if (rest) {
+            k_sort_count_fix<<<(unsigned)((rest + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, f.defer, (unsigned long long)f.keys_ndefer,
+                                                                                   (unsigned long long)f.keys_n_sorted, (unsigned long long)f.n, f.ntj, f.hist, f.keys, f.ranks, pred);
+            CU(cudaGetLastError());
+        } else { // (the launch count below assumes a counting pass)
+            ctx->launch_total--;
+            ctx->last_launches--;
+        }
+    } else {
+        CU(cudaMemsetAsync(f.hist, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
+        k_sort_count<<<(unsigned)((f.n + 256 * SF_COUNT_ILP - 1) / (256 * SF_COUNT_ILP)), 256, 0, ctx->stream>>>(ctx->d_meshes, mesh_id, f.p, (unsigned long long)f.n, f.ntj, f.hist, f.keys, f.ranks, pred);
+        CU(cudaGetLastError());
+    }
+    f.keys_ok = false;
     CU(cub::DeviceScan::ExclusiveSum(f.cub_tmp, f.cub_bytes, f.hist, f.offs, (int)(f.nkeys + 1), ctx->stream));
     if (ctx->sort_gather) { // inverse permutation first (the keys array is reused for it after the fact: ranks -> inv), then a gather with coalesced stores
         k_sort_invert<<<(unsigned)((f.n + 256 * SF_SORT_ILP - 1) / (256 * SF_SORT_ILP)), 256, 0, ctx->stream>>>((unsigned long long)f.n, f.offs, f.keys, f.ranks, f.inv);
@@ -502,6 +538,34 @@ static int fast_reserve_alt(sfgpu_ctx *ctx, FastStore &f)
     return 0;
 }
 
+template <bool SEG, int HALO, bool PREP>
+static void launch_fast_step_t(sfgpu_ctx *ctx, const FastStepArgs &a, const FastStepArgs *ga)
+{
+    typedef FastGeom<HALO> G;
+    k_fast_step<SEG, HALO, PREP><<<ctx->fast_grid[HALO], G::WARPS * 32, G::WARPS * G::WARP_BYTES, ctx->stream>>>(a, ga);
+}
+
+static void launch_fast_step(sfgpu_ctx *ctx, const FastStepArgs &a, const FastStepArgs *ga, int halo, bool seg, bool prep)
+{
+    const int k = (halo == 1 ? 0 : 4) + (seg ? 2 : 0) + (prep ? 1 : 0);
+    switch (k) {
+    case 0: launch_fast_step_t<false, 1, false>(ctx, a, ga); break;
+    case 1: launch_fast_step_t<false, 1, true>(ctx, a, ga); break;
+    case 2: launch_fast_step_t<true, 1, false>(ctx, a, ga); break;
+    case 3: launch_fast_step_t<true, 1, true>(ctx, a, ga); break;
+    case 4: launch_fast_step_t<false, 2, false>(ctx, a, ga); break;
+    case 5: launch_fast_step_t<false, 2, true>(ctx, a, ga); break;
+    case 6: launch_fast_step_t<true, 2, false>(ctx, a, ga); break;
+    default: launch_fast_step_t<true, 2, true>(ctx, a, ga); break;
+    }
+}
+
+template <bool SEG, int HALO, bool PREP>
+static cudaError_t fast_step_smem_attr()
+{
+    return cudaFuncSetAttribute(k_fast_step<SEG, HALO, PREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FastGeom<HALO>::WARPS * FastGeom<HALO>::WARP_BYTES);
+}
+
 static FastStepArgs fast_args(sfgpu_ctx *ctx, Species &s, int m, double dt, const SlowPtrs &slow)
 {
     Pop &pop = s.pops[m];
@@ -601,15 +665,16 @@ extern "C" int sfgpu_create(int device, int domain_type, sfgpu_ctx **out)
         CU(cudaMalloc(&ctx->d_args, sizeof(FastStepArgs) * SF_MAX_MESHES));
         if (const char *e = getenv("SFGPU_SORT_GATHER")) ctx->sort_gather = atoi(e) != 0;
         if (const char *e = getenv("SFGPU_SORT_PREDICT")) ctx->sort_predict = atof(e);
+        if (const char *e = getenv("SFGPU_FUSE_COUNT")) ctx->fuse_count = atoi(e) != 0;
         if (const char *e = getenv("SFGPU_SORT_EVERY")) ctx->sort_every = atoi(e) > 0 ? atoi(e) : ctx->sort_every;
-        CU(cudaFuncSetAttribute(k_fast_step<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FastGeom<1>::WARPS * FastGeom<1>::WARP_BYTES));
-        CU(cudaFuncSetAttribute(k_fast_step<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FastGeom<1>::WARPS * FastGeom<1>::WARP_BYTES));
-        CU(cudaFuncSetAttribute(k_fast_step<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FastGeom<2>::WARPS * FastGeom<2>::WARP_BYTES));
-        CU(cudaFuncSetAttribute(k_fast_step<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FastGeom<2>::WARPS * FastGeom<2>::WARP_BYTES));
+        CU((fast_step_smem_attr<false, 1, false>())); CU((fast_step_smem_attr<false, 1, true>()));
+        CU((fast_step_smem_attr<true, 1, false>())); CU((fast_step_smem_attr<true, 1, true>()));
+        CU((fast_step_smem_attr<false, 2, false>())); CU((fast_step_smem_attr<false, 2, true>()));
+        CU((fast_step_smem_attr<true, 2, false>())); CU((fast_step_smem_attr<true, 2, true>()));
         int nsm = 0, per_sm[3] = {0, 0, 0};
         CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fast_step<false, 1>, FastGeom<1>::WARPS * 32, FastGeom<1>::WARPS * FastGeom<1>::WARP_BYTES));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_fast_step<false, 2>, FastGeom<2>::WARPS * 32, FastGeom<2>::WARPS * FastGeom<2>::WARP_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_fast_step<false, 1, false>, FastGeom<1>::WARPS * 32, FastGeom<1>::WARPS * FastGeom<1>::WARP_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_fast_step<false, 2, false>, FastGeom<2>::WARPS * 32, FastGeom<2>::WARPS * FastGeom<2>::WARP_BYTES));
         if (per_sm[1] < 1 || per_sm[2] < 1) return fail(ctx, SFGPU_ECUDA, "k_fast_step does not fit on this device");
         for (int h = 1; h <= 2; h++) {
             ctx->fast_grid[h] = nsm * per_sm[h];
@@ -1361,8 +1426,9 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     }
     for (int m = 0; m < nmesh; m++) {
         FastStore &f = s.pops[m].fast;
-        if (untiled) { f.stream_ok = false; continue; }
+        if (untiled) { f.stream_ok = false; f.keys_ok = false; continue; }
         if (stream) {
+            f.keys_ok = false;
             if (!f.stream_ok) {
                 if (f.n > 0 && f.n_sorted > 0 && (f.n - f.n_sorted) * 16 <= f.n) rc = fast_rehist(ctx, m, f); // the layout stands, the cells moved
                 else rc = fast_sort(ctx, m, f);
@@ -1378,6 +1444,7 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
             if (rc) return rc;
             f.stream_ok = false;
         }
+        f.keys_ok = false; // this step moves the particles: a counting pass nobody consumed is stale
     }
     for (int m = 0; m < nmesh; m++) {
         Pop &pop = s.pops[m];
@@ -1493,15 +1560,17 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
                     f.defer_cap = f.cap;
                     a.defer = f.defer; a.defer_cap = (unsigned)(f.defer_cap > 0x7fffffff ? 0x7fffffff : f.defer_cap);
                 }
-                if (ctx->fast_halo == 1) {
-                    typedef FastGeom<1> G;
-                    if (a.m.any_seg) k_fast_step<true, 1><<<ctx->fast_grid[1], G::WARPS * 32, G::WARPS * G::WARP_BYTES, ctx->stream>>>(a, ctx->d_args + m);
-                    else k_fast_step<false, 1><<<ctx->fast_grid[1], G::WARPS * 32, G::WARPS * G::WARP_BYTES, ctx->stream>>>(a, ctx->d_args + m);
-                } else {
-                    typedef FastGeom<2> G;
-                    if (a.m.any_seg) k_fast_step<true, 2><<<ctx->fast_grid[2], G::WARPS * 32, G::WARPS * G::WARP_BYTES, ctx->stream>>>(a, ctx->d_args + m);
-                    else k_fast_step<false, 2><<<ctx->fast_grid[2], G::WARPS * 32, G::WARPS * G::WARP_BYTES, ctx->stream>>>(a, ctx->d_args + m);
+                // the step after this one starts with a cell sort: do that sort's counting pass here, on the state being stored anyway
+                const bool prep = ctx->fuse_count && ctx->sort_gather && !ctx->stream_sort && !ctx->hybrid && !multi &&
+                                  f.steps_since_sort + 1 >= ctx->sort_every && dt * sort_horizon(ctx) != 0;
+                if (prep) {
+                    rc = fast_reserve_keys(ctx, f);
+                    if (rc) return rc;
+                    CU(cudaMemsetAsync(f.hist, 0, ((size_t)f.nkeys + 1) * sizeof(unsigned), ctx->stream));
+                    a.sort_keys = f.keys; a.sort_ranks = f.ranks; a.sort_hist = f.hist; a.sort_dt = dt * sort_horizon(ctx);
                 }
+                launch_fast_step(ctx, a, ctx->d_args + m, ctx->fast_halo, a.m.any_seg != 0, prep);
+                if (prep) { f.keys_ok = true; f.keys_pred = a.sort_dt; f.keys_n_sorted = f.n_sorted; f.keys_ndefer = 0; }
                 CU(cudaGetLastError());
                 k_fast_deferred<<<148 * 4, 256, 0, ctx->stream>>>(a); // boundary crossers, tile misses, removals: a fraction of a percent
                 CU(cudaGetLastError());
@@ -1575,8 +1644,10 @@ extern "C" int sfgpu_step(sfgpu_ctx *ctx, int32_t sp, double dt, uint32_t flags)
     }
     if (ctx->h_cnt->overflow)
         return fail(ctx, SFGPU_EOVERFLOW, "%llu particles did not fit an internal list (records / slow path / mesh hand-off)", ctx->h_cnt->overflow);
-    for (int m = 0; m < nmesh; m++)
+    for (int m = 0; m < nmesh; m++) {
         if ((int64_t)ctx->h_cnt->n_defer[m] > s.pops[m].fast.defer_cap) return fail(ctx, SFGPU_EOVERFLOW, "internal: deferred list overflow");
+        s.pops[m].fast.keys_ndefer = (int64_t)ctx->h_cnt->n_defer[m];
+    }
     for (int m = 0; m < nmesh; m++) {
         Pop &pop = s.pops[m];
         FastStore &f = pop.fast;
@@ -1951,6 +2022,7 @@ extern "C" int sfgpu_upload(sfgpu_ctx *ctx, int32_t sp, int32_t mesh_id, int64_t
         pop.cur.n += (int64_t)n_exc;
         pop.fast.alive -= (int64_t)n_exc;
         pop.fast.stream_ok = false; // edited in place: cells may have changed
+        pop.fast.keys_ok = false;
         if (n_exc) pop.fast.dirty = true;
     }
     return 0;

@@ -311,6 +311,30 @@ def test_injection_every_step_zero_weight_and_edges(flags):
             compare_fields(km, ok)
 
 
+@pytest.mark.parametrize("every", [1, 3])
+@pytest.mark.parametrize("bc", ["open", "periodic"])
+def test_fused_counting_pass_of_the_sort(every, bc, monkeypatch):
+    """SFGPU_FUSE_COUNT=1: the tiled step before a cell sort writes the sort's keys, ranks and histogram itself; deferred particles (exits, wraps) and the
+    injected tail are keyed by k_sort_count_fix when the sort runs.  Order only: same results."""
+    monkeypatch.setenv("SFGPU_FUSE_COUNT", "1")
+    m = S.make_mesh(61, 47, DomainType.XY, 1e-3, bc)
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 5, vth_cells=0.6, kick_frac=0.1)
+    arr = wl.particles(0, 40000)
+    km, ok = make_pair([m], wl, [arr], _lib.STEP_INPLACE)
+    with km:
+        km.setSortInterval(every)
+        first = 40000
+        for step in range(8):
+            if step % 2:
+                extra = wl.particles(first, 700)
+                first += 700
+                assert km.addParticles(m, to_particles(extra), wl.dt) == ok.addParticles(0, extra, wl.dt)
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            compare_state(km, ok)
+            compare_fields(km, ok)
+
+
 @pytest.mark.parametrize("flags", PATHS)
 def test_explicit_lc_injection_goes_through_records(flags):
     """addParticle(md, part) with a caller-supplied lc and residual dt (restart load, KM:953-1000): full records."""

@@ -13,7 +13,7 @@ w=csv.writer(sys.stdout)
 for k,r in enumerate(rows): w.writerow([r[i][:52] if (k>1 and i==idx[0]) else r[i] for i in idx])
 " > profiles/r2_ncu_summary.csv
 bash tools/prof_summary.sh $R/prof.ncu-rep > profiles/r2_final_ncu_k_fast_step.txt
-python tools/ncu_lines.py $R/prof.ncu-rep k_fast_step --sym k_fast_stepILb0ELi1 --top 45 > profiles/r2_final_ncu_lines.txt 2>&1 || true
+python tools/ncu_lines.py $R/prof.ncu-rep k_fast_step --sym k_fast_stepILb0ELi1ELb0 --top 45 > profiles/r2_final_ncu_lines.txt 2>&1 || true
 python - <<'PY'
 import csv,collections,re
 rows=list(csv.reader(l for l in open('gpurun_out/final_r2/launches.csv') if l.startswith('"')))
@@ -32,8 +32,10 @@ with open('profiles/r2_launch_shares.csv','w') as f:
         f.write('"%s",%d,%.4f,%.2f,%.5f\n'%(n,c,t,100*t/tot,t/c))
 PY
 cp $R/launches.csv profiles/r2_final_launches.csv; cp $R/launches.csv profiles/r2_launches.csv
-for f in bench_n1 bench_ref bench_c_n1 bench_e_n1 bench_n1_halo2; do [ -f $R/$f.json ] && cp $R/$f.json profiles/r2_final_$f.json; done
-tail -3 $R/pytest_gpu.log > profiles/r2_final_pytest_gpu.log; cp $R/smoke.log profiles/r2_final_smoke.log
+for f in bench_n1 bench_ref bench_c_n1 bench_e_n1 bench_n1_halo2; do [ -s $R/$f.json ] && cp $R/$f.json profiles/r2_final_$f.json; done
+[ -f $R/pytest_gpu.log ] && tail -3 $R/pytest_gpu.log > profiles/r2_final_pytest_gpu.log
+[ -f $R/pytest_gpu_rest.log ] && tail -3 $R/pytest_gpu_rest.log > profiles/r2_final_pytest_gpu_rest.log
+cp $R/smoke.log profiles/r2_final_smoke.log
 # SASS excerpt of the hot kernel
-{ echo "# cuobjdump -sass starfish_b200/libstarfish_gpu.so, k_fast_step<false, 1> (sm_100a), $(git rev-parse --short HEAD)+"; cuobjdump -sass starfish_b200/libstarfish_gpu.so | awk '/Function : _Z11k_fast_stepILb0ELi1/{p=1} p&&/Function : /&&!/k_fast_stepILb0ELi1/{p=0} p' > /tmp/kfs.sass; n=$(grep -cE '^\s+/\*[0-9a-f]{4}\*/' /tmp/kfs.sass); echo "# instruction count: $n; mnemonic histogram:"; grep -E '^\s+/\*[0-9a-f]{4}\*/' /tmp/kfs.sass | sed -E 's/^\s+\/\*[0-9a-f]+\*\/\s+(@!?U?P[0-9T]+\s+)?([A-Z0-9_.]+).*/\2/' | sort | uniq -c | sort -rn | head -40; echo "# row walk (LDS.128 operands, DFMA chain, conditional flush):"; grep -n "LDS.128" /tmp/kfs.sass | head -3; L=$(grep -n "LDS.128" /tmp/kfs.sass | head -1 | cut -d: -f1); sed -n "$((L-5)),$((L+70))p" /tmp/kfs.sass; } > profiles/r2_k_fast_step_sass.txt
+{ echo "# cuobjdump -sass starfish_b200/libstarfish_gpu.so, k_fast_step<false, 1> (sm_100a), $(git rev-parse --short HEAD)+"; cuobjdump -sass starfish_b200/libstarfish_gpu.so | awk '/Function : _Z11k_fast_stepILb0ELi1ELb0/{p=1} p&&/Function : /&&!/k_fast_stepILb0ELi1ELb0/{p=0} p' > /tmp/kfs.sass; n=$(grep -cE '^\s+/\*[0-9a-f]{4}\*/' /tmp/kfs.sass); echo "# instruction count: $n; mnemonic histogram:"; grep -E '^\s+/\*[0-9a-f]{4}\*/' /tmp/kfs.sass | sed -E 's/^\s+\/\*[0-9a-f]+\*\/\s+(@!?U?P[0-9T]+\s+)?([A-Z0-9_.]+).*/\2/' | sort | uniq -c | sort -rn | head -40; echo "# row walk (LDS.128 operands, DFMA chain, conditional flush):"; grep -n "LDS.128" /tmp/kfs.sass | head -3; L=$(grep -n "LDS.128" /tmp/kfs.sass | head -1 | cut -d: -f1); sed -n "$((L-5)),$((L+70))p" /tmp/kfs.sass; } > profiles/r2_k_fast_step_sass.txt
 cat profiles/r2_launch_shares.csv; cat profiles/r2_final_ncu_k_fast_step.txt; head -12 profiles/r2_final_ncu_lines.txt; cat profiles/traffic.json
