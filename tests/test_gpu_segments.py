@@ -10,8 +10,8 @@ import pytest
 import pyref
 from oracle import oracle as O
 from starfish_b200 import KineticMaterial, Particles, _lib, synthetic as S
-from test_gpu_parity import compare_fields, compare_state
-from test_segments import py_mesh
+from test_gpu_parity import compare_fields, compare_state, to_particles
+from test_segments import py_mesh, random_walls_case
 
 pytestmark = pytest.mark.gpu
 
@@ -101,3 +101,27 @@ def test_tutorial_step2_host_slow_path_matches_oracle(flags):
             scale = np.abs(ok.raw[0][f]).max()
             assert np.allclose(km.last_deposit[0][f], ok.raw[0][f], rtol=1e-10, atol=1e-10 * scale), f
         assert np.array_equal(km.last_deposit[0][7], ok.raw[0][7])
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_walls_device_segments_match_oracle(seed, flags):
+    """Random absorbing / surviving / SINK polylines in XY, RZ and ZR domains with open, periodic and symmetry faces; particles that cross several
+    cells and segments per step (tests/test_segments.py runs the same cases oracle against Python restatement)."""
+    m, wl, arr = random_walls_case(seed)
+    ok = O.OracleKM(wl.charge, wl.mass, [m])
+    with KineticMaterial("ion", wl.charge, wl.mass, [m], m.domain_type, step_flags=flags) as km:
+        km.dt = wl.dt
+        assert km.addParticles(m, to_particles(arr), wl.dt) == ok.addParticles(0, arr, wl.dt)
+        hits = 0
+        for it in range(6):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            h = km.takeSurfaceHits()
+            assert km.n_slow == 0 and not ok.slow
+            assert km.n_absorbed == ok.n_absorbed and km.n_exited == ok.n_exited and km.getNp() == ok.getNp(), it
+            assert _hit_key(h) == _hit_key(ok.hits[0]), it
+            hits += len(h["seg"])
+            compare_state(km, ok)
+            compare_fields(km, ok)
+        assert hits > 30

@@ -92,3 +92,60 @@ def test_oracle_matches_python_restatement_on_tutorial_step2(wall_kind):
                      ("lj", lambda a: a.lc[1]), ("dt", lambda a: a.dt)):
         assert np.array_equal(p[key], np.array([get(a) for a in q])), key
     assert state == rnd.state
+
+
+def random_walls_case(seed):
+    """Mesh with a random absorbing polygon, a random open polyline whose hits leave the particle alive, a random SINK line; hot particles."""
+    rng = np.random.default_rng(1000 + seed)
+    dom = [DomainType.XY, DomainType.RZ, DomainType.ZR][seed % 3]
+    bc = ["open", "periodic", "symmetry"][(seed // 3 + seed) % 3]
+    ni, nj = int(rng.integers(24, 40)), int(rng.integers(20, 36))
+    m = S.make_mesh(ni, nj, dom, 1e-3, bc)
+    lx, ly = (ni - 1) * 1e-3, (nj - 1) * 1e-3
+    walls = []
+    # a closed polygon around a random centre (absorbing) ...
+    cx, cy, r = lx * rng.uniform(0.35, 0.65), ly * rng.uniform(0.35, 0.65), min(lx, ly) * rng.uniform(0.08, 0.2)
+    nv = int(rng.integers(3, 9))
+    ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+    poly = np.stack([cx + r * np.cos(ang), cy + r * np.sin(ang)], axis=1)
+    walls.append(SolidBoundary("poly", np.vstack([poly, poly[:1]]), kind=0))
+    # ... an open polyline whose hits leave the particle alive (it goes on with the rest of its step) ...
+    pts = np.stack([lx * rng.uniform(0.05, 0.95, 4), ly * rng.uniform(0.05, 0.95, 4)], axis=1)
+    walls.append(SolidBoundary("keep", pts, kind=1))
+    # ... and a SINK line
+    pts = np.stack([lx * rng.uniform(0.05, 0.95, 2), ly * rng.uniform(0.05, 0.95, 2)], axis=1)
+    walls.append(SolidBoundary("sink", pts, kind=1, sink=True))
+    set_boundaries(m, walls)
+    wl = S.Workload("t", m, 1e-7, S.QE, 16 * S.AMU, 77 + seed, vth_cells=1.7, kick_frac=0.2)
+    arr = wl.particles(0, 3000)
+    return m, wl, arr
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_matches_python_restatement_on_random_walls(seed):
+    """Differential test beyond the tutorial geometry: random closed and open polylines of absorbing, surviving and SINK segments, hot particles
+    that cross several cells (and several segments) per step, every domain type and face type: two independent restatements, bit for bit."""
+    m, wl, arr = random_walls_case(seed)
+    ok = O.OracleKM(wl.charge, wl.mass, [m])
+    km = pyref.KM(wl.charge, wl.mass, [py_mesh(m)])
+    ok.addParticles(0, arr, wl.dt)
+    for q in range(len(arr["x"])):
+        km.addParticle(0, pyref.Particle([arr["x"][q], arr["y"][q], arr["z"][q]], [arr["u"][q], arr["v"][q], arr["w"][q]], arr["mpw"][q]), wl.dt)
+    total_hits = 0
+    for _ in range(6):
+        ok.updateFields(wl.dt)
+        km.updateFields(wl.dt)
+        assert (ok.n_absorbed, ok.n_exited, len(ok.slow)) == (km.n_absorbed, km.n_exited, len(km.slow))
+        h = ok.hits[0]
+        assert len(h["seg"]) == len(km.hits)
+        for q, (sid, ts, vel, mpw, alive) in enumerate(km.hits):
+            assert (int(h["seg"][q]), float(h["t"][q]), float(h["u"][q]), float(h["v"][q]), float(h["w"][q]), float(h["mpw"][q]), bool(h["alive"][q])) == \
+                   (sid, ts, vel[0], vel[1], vel[2], mpw, alive)
+        total_hits += len(km.hits)
+        p = ok.sorted_parts(0)
+        q = sorted(km.particles[0], key=lambda a: a.id)
+        assert len(q) == len(p["x"])
+        for key, get in (("x", lambda a: a.pos[0]), ("y", lambda a: a.pos[1]), ("z", lambda a: a.pos[2]), ("u", lambda a: a.vel[0]), ("v", lambda a: a.vel[1]),
+                         ("w", lambda a: a.vel[2]), ("li", lambda a: a.lc[0]), ("lj", lambda a: a.lc[1]), ("dt", lambda a: a.dt)):
+            assert np.array_equal(p[key], np.array([get(a) for a in q])), key
+    assert total_hits > 30
