@@ -11,7 +11,7 @@ import pyref
 from oracle import oracle as O
 from starfish_b200 import KineticMaterial, Particles, _lib, synthetic as S
 from test_gpu_parity import compare_fields, compare_state, to_particles
-from test_segments import py_mesh, random_walls_case
+from test_segments import handoff_walls_case, py_mesh, random_walls_case
 
 pytestmark = pytest.mark.gpu
 
@@ -125,3 +125,28 @@ def test_random_walls_device_segments_match_oracle(seed, flags):
             compare_state(km, ok)
             compare_fields(km, ok)
         assert hits > 30
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("kind", [0, 1], ids=["absorb", "keep"])
+def test_walls_next_to_a_mesh_handoff_match_oracle(kind, flags):
+    """Walls on both sides of a MESH face: hits in the main pass and in the transfer sweeps of the neighbour mesh (KM:131-142), hit lists per mesh."""
+    meshes, wl, arr = handoff_walls_case(kind)
+    ok = O.OracleKM(wl.charge, wl.mass, meshes)
+    with KineticMaterial("ion", wl.charge, wl.mass, meshes, meshes[0].domain_type, step_flags=flags) as km:
+        km.dt = wl.dt
+        assert km.addParticles(meshes[0], to_particles(arr), wl.dt) == ok.addParticles(0, arr, wl.dt)
+        hits = [0, 0]
+        for it in range(14):
+            km.updateFields()
+            ok.updateFields(wl.dt)
+            h = km.takeSurfaceHits()
+            assert km.n_slow == 0 and not ok.slow
+            assert km.n_absorbed == ok.n_absorbed and km.n_exited == ok.n_exited and km.getNp() == ok.getNp(), it
+            for k in range(2):
+                sel = h["mesh"] == k
+                assert _hit_key({key: v[sel] for key, v in h.items()}) == _hit_key(ok.hits[k]), (it, k)
+                hits[k] += int(sel.sum())
+            compare_state(km, ok)
+            compare_fields(km, ok)
+        assert hits[0] > 10 and hits[1] > 10

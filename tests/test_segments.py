@@ -149,3 +149,59 @@ def test_oracle_matches_python_restatement_on_random_walls(seed):
                          ("w", lambda a: a.vel[2]), ("li", lambda a: a.lc[0]), ("lj", lambda a: a.lc[1]), ("dt", lambda a: a.dt)):
             assert np.array_equal(p[key], np.array([get(a) for a in q])), key
     assert total_hits > 30
+
+
+def handoff_walls_case(kind):
+    """Two RZ meshes stacked in z (MESH faces between them), a two-segment wall on either side of the interface, a SINK line further up; a drifting population."""
+    from starfish_b200.domain import DomainBoundaryType as BC, Face
+    a = UniformMesh(13, 11, (0.0, 0.0), (1e-3, 1e-3), DomainType.RZ)
+    b = UniformMesh(7, 13, (0.0, 10e-3), (2e-3, 0.5e-3), DomainType.RZ)
+    for m in (a, b):
+        m.setMeshBCType(Face.LEFT, BC.SYMMETRY)
+    for i in range(a.ni):
+        a.setNeighbor(Face.TOP, i, 0, 1)
+    for i in range(b.ni):
+        b.setNeighbor(Face.BOTTOM, i, 0, 0)
+    set_boundaries(a, [SolidBoundary("wa", np.array([[2e-3, 8.4e-3], [6e-3, 9.3e-3], [9e-3, 7.7e-3]]), kind=kind)])
+    set_boundaries(b, [SolidBoundary("wb", np.array([[1e-3, 11.2e-3], [5e-3, 10.6e-3], [10e-3, 12.1e-3]]), kind=kind),
+                       SolidBoundary("sink", np.array([[0.5e-3, 14e-3], [11e-3, 14.4e-3]]), kind=1, sink=True)])
+    wl = S.Workload("t", a, 1e-7, S.QE, 16 * S.AMU, 19, vth_cells=0.5, drift_cells=(0.0, 1.3), kick_frac=0.0)
+    arr = wl.particles(0, 1500)
+    arr["x"] = np.abs(arr["x"]) * 0.9 + 1e-5
+    return [a, b], wl, arr
+
+
+@pytest.mark.parametrize("kind", [0, 1], ids=["absorb", "keep"])
+def test_oracle_matches_python_restatement_walls_next_to_a_mesh_handoff(kind):
+    """Two RZ meshes stacked in z with different spacings (MESH faces, KM:708-722) and a wall on either side of the interface: a particle can hit a
+    surviving segment, finish its step across the MESH face and hit the neighbour's wall in the transfer sweep (KM:131-142) -- both restatements, bit for bit."""
+    (a, b), wl, arr = handoff_walls_case(kind)
+
+    def pm(m):
+        q = py_mesh(m)
+        for f in range(4):
+            q.nbr[f] = [[None if v < 0 else int(v) for v in row] for row in m.nbr[f]]
+        return q
+    ok = O.OracleKM(wl.charge, wl.mass, [a, b])
+    km = pyref.KM(wl.charge, wl.mass, [pm(a), pm(b)])
+    ok.addParticles(0, arr, wl.dt)
+    for q in range(len(arr["x"])):
+        km.addParticle(0, pyref.Particle([arr["x"][q], arr["y"][q], arr["z"][q]], [arr["u"][q], arr["v"][q], arr["w"][q]], arr["mpw"][q]), wl.dt)
+    hits = [0, 0]
+    for _ in range(14):
+        ok.updateFields(wl.dt)
+        km.updateFields(wl.dt)
+        assert (ok.n_absorbed, ok.n_exited, len(ok.slow)) == (km.n_absorbed, km.n_exited, len(km.slow))
+        got = sorted((int(h["mesh"][q]) if "mesh" in h else k, int(h["seg"][q]), float(h["t"][q]), float(h["u"][q]), float(h["v"][q]), float(h["mpw"][q]), bool(h["alive"][q]))
+                     for k, h in enumerate(ok.hits) for q in range(len(h["seg"])))
+        for k, h in enumerate(ok.hits):
+            hits[k] += len(h["seg"])
+        assert len(got) == len(km.hits)
+        for k in range(2):
+            p = ok.sorted_parts(k)
+            q = sorted(km.particles[k], key=lambda a_: a_.id)
+            assert len(q) == len(p["x"])
+            for key, get in (("x", lambda a_: a_.pos[0]), ("y", lambda a_: a_.pos[1]), ("u", lambda a_: a_.vel[0]), ("v", lambda a_: a_.vel[1]),
+                             ("w", lambda a_: a_.vel[2]), ("li", lambda a_: a_.lc[0]), ("lj", lambda a_: a_.lc[1]), ("dt", lambda a_: a_.dt)):
+                assert np.array_equal(p[key], np.array([get(a_) for a_ in q])), (k, key)
+    assert hits[0] > 10 and hits[1] > 10 and ok.getNp(1) > 0
