@@ -61,6 +61,11 @@ extern "C" {
 #define SFGPU_BC_SINK 5
 #define SFGPU_BC_CIRCUIT 6
 
+/* per-segment outcome of a surface hit for sfgpu_mesh_set_segments */
+#define SFGPU_SURFACE_REMOVE 0
+#define SFGPU_SURFACE_NONE 1
+#define SFGPU_SURFACE_SPECULAR 2
+
 /* sfgpu_inject flags */
 #define SFGPU_INJECT_REWIND 1u      /* apply the -0.5*dt velocity rewind of addParticle, KM:776-794 */
 #define SFGPU_INJECT_DEPOSIT_NOW 2u /* particle was already moved this step (slow-path survivor):
@@ -143,8 +148,10 @@ int sfgpu_mesh_add(sfgpu_ctx *ctx, int32_t ni, int32_t nj, const double x0[2], c
                    const double *node_vol, int32_t *mesh_id);
 /* surface hits on the device.  The DIRICHLET / SINK LinearSegments (boundaries/LinearSegment.java) of node[i][j].segments
  * (Mesh.setNodeControlVolumes, MESH:1215-1290) as a CSR over nodes i*nj+j (node_offs: ni*nj+1 entries, node_ids: segment indices), and per
- * segment what Material.performSurfaceInteraction (Material.java:279-300) does to THIS material's particles: kind 0 = the particle is
- * removed (no interaction listed, or ABSORB), kind 1 = it lives on unchanged (NONE; SPECULAR as SurfaceInteraction.java:82-125 is written);
+ * segment what Material.performSurfaceInteraction (Material.java:279-300) does to THIS material's particles: SFGPU_SURFACE_REMOVE (0) = the
+ * particle is removed (no interaction listed for the pair, or ABSORB, SurfaceInteraction.java:92-101), SFGPU_SURFACE_NONE (1) = it lives on
+ * unchanged (NONE, :82-90, or a boundary without a material, KM:586), SFGPU_SURFACE_SPECULAR (2) = SurfaceImpactSpecular without a species
+ * change (:104-149): vel[0..1] += LinearSegment.normal * (Vec.mag2(vel) * sqrt 2), the particle lives on and the hit carries the new velocity;
  * sink[k] != 0: the boundary is a SINK (KM:593-594).  With the table set, the segment part of ProcessBoundary (KM:482-603: nearest
  * LinearSegment.intersect, start-of-step exclusion, 0.9999 back-off, dt_rem) runs inside sfgpu_step and such particles no longer come back
  * through sfgpu_take_slowpath; hits are listed for sfgpu_take_surface_hits.  Models that draw random numbers (DIFFUSE / COSINE, sputtering,

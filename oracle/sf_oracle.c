@@ -196,7 +196,7 @@ void sfo_segment_intersect(const sfo_segment *s, const double p3[2], const doubl
 
 /* segment part of ProcessBoundary, KM:504-603, for LinearSegments with a deterministic surface outcome.
  * Returns 0: no hit, 1: hit and alive (pos, lc, *dtp updated), 2: hit and removed. */
-static int process_segments(const sfo_mesh *m, double dt0, const double old[2], double lio, double ljo, double pos[3], const double vel[3],
+static int process_segments(const sfo_mesh *m, double dt0, const double old[2], double lio, double ljo, double pos[3], double vel[3],
                             double mpw, double *li, double *lj, double *dtp)
 {
     /* the node bounding box of the sub-step, KM:482-502 */
@@ -243,7 +243,17 @@ static int process_segments(const sfo_mesh *m, double dt0, const double old[2], 
     if (*li < 0 && *li > -FLT_EPS) *li = 0; /* KM:574-577 */
     if (*lj < 0 && *lj > -FLT_EPS) *lj = 0;
     const sfo_segment *seg = &m->segs[seg_min];
-    int alive = seg->kind != 0; /* performSurfaceInteraction, KM:586-587 */
+    int alive = seg->kind != 0; /* performSurfaceInteraction, KM:586-587 (Material.java:279-300): nothing listed / ABSORB remove, NONE keeps */
+    if (seg->kind == 2) { /* SurfaceImpactSpecular without a species change, SurfaceInteraction.java:104-149: the velocity the hit records carry is the new one */
+        double dx = seg->x2 - seg->x1, dy = seg->y2 - seg->y1; /* LinearSegment.normal, LinearSegment.java:26-44 */
+        const double len = sqrt(dx * dx + dy * dy);
+        dx /= len;
+        dy /= len;
+        const double n0 = -dy, n1 = dx;
+        const double mag = sqrt(vel[0] * vel[0] + vel[1] * vel[1]) * sqrt(2.0); /* Vec.mag2 (Vec.java:269-272) * Constants.SQRT2 */
+        vel[0] += n0 * mag;
+        vel[1] += n1 * mag;
+    }
     if (seg->sink) alive = 0;   /* KM:593-594 */
     if (m->hits) {
         const int64_t h = __sync_fetch_and_add(&m->hits->n, 1);

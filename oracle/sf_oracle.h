@@ -50,9 +50,9 @@ enum {
  * with the outcome of Material.performSurfaceInteraction (Material.java:279-300) folded into `kind` */
 typedef struct {
     double x1, y1, x2, y2;
-    int32_t kind;  /* 0: the particle dies (no interaction listed, or ABSORB: SurfaceInteraction.java:72-79);
-                      1: it lives on with unchanged velocity (NONE, and SPECULAR as the reference implements it:
-                         the reflection arithmetic of SurfaceInteraction.java:86-104 sits inside a comment) */
+    int32_t kind;  /* 0: the particle dies (no interaction listed, or ABSORB: SurfaceInteraction.java:92-101);
+                      1: it lives on with unchanged velocity (NONE, SurfaceInteraction.java:82-90);
+                      2: SPECULAR without a species change (SurfaceInteraction.java:104-149): vel[0..1] += normal * (Vec.mag2(vel) * SQRT2), alive */
     int32_t sink;  /* the Boundary is of type SINK: dies regardless, KM:593-594 */
 } sfo_segment;
 

@@ -297,6 +297,17 @@ __device__ __noinline__ int sf_process_segments(const MeshDev *mp, double dt0, d
     if (p.lj < 0 && p.lj > -SF_FLT_EPS) p.lj = 0;
     const int2 kd = m.seg_kind[seg_min];
     const bool alive = kd.x != 0 && kd.y == 0; // performSurfaceInteraction KM:586-587, SINK KM:593-594
+    if (kd.x == 2) { // SurfaceImpactSpecular without a species change (SurfaceInteraction.java:104-149): vel += n * (|vel_xy| * sqrt 2), before the hit is recorded
+        const double4 sg = m.seg_xy[seg_min];
+        double dx = sg.z - sg.x, dy = sg.w - sg.y; // LinearSegment.normal, LinearSegment.java:26-44
+        const double len = sqrt(dx * dx + dy * dy);
+        dx /= len;
+        dy /= len;
+        const double n0 = -dy, n1 = dx;
+        const double mag = sqrt(p.u * p.u + p.v * p.v) * 1.4142135623730951; // Vec.mag2 * Constants.SQRT2 (= Math.sqrt(2))
+        p.u += n0 * mag;
+        p.v += n1 * mag;
+    }
     if (m.hits.n) {
         const unsigned long long h = atomicAdd(m.hits.n, 1ULL);
         if (h < m.hits.cap) {

@@ -879,6 +879,8 @@ extern "C" int sfgpu_mesh_set_segments(sfgpu_ctx *ctx, int32_t mesh_id, int32_t 
     std::vector<double4> xy(n_seg);
     std::vector<int2> kd(n_seg);
     for (int k = 0; k < n_seg; k++) {
+        if (kind[k] < 0 || kind[k] > SFGPU_SURFACE_SPECULAR)
+            return fail(ctx, SFGPU_EINVAL, "sfgpu_mesh_set_segments: segment %d has outcome %d (0 removed, 1 unchanged, 2 specular); other surface models stay on the host path", k, (int)kind[k]);
         xy[k] = make_double4(x1[k], y1[k], x2[k], y2[k]);
         kd[k] = make_int2(kind[k], sink ? sink[k] : 0);
     }

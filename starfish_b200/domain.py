@@ -224,8 +224,8 @@ def _segment_intersect(x1, y1, x2, y2, p3, p4):
 class SolidBoundary:
     """A ``Boundary`` of type DIRICHLET ("solid") or SINK made of linear segments (boundaries.xml ``<path>M .. L ..</path>``),
     with the outcome ``Material.performSurfaceInteraction`` (Material.java:279-300) has for the species that hits it:
-    ``kind`` 0 = the particle dies (no interaction listed for the pair, or ABSORB), 1 = it lives on unchanged (NONE; SPECULAR
-    as SurfaceInteraction.java:82-125 implements it)."""
+    ``kind`` 0 = the particle dies (no interaction listed for the pair, or ABSORB), 1 = it lives on unchanged (NONE), 2 = SPECULAR
+    without a species change (SurfaceInteraction.java:104-149: ``vel += normal * |vel_xy| * sqrt(2)``, alive)."""
 
     def __init__(self, name, points, kind=0, sink=False):
         pts = np.asarray(points, np.float64)

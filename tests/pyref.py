@@ -272,7 +272,12 @@ class KM:
             part.lc[0] = 0.0
         if part.lc[1] < 0 and part.lc[1] > -FLT_EPS:
             part.lc[1] = 0.0
-        alive = seg_min.kind != 0  # Material.performSurfaceInteraction: no handler / ABSORB kills, NONE / SPECULAR-as-written keep
+        alive = seg_min.kind != 0  # Material.performSurfaceInteraction (Material.java:279-300): no handler listed / ABSORB kill, NONE keeps
+        if seg_min.kind == 2:  # SurfaceImpactSpecular without a species change, SurfaceInteraction.java:104-149: vel += n * (|vel_xy| * sqrt 2)
+            n = seg_min.normal
+            mag = math.sqrt(part.vel[0] * part.vel[0] + part.vel[1] * part.vel[1]) * math.sqrt(2)
+            part.vel[0] += n[0] * mag
+            part.vel[1] += n[1] * mag
         if seg_min.sink:
             alive = False
         self.hits.append((seg_min.sid, tsurf_min, list(part.vel), part.mpw, alive))

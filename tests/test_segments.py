@@ -95,7 +95,8 @@ def test_oracle_matches_python_restatement_on_tutorial_step2(wall_kind):
 
 
 def random_walls_case(seed):
-    """Mesh with a random absorbing polygon, a random open polyline whose hits leave the particle alive, a random SINK line; hot particles."""
+    """Mesh with a random polygon (absorbing or specular), a random open polyline whose hits leave the particle alive (unchanged or specular), a random SINK line;
+    hot particles."""
     rng = np.random.default_rng(1000 + seed)
     dom = [DomainType.XY, DomainType.RZ, DomainType.ZR][seed % 3]
     bc = ["open", "periodic", "symmetry"][(seed // 3 + seed) % 3]
@@ -108,10 +109,10 @@ def random_walls_case(seed):
     nv = int(rng.integers(3, 9))
     ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
     poly = np.stack([cx + r * np.cos(ang), cy + r * np.sin(ang)], axis=1)
-    walls.append(SolidBoundary("poly", np.vstack([poly, poly[:1]]), kind=0))
+    walls.append(SolidBoundary("poly", np.vstack([poly, poly[:1]]), kind=2 if seed % 2 else 0))  # odd seeds: a specular body instead of an absorbing one
     # ... an open polyline whose hits leave the particle alive (it goes on with the rest of its step) ...
     pts = np.stack([lx * rng.uniform(0.05, 0.95, 4), ly * rng.uniform(0.05, 0.95, 4)], axis=1)
-    walls.append(SolidBoundary("keep", pts, kind=1))
+    walls.append(SolidBoundary("keep", pts, kind=2 if seed % 3 == 0 else 1))
     # ... and a SINK line
     pts = np.stack([lx * rng.uniform(0.05, 0.95, 2), ly * rng.uniform(0.05, 0.95, 2)], axis=1)
     walls.append(SolidBoundary("sink", pts, kind=1, sink=True))
@@ -205,3 +206,25 @@ def test_oracle_matches_python_restatement_walls_next_to_a_mesh_handoff(kind):
                              ("w", lambda a_: a_.vel[2]), ("li", lambda a_: a_.lc[0]), ("lj", lambda a_: a_.lc[1]), ("dt", lambda a_: a_.dt)):
                 assert np.array_equal(p[key], np.array([get(a_) for a_ in q])), (k, key)
     assert hits[0] > 10 and hits[1] > 10 and ok.getNp(1) > 0
+
+
+def test_kat_specular_as_the_reference_writes_it():
+    """SurfaceImpactSpecular (SurfaceInteraction.java:104-149) adds normal * |vel_xy| * sqrt(2) to the in-plane velocity; LinearSegment.normal = (-dy, dx) / length
+    (LinearSegment.java:26-44).  One particle flying straight down onto a horizontal wall that runs along +x (normal +y): u unchanged, v = -|v| + |v| sqrt 2."""
+    m = S.make_mesh(11, 11, DomainType.XY, 1e-3, "open")
+    m.efi[:] = 0.0
+    m.efj[:] = 0.0
+    set_boundaries(m, [SolidBoundary("floor", np.array([[1e-3, 4.25e-3], [9e-3, 4.25e-3]]), kind=2)])
+    ok = O.OracleKM(S.QE, 16 * S.AMU, [m])
+    v0 = -7000.0
+    arr = dict(x=np.array([5.2e-3]), y=np.array([4.6e-3]), z=np.zeros(1), u=np.zeros(1), v=np.array([v0]), w=np.array([300.0]), mpw=np.array([2.0]))
+    ok.addParticles(0, arr, 1e-7)
+    ok.updateFields(1e-7)  # 0.7 mm of travel: crosses y = 4.25 mm at half of the step
+    h = ok.hits[0]
+    assert len(h["seg"]) == 1 and bool(h["alive"][0]) and ok.n_absorbed == 0
+    mag = np.sqrt(0.0 * 0.0 + v0 * v0) * np.sqrt(2.0)
+    want_v = v0 + 1.0 * mag
+    p = ok.sorted_parts(0)
+    assert p["u"][0] == 0.0 and p["v"][0] == want_v and p["w"][0] == 300.0 and h["v"][0] == want_v
+    t_hit = (4.6e-3 - 4.25e-3) / 7e-4 * 0.9999
+    assert abs(p["y"][0] - (4.6e-3 + v0 * 1e-7 * t_hit + want_v * 1e-7 * (1 - t_hit))) < 1e-12  # the rest of the step runs with the new velocity
