@@ -155,8 +155,10 @@ int sfgpu_mesh_add(sfgpu_ctx *ctx, int32_t ni, int32_t nj, const double x0[2], c
  * sink[k] != 0: the boundary is a SINK (KM:593-594).  With the table set, the segment part of ProcessBoundary (KM:482-603: nearest
  * LinearSegment.intersect, start-of-step exclusion, 0.9999 back-off, dt_rem) runs inside sfgpu_step and such particles no longer come back
  * through sfgpu_take_slowpath; hits are listed for sfgpu_take_surface_hits.  Models that draw random numbers (DIFFUSE / COSINE, sputtering,
- * species change) keep the host path: do not register those boundaries' segments (has_seg of sfgpu_mesh_add still flags them).
- * The node table replaces has_seg.  n_seg = 0 clears it. */
+ * species change) keep the host path.  The choice is per MESH: the node table replaces has_seg of sfgpu_mesh_add, so a mesh registers ALL of
+ * its DIRICHLET / SINK segments here (every one of them with a deterministic outcome for this material) or none of them (and then keeps
+ * has_seg + sfgpu_take_slowpath).  n_seg = 0 clears the table; the nodes stay flagged, so their particles come back through
+ * sfgpu_take_slowpath again. */
 int sfgpu_mesh_set_segments(sfgpu_ctx *ctx, int32_t mesh_id, int32_t n_seg, const double *x1, const double *y1, const double *x2,
                             const double *y2, const int32_t *kind, const int32_t *sink, const int32_t *node_offs, const int32_t *node_ids);
 /* the surface hits of the last sfgpu_step in any order: mesh, segment index, t along the segment, velocity at impact, mpw, survived?

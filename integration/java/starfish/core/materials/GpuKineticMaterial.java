@@ -16,11 +16,14 @@ package starfish.core.materials;
 import java.nio.ByteBuffer;
 import java.nio.ByteOrder;
 import java.nio.DoubleBuffer;
+import java.lang.reflect.Field;
 import java.util.ArrayList;
+import java.util.HashMap;
 import java.util.Iterator;
 
 import org.w3c.dom.Element;
 
+import starfish.core.boundaries.Boundary;
 import starfish.core.boundaries.Boundary.BoundaryType;
 import starfish.core.boundaries.Segment;
 import starfish.core.common.Starfish;
@@ -32,6 +35,8 @@ import starfish.core.domain.Mesh.DomainBoundaryType;
 import starfish.core.domain.Mesh.Face;
 import starfish.core.domain.Mesh.MeshBoundaryData;
 import starfish.core.domain.UniformMesh;
+import starfish.interactions.MaterialInteraction;
+import starfish.interactions.SurfaceInteraction;
 
 public class GpuKineticMaterial extends KineticMaterial {
     private long ctx = 0;
@@ -45,6 +50,10 @@ public class GpuKineticMaterial extends KineticMaterial {
     /* particles added since the last step, per mesh (KM:759: sources call addParticle one particle at a time) */
     private ArrayList<ArrayList<Particle>> pending = new ArrayList<>();
     private boolean gpu_first_time = true;
+    /* surfaces handled on the device (sfgpu_mesh_set_segments): per mesh the segments in table order and their SFGPU_SURFACE_* outcome; null = host path */
+    private Segment[][] devSeg;
+    private int[][] devKind;
+    private boolean deviceSurfaces = false;
 
     public GpuKineticMaterial(String name, Element element) {
         super(name, element);
@@ -75,6 +84,50 @@ public class GpuKineticMaterial extends KineticMaterial {
             d.get(dst[i]);
     }
 
+    /**
+     * What Material.performSurfaceInteraction (Material.java:279-300) does to THIS material on a segment, if that is deterministic:
+     * SURFACE_REMOVE (nothing listed for the pair, or ABSORB), SURFACE_NONE (NONE, or a boundary without material, KM:586), SURFACE_SPECULAR
+     * (SPECULAR without a species change); -1 when the outcome needs the Java code (models that draw random numbers, emission hooks,
+     * several handlers with probabilities, curved segments).  MaterialInteraction keeps its handler package-private: read by reflection.
+     */
+    private int surfaceOutcome(Segment seg) {
+        if (!seg.getClass().getSimpleName().equals("LinearSegment"))
+            return -1;
+        Material target = seg.getBoundary().getMaterial(0.5);
+        if (target == null)
+            return SfgpuJni.SURFACE_NONE;
+        if (target.target_interactions != null && !target.target_interactions.getInteractionList(mat_index).isEmpty())
+            return -1; /* sputtering / emission hooks run first, Material.java:281-286 */
+        if (target.source_interactions == null)
+            return SfgpuJni.SURFACE_REMOVE;
+        ArrayList<MaterialInteraction> list = target.source_interactions.getInteractionList(mat_index);
+        if (list.isEmpty())
+            return SfgpuJni.SURFACE_REMOVE; /* Material.java:291-295 */
+        if (list.size() != 1 || list.get(0).getProbability() != 1.0)
+            return -1;
+        try {
+            MaterialInteraction mi = list.get(0);
+            Field hf = MaterialInteraction.class.getDeclaredField("surface_impact_handler");
+            hf.setAccessible(true);
+            Object handler = hf.get(mi);
+            if (handler == SurfaceInteraction.SurfaceImpactAbsorb)
+                return SfgpuJni.SURFACE_REMOVE;
+            if (handler == SurfaceInteraction.SurfaceImpactNone)
+                return SfgpuJni.SURFACE_NONE;
+            if (handler == SurfaceInteraction.SurfaceImpactSpecular) {
+                Field sf = MaterialInteraction.class.getDeclaredField("source_mat");
+                Field pf = MaterialInteraction.class.getDeclaredField("product_mat");
+                Field kf = MaterialInteraction.class.getDeclaredField("product_km_mat");
+                sf.setAccessible(true); pf.setAccessible(true); kf.setAccessible(true);
+                boolean speciesChange = sf.get(mi) != pf.get(mi) && kf.get(mi) != null; /* SurfaceInteraction.java:128 */
+                return speciesChange ? -1 : SfgpuJni.SURFACE_SPECULAR;
+            }
+        } catch (ReflectiveOperationException | SecurityException ex) {
+            Log.warning("sfgpu: cannot inspect the surface model of " + seg.getBoundary().getName() + " (" + ex + "): host path");
+        }
+        return -1;
+    }
+
     @Override
     public void init() {
         super.init(); /* KM:83-112: MeshData per mesh, sample fields */
@@ -89,6 +142,8 @@ public class GpuKineticMaterial extends KineticMaterial {
         efi = new ByteBuffer[nMesh]; efj = new ByteBuffer[nMesh]; bfi = new ByteBuffer[nMesh]; bfj = new ByteBuffer[nMesh];
         nd = new ByteBuffer[nMesh]; u = new ByteBuffer[nMesh]; v = new ByteBuffer[nMesh]; w = new ByteBuffer[nMesh];
         samples = new ByteBuffer[nMesh][SfgpuJni.NFIELDS];
+        devSeg = new Segment[nMesh][];
+        devKind = new int[nMesh][];
         for (int m = 0; m < nMesh; m++) {
             if (!(meshes[m] instanceof UniformMesh))
                 Log.error("type=\"kinetic_gpu\" needs uniform meshes; mesh " + meshes[m].getName() + " is not");
@@ -111,15 +166,38 @@ public class GpuKineticMaterial extends KineticMaterial {
                         nbr[face.val()][2 * k + q] = bd.neighbor[q] == null ? -1 : list.indexOf(bd.neighbor[q]);
                 }
             }
-            /* nodes that own a DIRICHLET or SINK segment (KM:508-518) */
+            /* nodes that own a DIRICHLET or SINK segment (KM:508-518), and node.segments as a CSR over the distinct segments of the mesh */
             byte[] hasSeg = new byte[ni * nj];
+            ArrayList<Segment> segList = new ArrayList<>();
+            HashMap<Segment, Integer> segIndex = new HashMap<>();
+            int[] nodeOffs = new int[ni * nj + 1];
+            ArrayList<Integer> nodeIds = new ArrayList<>();
             for (int i = 0; i < ni; i++)
-                for (int j = 0; j < nj; j++)
+                for (int j = 0; j < nj; j++) {
+                    nodeOffs[i * nj + j] = nodeIds.size();
                     for (Segment seg : mesh.getNode(i, j).segments)
                         if (seg.getBoundaryType() == BoundaryType.DIRICHLET || seg.getBoundaryType() == BoundaryType.SINK) {
                             hasSeg[i * nj + j] = 1;
-                            needsSlowPath = true;
+                            Integer k = segIndex.get(seg);
+                            if (k == null) {
+                                k = segList.size();
+                                segIndex.put(seg, k);
+                                segList.add(seg);
+                            }
+                            if (!nodeIds.subList(nodeOffs[i * nj + j], nodeIds.size()).contains(k))
+                                nodeIds.add(k);
                         }
+                }
+            nodeOffs[ni * nj] = nodeIds.size();
+            /* surfaces on the device when every segment of the mesh has a deterministic outcome for this material (sfgpu.h: all or none per mesh) */
+            int[] kinds = new int[segList.size()];
+            boolean onDevice = !segList.isEmpty();
+            for (int k = 0; k < kinds.length && onDevice; k++) {
+                kinds[k] = surfaceOutcome(segList.get(k));
+                onDevice = kinds[k] >= 0;
+            }
+            if (!segList.isEmpty() && !onDevice)
+                needsSlowPath = true;
             double[] nodeVol = new double[ni * nj];
             double[][] nv = Starfish.getFieldCollection("NodeVol").getField(mesh).getData();
             for (int i = 0; i < ni; i++)
@@ -128,6 +206,23 @@ public class GpuKineticMaterial extends KineticMaterial {
             check(id, "mesh_add");
             if (id != m)
                 Log.error("sfgpu mesh ids must follow Starfish.getMeshList()");
+            if (onDevice) {
+                int ns = segList.size();
+                double[][] xy = new double[4][ns];
+                int[] sink = new int[ns], ids = new int[nodeIds.size()];
+                for (int k = 0; k < ns; k++) {
+                    double[] p1 = segList.get(k).firstPoint(), p2 = segList.get(k).lastPoint();
+                    xy[0][k] = p1[0]; xy[1][k] = p1[1]; xy[2][k] = p2[0]; xy[3][k] = p2[1];
+                    sink[k] = segList.get(k).getBoundaryType() == BoundaryType.SINK ? 1 : 0;
+                }
+                for (int k = 0; k < ids.length; k++)
+                    ids[k] = nodeIds.get(k);
+                check(SfgpuJni.meshSetSegments(ctx, m, ns, xy, kinds, sink, nodeOffs, ids), "mesh_set_segments");
+                devSeg[m] = segList.toArray(new Segment[0]);
+                devKind[m] = kinds;
+                deviceSurfaces = true;
+                Log.log("> mesh " + mesh.getName() + ": " + ns + " surface segments handled on the GPU");
+            }
             efi[m] = plane(ni * nj); efj[m] = plane(ni * nj); bfi[m] = plane(ni * nj); bfj[m] = plane(ni * nj);
             nd[m] = plane(ni * nj); u[m] = plane(ni * nj); v[m] = plane(ni * nj); w[m] = plane(ni * nj);
             for (int f = 0; f < SfgpuJni.NFIELDS; f++)
@@ -212,6 +307,8 @@ public class GpuKineticMaterial extends KineticMaterial {
             finishSlowPath(dt);
             check(SfgpuJni.finishStep(ctx, sp), "finish_step");
         }
+        if (deviceSurfaces)
+            applySurfaceHits();
         double[] s5 = new double[5];
         long[] counts = new long[3];
         check(SfgpuJni.getSums(ctx, sp, s5, counts), "get_sums");
@@ -240,6 +337,32 @@ public class GpuKineticMaterial extends KineticMaterial {
         updateBoundaries(); /* Material.java:650-657 */
         gpu_first_time = false;
         first_time = false;
+    }
+
+    /** what ProcessBoundary does with a surface hit besides moving the particle (KM:586-602), for the hits the device processed in this step */
+    private void applySurfaceHits() {
+        long[] out2 = new long[2];
+        check(SfgpuJni.takeSurfaceHits(ctx, sp, 0, null, null, null, null, out2), "take_surface_hits");
+        int n = (int) out2[0];
+        if (n == 0)
+            return;
+        int[] hm = new int[n], hs = new int[n];
+        double[][] h = new double[5][n]; /* t, u, v, w, mpw */
+        byte[] alive = new byte[n];
+        long got = SfgpuJni.takeSurfaceHits(ctx, sp, n, hm, hs, h, alive, out2);
+        check(got, "take_surface_hits");
+        double[] vel = new double[3];
+        for (int k = 0; k < got; k++) {
+            Segment seg = devSeg[hm[k]][hs[k]];
+            Boundary boundary = seg.getBoundary();
+            double boundary_t = seg.id() + h[0][k]; /* KM:583 */
+            vel[0] = h[1][k]; vel[1] = h[2][k]; vel[2] = h[3][k];
+            if (devKind[hm[k]][hs[k]] == SfgpuJni.SURFACE_REMOVE)
+                Starfish.source_module.boundary_charge += h[4][k] * charge; /* KM:589-591: only what performSurfaceInteraction removed, not the SINK */
+            addSurfaceMomentum(boundary, boundary_t, vel, h[4][k]); /* KM:596 */
+            if (alive[k] == 0)
+                addSurfaceMassDeposit(boundary, boundary_t, h[4][k]); /* KM:598-602 */
+        }
     }
 
     /** the unchanged Java surface handling for the particles the device handed back in their pre-ProcessBoundary state */

@@ -78,4 +78,18 @@ final class SfgpuJni {
     static native int restartLoad(long ctx, int sp, int mesh, byte[] buf, double dtStep, long[] out2);
 
     static native int sort(long ctx, int sp);
+
+    /* per-segment outcome of a surface hit, include/sfgpu.h SFGPU_SURFACE_* */
+    static final int SURFACE_REMOVE = 0, SURFACE_NONE = 1, SURFACE_SPECULAR = 2;
+
+    /** sfgpu_mesh_set_segments: xy = {x1, y1, x2, y2}; kind = SURFACE_*; sink != 0 for SINK boundaries; CSR of node.segments over nodes i*nj + j.  nSeg = 0 clears. */
+    static native int meshSetSegments(long ctx, int mesh, int nSeg, double[][] xy, int[] kind, int[] sink, int[] nodeOffs, int[] nodeIds);
+
+    /** sfgpu_take_surface_hits: tuvwm = {t, u, v, w, mpw}; out2 = {hits of the step, particles removed}; returns the number copied (max = 0: counts only) */
+    static native long takeSurfaceHits(long ctx, int sp, int max, int[] mesh, int[] seg, double[][] tuvwm, byte[] alive, long[] out2);
+
+    static native int setSortInterval(long ctx, int steps);
+
+    /** sfgpu_set_tile_halo: 0 automatic, 1 / 2 fixed */
+    static native int setTileHalo(long ctx, int halo);
 }

@@ -234,3 +234,63 @@ JNIEXPORT jint JNICALL FN(restartLoad)(JNIEnv *e, jclass c, jlong ctx, jint sp, 
 }
 
 JNIEXPORT jint JNICALL FN(sort)(JNIEnv *e, jclass c, jlong ctx, jint sp) { return sfgpu_sort(CTX(ctx), sp); }
+
+/* sfgpu_mesh_set_segments: xy = {x1, y1, x2, y2} (one double[] each), kind / sink per segment, CSR of node.segments over nodes i*nj + j */
+JNIEXPORT jint JNICALL FN(meshSetSegments)(JNIEnv *e, jclass c, jlong ctx, jint mesh, jint nSeg, jobjectArray xy, jintArray kind, jintArray sink,
+                                           jintArray nodeOffs, jintArray nodeIds)
+{
+    if (nSeg == 0) return sfgpu_mesh_set_segments(CTX(ctx), mesh, 0, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+    jdoubleArray a[4];
+    jdouble *p[4];
+    for (int k = 0; k < 4; k++) {
+        a[k] = (jdoubleArray)(*e)->GetObjectArrayElement(e, xy, k);
+        p[k] = (*e)->GetDoubleArrayElements(e, a[k], NULL);
+    }
+    jint *kd = (*e)->GetIntArrayElements(e, kind, NULL);
+    jint *sk = sink ? (*e)->GetIntArrayElements(e, sink, NULL) : NULL;
+    jint *no = (*e)->GetIntArrayElements(e, nodeOffs, NULL);
+    jint *nd = nodeIds ? (*e)->GetIntArrayElements(e, nodeIds, NULL) : NULL;
+    int rc = sfgpu_mesh_set_segments(CTX(ctx), mesh, nSeg, p[0], p[1], p[2], p[3], (const int32_t *)kd, (const int32_t *)sk, (const int32_t *)no, (const int32_t *)nd);
+    for (int k = 0; k < 4; k++) (*e)->ReleaseDoubleArrayElements(e, a[k], p[k], JNI_ABORT);
+    (*e)->ReleaseIntArrayElements(e, kind, kd, JNI_ABORT);
+    if (sk) (*e)->ReleaseIntArrayElements(e, sink, sk, JNI_ABORT);
+    (*e)->ReleaseIntArrayElements(e, nodeOffs, no, JNI_ABORT);
+    if (nd) (*e)->ReleaseIntArrayElements(e, nodeIds, nd, JNI_ABORT);
+    return rc;
+}
+
+/* sfgpu_take_surface_hits: tuvwm = {t, u, v, w, mpw}; out2 = {hits of the step, particles the surfaces removed}; returns the number copied */
+JNIEXPORT jlong JNICALL FN(takeSurfaceHits)(JNIEnv *e, jclass c, jlong ctx, jint sp, jint max, jintArray mesh, jintArray seg, jobjectArray tuvwm,
+                                            jbyteArray alive, jlongArray out2)
+{
+    int64_t n = 0, n_abs = 0;
+    int rc;
+    if (max <= 0 || !tuvwm) {
+        rc = sfgpu_take_surface_hits(CTX(ctx), sp, 0, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, &n, &n_abs);
+    } else {
+        jdoubleArray a[5];
+        jdouble *p[5];
+        for (int k = 0; k < 5; k++) {
+            a[k] = (jdoubleArray)(*e)->GetObjectArrayElement(e, tuvwm, k);
+            p[k] = (*e)->GetDoubleArrayElements(e, a[k], NULL);
+        }
+        jint *ms = (*e)->GetIntArrayElements(e, mesh, NULL);
+        jint *sg = (*e)->GetIntArrayElements(e, seg, NULL);
+        jbyte *al = (*e)->GetByteArrayElements(e, alive, NULL);
+        rc = sfgpu_take_surface_hits(CTX(ctx), sp, max, (int32_t *)ms, (int32_t *)sg, p[0], p[1], p[2], p[3], p[4], (int8_t *)al, &n, &n_abs);
+        for (int k = 0; k < 5; k++) (*e)->ReleaseDoubleArrayElements(e, a[k], p[k], 0);
+        (*e)->ReleaseIntArrayElements(e, mesh, ms, 0);
+        (*e)->ReleaseIntArrayElements(e, seg, sg, 0);
+        (*e)->ReleaseByteArrayElements(e, alive, al, 0);
+    }
+    if (out2) {
+        jlong v[2] = {n, n_abs};
+        (*e)->SetLongArrayRegion(e, out2, 0, 2, v);
+    }
+    if (rc != SFGPU_OK) return rc;
+    return n < max ? n : max;
+}
+
+JNIEXPORT jint JNICALL FN(setSortInterval)(JNIEnv *e, jclass c, jlong ctx, jint steps) { return sfgpu_set_sort_interval(CTX(ctx), steps); }
+
+JNIEXPORT jint JNICALL FN(setTileHalo)(JNIEnv *e, jclass c, jlong ctx, jint halo) { return sfgpu_set_tile_halo(CTX(ctx), halo); }
